@@ -1,0 +1,122 @@
+/*
+ * voc_b200.h -- C ABI of the B200-native Qwen3-TTS 12 Hz codec vocoder backend.
+ *
+ * This is the drop-in boundary for ONE path of MasterVVK/qwen3-tts-axera-russian: the model
+ * call and chunk loop of dual_npu/vocoder_server.py.  Conventions follow the reference's own
+ * FFI precedent (dual_npu/llama_wrapper.c:1-6 and dual_npu/llama_cpp_bindings.py:41-81):
+ * scalar / pointer arguments only, no structs by value, opaque handles, caller-allocated
+ * outputs, `int` status (0 = ok, negative = error), create/destroy pairs, loadable with
+ * ctypes.CDLL.  No torch types appear in any signature.
+ *
+ * All "host" entry points take ordinary (pageable or pinned) host pointers and perform the
+ * H2D / D2H copies themselves; the "_dev" twins take device pointers on the handle's device
+ * and a cudaStream_t passed as void* (NULL = the handle's own stream) and do not synchronise.
+ *
+ * There is no CPU fallback: every entry point that computes fails with VOC_E_CUDA when no
+ * sm_100 device is usable.
+ */
+#ifndef VOC_B200_H
+#define VOC_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VOC_OK          0
+#define VOC_E_INVALID  (-1)  /* bad argument, or a code outside [0, codebook_size): ORT's Gather
+                                would throw there (SURVEY 8b "Errors")                          */
+#define VOC_E_CUDA     (-2)  /* CUDA runtime / driver failure, or no sm_100 device              */
+#define VOC_E_STATE    (-3)  /* wrong call order: tensor missing, not finalized ...             */
+#define VOC_E_NOMEM    (-4)
+
+/* ABI version of this header (bumped on any signature change). */
+int voc_abi_version(void);
+
+/* ---- lifetime ------------------------------------------------------------------------
+ * Replaces: ort.InferenceSession(model_path, ...)       dual_npu/vocoder_server.py:39-44
+ *   cfg_json  : architecture JSON (VocoderConfig.to_json()); NULL or "" = default architecture
+ *   device    : CUDA device ordinal
+ *   wave      : how many 64-frame windows are resident in HBM at once (activations for
+ *               `wave` windows are pre-allocated; larger batches are processed in waves)
+ * Returns NULL on failure (message on stderr, like the reference's wrappers).            */
+void* voc_create(const char* cfg_json, int device, int wave);
+void  voc_destroy(void* h);
+
+/* Upload one FP32 tensor in torch layout (names and shapes: weights.py:weight_shapes).
+ * Replaces the weights baked into vocoder_traced_64.onnx
+ * (scripts/export_vocoder_traced.py:74-99).                                               */
+int voc_set_tensor(void* h, const char* name, const float* data, long long n_elem);
+/* Build the kernel-ready weight layouts.  Must be called once after all voc_set_tensor.   */
+int voc_finalize(void* h);
+
+/* ---- shape queries -------------------------------------------------------------------
+ * voc_max_tokens    replaces  sess.get_inputs()[0].shape[1]   vocoder_server.py:45-46
+ * voc_chunk_samples = L, the float samples the graph emits per window
+ * voc_out_samples   = len(VocoderServer.synthesize(codes[n])) incl. the short-last-window
+ *                     duplication quirk                        vocoder_server.py:73-121     */
+int       voc_max_tokens(void* h);
+long long voc_chunk_samples(void* h);
+long long voc_out_samples(void* h, int n_tokens);
+int       voc_num_windows(void* h, int n_tokens);
+
+/* ---- level 1: the chunk interface ----------------------------------------------------
+ * Replaces: sess.run(None, {'audio_codes': padded})[0]        vocoder_server.py:67-71
+ *   codes : int64 [B][max_tokens][16], C-contiguous   (graph input `audio_codes`,
+ *           scripts/export_vocoder_traced.py:95)
+ *   out   : float32 [B][voc_chunk_samples()]          (graph output `audio_values`)       */
+int voc_infer_chunks(void* h, const long long* codes, int B, float* out);
+int voc_infer_chunks_dev(void* h, const long long* d_codes, int B, float* d_out, void* stream);
+
+/* ---- level 2: whole request, all windows in batched launches -------------------------
+ * Replaces: VocoderServer.synthesize(codes_array)             vocoder_server.py:73-121
+ *           + np.clip(audio*32767,...).astype(int16)          vocoder_server.py:175
+ *   codes : int64 [n_tokens][16]
+ *   out   : caller-allocated, capacity `cap` elements; *n_out receives the element count
+ * Results equal level 1 + the reference's Python stitching bit for bit.                   */
+int voc_synthesize_f32(void* h, const long long* codes, int n_tokens, float* out,
+                       long long cap, long long* n_out);
+int voc_synthesize_pcm16(void* h, const long long* codes, int n_tokens, short* out,
+                         long long cap, long long* n_out);
+/* Device twin.  Either of d_out_f32 / d_out_i16 may be NULL.                              */
+int voc_synthesize_dev(void* h, const long long* d_codes, int n_tokens, float* d_out_f32,
+                       short* d_out_i16, long long cap, long long* n_out, void* stream);
+
+/* The _dev twins do not synchronise, so an out-of-range code cannot be reported by their
+ * return value.  voc_check_dev synchronises `stream` and returns VOC_E_INVALID if any launch
+ * since the last check met a code outside [0, codebook_size) (and clears the flag).        */
+int voc_check_dev(void* h, void* stream);
+
+/* ---- multi-GPU: a contiguous range of windows of one long request --------
+ * Computes windows [w0, w1) of the n_tokens request (plus window w0-1 when the overlap with
+ * it must be blended) and writes the output samples those windows own:
+ *   out[0 .. *n_out) == synthesize(codes)[*out_offset .. *out_offset + *n_out)
+ * Ranges of consecutive ranks tile the full output exactly; no inter-GPU traffic needed.  */
+int voc_synthesize_range_dev(void* h, const long long* d_codes, int n_tokens, int w0, int w1,
+                             float* d_out_f32, short* d_out_i16, long long cap,
+                             long long* out_offset, long long* n_out, void* stream);
+
+/* ---- host-side planning, usable without a GPU or a handle ---------------------------
+ * voc_plan restates the window loop of synthesize() (vocoder_server.py:83-119) for a model
+ * that emits `chunk_samples` per `max_tokens`-frame window.  meta (may be NULL) receives
+ * 6 ints per window: {dst, a_len, blended, next_blended, prev_a_len, start_frame}.
+ * Returns the number of windows (or a negative error); *total = output samples;
+ * *pairwise = 1 when every crossfade reads un-blended samples of the previous window.
+ * voc_fade_tables fills np.linspace(1,0,ov,dtype=f32) and 1-fade_out (:108-109).          */
+int voc_plan(int max_tokens, long long chunk_samples, int n_tokens, int meta_cap, int* meta,
+             long long* total, int* pairwise);
+int voc_fade_tables(int ov, float* fade_out, float* fade_in);
+
+/* ---- diagnostics ---------------------------------------------------------------------*/
+const char* voc_last_error(void* h);       /* NULL handle: error of the last failed voc_create */
+long long   voc_kernel_launches(void* h);  /* kernels launched by this handle so far            */
+/* Options: "gemm" = "auto" | "simt" | "tc"   (kernel family for the dense layers)          */
+int         voc_set_option(void* h, const char* key, const char* value);
+/* Intermediate activations for parity tests: copies stage `name` ("rvq","pre_conv","xf",
+ * "up0","up1","conv_in_s","dec0".."dec3") of the last wave into `out` (channels-last
+ * [windows][time][channels]); returns the element count or a negative error.               */
+long long   voc_debug_stage(void* h, const char* name, float* out, long long cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOC_B200_H */

@@ -1,0 +1,580 @@
+// CUDA-core (FP32) kernels of the vocoder path: the generic tap-GEMM used for bring-up, small
+// shapes and as the on-device cross-check of the tcgen05 path, plus every HBM-bound /
+// latency-bound stage that is not a dense contraction (RVQ gather-sum, norms, attention at
+// T<=256, depth-wise conv + LayerNorm, output head, overlap-crossfade stitch, PCM16).
+//
+// Reference behaviour each kernel restates is cited at the kernel.
+#include "voc_common.cuh"
+
+// =====================================================================================
+// tap GEMM, FP32 FFMA, 256 threads, BMxBN tile, BK = 16, register double buffering
+// =====================================================================================
+namespace {
+
+constexpr int BK = 16;
+
+template <int VN> struct VecT;
+template <> struct VecT<4> { using T = float4; };
+template <> struct VecT<2> { using T = float2; };
+
+template <int VN> __device__ __forceinline__ void vload(float* dst, const float* src) {
+    if constexpr (VN == 4) { float4 v = *reinterpret_cast<const float4*>(src); dst[0]=v.x; dst[1]=v.y; dst[2]=v.z; dst[3]=v.w; }
+    else                   { float2 v = *reinterpret_cast<const float2*>(src); dst[0]=v.x; dst[1]=v.y; }
+}
+template <int VN> __device__ __forceinline__ void vstore(float* dst, const float* src) {
+    if constexpr (VN == 4) *reinterpret_cast<float4*>(dst) = make_float4(src[0], src[1], src[2], src[3]);
+    else                   *reinterpret_cast<float2*>(dst) = make_float2(src[0], src[1]);
+}
+
+template <int BM, int BN, int VN, int CN>
+__global__ void __launch_bounds__(256)
+tapgemm_simt_kernel(const __grid_constant__ TapGemmParams p) {
+    static_assert(BN == 16 * VN * CN, "BN = 16*VN*CN");
+    constexpr int TM = BM / 16;          // rows per thread (8 or 4)
+    constexpr int RM = TM / 4;           // float4 row groups per thread
+    constexpr int TN = VN * CN;          // cols per thread
+    constexpr int AS = BM + 4;           // padded A-tile row (k-major)
+    constexpr int A_LD = (BM * BK / 4) / 256;            // float4 loads of A per thread
+    constexpr int B_F4 = BK * BN / 4;                    // float4 in a W tile
+    constexpr int B_LD = (B_F4 + 255) / 256;
+
+    __shared__ __align__(16) float As[2][BK][AS];
+    __shared__ __align__(16) float Bs[2][BK][BN];
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN, b = blockIdx.z;
+    const float* __restrict__ A = p.A + (long long)b * p.a_bstride;
+    const float* __restrict__ W = p.W;
+    const int kIters = (p.K + BK - 1) / BK;
+    const int nIt = p.ntaps * kIters;
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    float4 ra[A_LD], rb[B_LD];
+
+    auto gload = [&](int it) {
+        const int tap = it / kIters;
+        const int k0 = (it - tap * kIters) * BK;
+        const int roff = p.a_row0 + p.tap_off[tap];
+#pragma unroll
+        for (int i = 0; i < A_LD; ++i) {
+            const int idx = tid + i * 256;
+            const int row = idx >> 2, kq = idx & 3;
+            const int gr = m0 + row + roff;
+            const int gk = k0 + kq * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gr >= 0 && gr < p.a_rows && gk < p.K)
+                v = *reinterpret_cast<const float4*>(A + (long long)gr * p.lda + gk);
+            ra[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < B_LD; ++i) {
+            const int idx = tid + i * 256;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx < B_F4) {
+                const int kk = idx / (BN / 4), nq = idx - kk * (BN / 4);
+                const int gk = k0 + kk, gn = n0 + nq * 4;
+                if (gk < p.K && gn < p.N)
+                    v = *reinterpret_cast<const float4*>(W + ((long long)tap * p.K + gk) * p.N + gn);
+            }
+            rb[i] = v;
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < A_LD; ++i) {
+            const int idx = tid + i * 256;
+            const int row = idx >> 2, kq = idx & 3;
+            As[buf][kq * 4 + 0][row] = ra[i].x;
+            As[buf][kq * 4 + 1][row] = ra[i].y;
+            As[buf][kq * 4 + 2][row] = ra[i].z;
+            As[buf][kq * 4 + 3][row] = ra[i].w;
+        }
+#pragma unroll
+        for (int i = 0; i < B_LD; ++i) {
+            const int idx = tid + i * 256;
+            if (idx < B_F4) {
+                const int kk = idx / (BN / 4), nq = idx - kk * (BN / 4);
+                *reinterpret_cast<float4*>(&Bs[buf][kk][nq * 4]) = rb[i];
+            }
+        }
+    };
+
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    int cur = 0;
+    for (int it = 0; it < nIt; ++it) {
+        if (it + 1 < nIt) gload(it + 1);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float av[TM], bv[TN];
+#pragma unroll
+            for (int r = 0; r < RM; ++r) {
+                const float4 t = *reinterpret_cast<const float4*>(&As[cur][k][r * (BM / RM) + ty * 4]);
+                av[r * 4 + 0] = t.x; av[r * 4 + 1] = t.y; av[r * 4 + 2] = t.z; av[r * 4 + 3] = t.w;
+            }
+#pragma unroll
+            for (int c = 0; c < CN; ++c) vload<VN>(&bv[c * VN], &Bs[cur][k][c * 16 * VN + tx * VN]);
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (it + 1 < nIt) sstore(cur ^ 1);
+        __syncthreads();
+        cur ^= 1;
+    }
+
+    // ---- epilogue ----
+#pragma unroll
+    for (int c = 0; c < CN; ++c) {
+        const int n = n0 + c * 16 * VN + tx * VN;
+        if (n >= p.N) continue;
+        float bias[VN], scl[VN], sa[VN], sb[VN];
+#pragma unroll
+        for (int v = 0; v < VN; ++v) { bias[v] = 0.f; scl[v] = 1.f; sa[v] = 1.f; sb[v] = 1.f; }
+        if (p.bias) vload<VN>(bias, p.bias + n);
+        if (p.scale) vload<VN>(scl, p.scale + n);
+        if (p.S) { vload<VN>(sa, p.sn_a + n); vload<VN>(sb, p.sn_invb + n); }
+#pragma unroll
+        for (int r = 0; r < RM; ++r)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int m = m0 + r * (BM / RM) + ty * 4 + u;
+                if (m >= p.M) continue;
+                float v[VN];
+#pragma unroll
+                for (int q = 0; q < VN; ++q) {
+                    float x = acc[r * 4 + u][c * VN + q] + bias[q];
+                    if (p.act == VOC_ACT_GELU) x = voc_gelu(x);
+                    v[q] = x * scl[q];
+                }
+                if (p.R) {
+                    float rr[VN];
+                    vload<VN>(rr, p.R + (long long)b * p.r_bstride + (long long)m * p.ldr + n);
+#pragma unroll
+                    for (int q = 0; q < VN; ++q) v[q] += rr[q];
+                }
+                if (p.Y) vstore<VN>(p.Y + (long long)b * p.y_bstride + (long long)m * p.ldy + n, v);
+                if (p.S) {
+                    float s[VN];
+#pragma unroll
+                    for (int q = 0; q < VN; ++q) s[q] = voc_snake(v[q], sa[q], sb[q]);
+                    vstore<VN>(p.S + (long long)b * p.s_bstride + (long long)m * p.lds + n, s);
+                }
+            }
+    }
+}
+
+template <int BM, int BN, int VN, int CN>
+cudaError_t launch_cfg(const TapGemmParams& p, cudaStream_t st) {
+    dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN, p.B);
+    tapgemm_simt_kernel<BM, BN, VN, CN><<<grid, 256, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t voc_launch_tapgemm_simt(const TapGemmParams& p, cudaStream_t st) {
+    if (p.K % 4 || p.N % 4 || p.lda % 4 || p.ntaps < 1 || p.ntaps > VOC_MAX_TAPS) return cudaErrorInvalidValue;
+    if (p.M <= 0 || p.B <= 0) return cudaSuccess;
+    if (p.N >= 96 && p.N % 96 == 0 && p.N % 128 != 0) return launch_cfg<128, 96, 2, 3>(p, st);
+    if (p.N >= 128) return launch_cfg<128, 128, 4, 2>(p, st);
+    if (p.N > 32)   return launch_cfg<128, 96, 2, 3>(p, st);
+    return launch_cfg<64, 32, 2, 1>(p, st);
+}
+
+// =====================================================================================
+// K1: RVQ codebook gather + sum.  tables = the out-projections folded into
+// the codebooks: tables[q][code][:] = P_{sem|ac} * E_q[code]  (dim floats).
+// Window w, frame t reads codes[w*win_step + t] when that frame exists, else code 0 -- the
+// reference pads with *code index 0*, not silence (dual_npu/vocoder_server.py:78,93).
+// An out-of-range code raises err_flag (ONNX Runtime's Gather would throw).
+// =====================================================================================
+__global__ void rvq_gather_kernel(const long long* __restrict__ codes, int n_frames, int frames_per_win,
+                                  int win_step, int n_q, int codebook_size,
+                                  const float* __restrict__ tables, int dim, float* __restrict__ out,
+                                  int* err_flag) {
+    const int w = blockIdx.y, t = blockIdx.x;
+    const long long src = (long long)w * win_step + t;
+    const bool have = src < n_frames;
+    const long long row_out = (long long)w * frames_per_win + t;
+    for (int d = threadIdx.x * 4; d < dim; d += blockDim.x * 4) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < n_q; ++q) {
+            long long c = have ? codes[src * n_q + q] : 0;
+            if (c < 0 || c >= codebook_size) { if (d == 0) atomicExch(err_flag, 1); c = 0; }
+            const float4 v = *reinterpret_cast<const float4*>(
+                tables + ((long long)q * codebook_size + c) * dim + d);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        *reinterpret_cast<float4*>(out + row_out * dim + d) = acc;
+    }
+}
+
+cudaError_t voc_launch_rvq_gather(const long long* codes, int n_frames, int frames_per_win, int win_step,
+                                  int n_windows, int n_q, int codebook_size, const float* tables,
+                                  int dim, float* out, int* err_flag, cudaStream_t st) {
+    if (dim % 4) return cudaErrorInvalidValue;
+    int threads = dim / 4; if (threads > 256) threads = 256; if (threads < 32) threads = 32;
+    dim3 grid(frames_per_win, n_windows);
+    rvq_gather_kernel<<<grid, threads, 0, st>>>(codes, n_frames, frames_per_win, win_step, n_q,
+                                                codebook_size, tables, dim, out, err_flag);
+    return cudaGetLastError();
+}
+
+// =====================================================================================
+// RMSNorm over channels, one warp per row (sibling :3458-3476)
+// =====================================================================================
+__global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                               float* __restrict__ y, int rows, int C, float eps) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* xr = x + (long long)row * C;
+    float ss = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + c);
+        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float inv = rsqrtf(ss / (float)C + eps);
+    float* yr = y + (long long)row * C;
+    for (int c = lane * 4; c < C; c += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + c);
+        const float4 g = *reinterpret_cast<const float4*>(w + c);
+        *reinterpret_cast<float4*>(yr + c) =
+            make_float4(g.x * (v.x * inv), g.y * (v.y * inv), g.z * (v.z * inv), g.w * (v.w * inv));
+    }
+}
+
+cudaError_t voc_launch_rmsnorm(const float* x, const float* w, float* y, int rows, int C, float eps,
+                               cudaStream_t st) {
+    if (C % 4) return cudaErrorInvalidValue;
+    if (rows <= 0) return cudaSuccess;
+    rmsnorm_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, w, y, rows, C, eps);
+    return cudaGetLastError();
+}
+
+// =====================================================================================
+// ConvNeXt prologue: causal depth-wise conv (k taps) + LayerNorm over channels, one block per
+// (batch, time) row (sibling :3334-3366).  dw_w is stored [k][C].
+// =====================================================================================
+__global__ void dwconv_ln_kernel(const float* __restrict__ x, const float* __restrict__ dw_w,
+                                 const float* __restrict__ dw_b, const float* __restrict__ ln_w,
+                                 const float* __restrict__ ln_b, float* __restrict__ y, int L, int C,
+                                 int ksz, float eps) {
+    extern __shared__ float sh[];          // C floats + 32 reduction slots
+    float* h = sh;
+    float* red = sh + C;
+    const int t = blockIdx.x, b = blockIdx.y;
+    const float* xb = x + (long long)b * L * C;
+    float lsum = 0.f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = dw_b[c];
+        for (int j = 0; j < ksz; ++j) {
+            const int tt = t - (ksz - 1 - j);
+            if (tt >= 0) a = fmaf(dw_w[j * C + c], xb[(long long)tt * C + c], a);
+        }
+        h[c] = a;
+        lsum += a;
+    }
+    auto block_sum = [&](float v) -> float {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        float tot = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+        return tot;
+    };
+    const float mean = block_sum(lsum) / (float)C;
+    float lvar = 0.f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) { const float d = h[c] - mean; lvar += d * d; }
+    const float var = block_sum(lvar) / (float)C;
+    const float inv = rsqrtf(var + eps);
+    float* yr = y + ((long long)b * L + t) * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) yr[c] = (h[c] - mean) * inv * ln_w[c] + ln_b[c];
+}
+
+cudaError_t voc_launch_dwconv_ln(const float* x, const float* dw_w, const float* dw_b, const float* ln_w,
+                                 const float* ln_b, float* y, int B, int L, int C, int ksz, float eps,
+                                 cudaStream_t st) {
+    if (B <= 0 || L <= 0) return cudaSuccess;
+    dim3 grid(L, B);
+    dwconv_ln_kernel<<<grid, 256, (C + 32) * sizeof(float), st>>>(x, dw_w, dw_b, ln_w, ln_b, y, L, C, ksz, eps);
+    return cudaGetLastError();
+}
+
+// =====================================================================================
+// Causal sliding-window attention with RoPE, one thread per query row, per-key online
+// softmax (sibling :3370-3439).  qkv is [B*T][3*heads*HD] (q | k | v).
+// rope_cos / rope_sin are [T][HD/2] tables built on the host in float64.
+// The path's T is 64 (or 256 for the reference's other export); FLOP share 0.03 %.
+// =====================================================================================
+template <int HD>
+__global__ void __launch_bounds__(64)
+attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int T, int heads,
+                 const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, int window) {
+    constexpr int H2 = HD / 2;
+    __shared__ float Ks[64][HD + 1];
+    __shared__ float Vs[64][HD + 1];
+    const int b = blockIdx.z, hh = blockIdx.y, q0 = blockIdx.x * 64;
+    const int tid = threadIdx.x;
+    const int A = heads * HD;
+    const int ld = 3 * A;
+    const float* base = qkv + (long long)b * T * ld;
+    const int qi = q0 + tid;
+    const bool qvalid = qi < T;
+    float q[HD], o[HD];
+    if (qvalid) {
+        const float* qr = base + (long long)qi * ld + hh * HD;
+#pragma unroll
+        for (int d = 0; d < H2; ++d) {
+            const float c = rope_cos[qi * H2 + d], s = rope_sin[qi * H2 + d];
+            const float x1 = qr[d], x2 = qr[d + H2];
+            q[d] = x1 * c - x2 * s;
+            q[d + H2] = x2 * c + x1 * s;
+        }
+    } else {
+#pragma unroll
+        for (int d = 0; d < HD; ++d) q[d] = 0.f;
+    }
+#pragma unroll
+    for (int d = 0; d < HD; ++d) o[d] = 0.f;
+    float mx = -INFINITY, l = 0.f;
+    const float scaling = rsqrtf((float)HD);
+    int kstart = q0 - window + 1; if (kstart < 0) kstart = 0;
+    kstart = (kstart / 64) * 64;
+    const int kend = min(T, q0 + 64);
+    for (int k0 = kstart; k0 < kend; k0 += 64) {
+        __syncthreads();
+        for (int idx = tid; idx < 64 * H2; idx += 64) {
+            const int j = idx / H2, d = idx - j * H2;
+            const int kj = k0 + j;
+            float k1 = 0.f, k2 = 0.f, v1 = 0.f, v2 = 0.f, c = 1.f, s = 0.f;
+            if (kj < T) {
+                const float* kr = base + (long long)kj * ld + A + hh * HD;
+                const float* vr = base + (long long)kj * ld + 2 * A + hh * HD;
+                k1 = kr[d]; k2 = kr[d + H2]; v1 = vr[d]; v2 = vr[d + H2];
+                c = rope_cos[kj * H2 + d]; s = rope_sin[kj * H2 + d];
+            }
+            Ks[j][d] = k1 * c - k2 * s;
+            Ks[j][d + H2] = k2 * c + k1 * s;
+            Vs[j][d] = v1;
+            Vs[j][d + H2] = v2;
+        }
+        __syncthreads();
+        if (!qvalid) continue;
+        const int jmax = min(64, kend - k0);
+        for (int j = 0; j < jmax; ++j) {
+            const int kj = k0 + j;
+            if (kj > qi || kj <= qi - window) continue;
+            float s = 0.f;
+#pragma unroll
+            for (int d = 0; d < HD; ++d) s = fmaf(q[d], Ks[j][d], s);
+            s *= scaling;
+            if (s > mx) {
+                const float corr = expf(mx - s);        // exp(-inf) = 0 on first key
+                l *= corr;
+#pragma unroll
+                for (int d = 0; d < HD; ++d) o[d] *= corr;
+                mx = s;
+            }
+            const float pexp = expf(s - mx);
+            l += pexp;
+#pragma unroll
+            for (int d = 0; d < HD; ++d) o[d] = fmaf(pexp, Vs[j][d], o[d]);
+        }
+    }
+    if (qvalid) {
+        const float inv = 1.f / l;
+        float* orow = out + ((long long)b * T + qi) * A + hh * HD;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) orow[d] = o[d] * inv;
+    }
+}
+
+cudaError_t voc_launch_attention(const float* qkv, float* out, int B, int T, int heads, int head_dim,
+                                 const float* rope_cos, const float* rope_sin, int window,
+                                 cudaStream_t st) {
+    if (B <= 0) return cudaSuccess;
+    dim3 grid((T + 63) / 64, heads, B);
+    switch (head_dim) {
+        case 64: attention_kernel<64><<<grid, 64, 0, st>>>(qkv, out, T, heads, rope_cos, rope_sin, window); break;
+        case 32: attention_kernel<32><<<grid, 64, 0, st>>>(qkv, out, T, heads, rope_cos, rope_sin, window); break;
+        case 16: attention_kernel<16><<<grid, 64, 0, st>>>(qkv, out, T, heads, rope_cos, rope_sin, window); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+// SwiGLU gate: out[r][i] = silu(gu[r][i]) * gu[r][inter+i]     (sibling :3442-3455)
+__global__ void swiglu_kernel(const float* __restrict__ gu, float* __restrict__ out, long long total,
+                              int inter) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long r = i / inter;
+    const int c = (int)(i - r * inter);
+    const float g = gu[r * 2 * inter + c], u = gu[r * 2 * inter + inter + c];
+    out[i] = (g / (1.f + expf(-g))) * u;
+}
+
+cudaError_t voc_launch_swiglu(const float* gu, float* out, long long rows, int inter, cudaStream_t st) {
+    const long long total = rows * inter;
+    if (total <= 0) return cudaSuccess;
+    swiglu_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(gu, out, total, inter);
+    return cudaGetLastError();
+}
+
+// =====================================================================================
+// K7: output head -- causal Conv1d(C -> 1, k) on the Snake-activated signal + clamp(-1, 1)
+// (sibling :3757-3761,3778).  HBM-bound: C*4 bytes read per output sample.
+// A (64 + k - 1) x C tile is staged in shared memory with coalesced loads, then four threads
+// share one output sample (C/4 channels each) and reduce by shuffle.
+// =====================================================================================
+__global__ void __launch_bounds__(256)
+head_kernel(const float* __restrict__ S, long long s_bstride, int L, int C, int ksz,
+            const float* __restrict__ w /*[k][C]*/, float bias, float* __restrict__ out,
+            long long o_bstride) {
+    extern __shared__ float sh[];
+    const int TT = 64;
+    const int CP = C + 1;
+    float* tile = sh;                       // (TT + ksz - 1) x CP
+    float* ws = sh + (TT + ksz - 1) * CP;   // ksz x C
+    const int b = blockIdx.y, t0 = blockIdx.x * TT;
+    const float* Sb = S + (long long)b * s_bstride;
+    const int rows = TT + ksz - 1;
+    for (int idx = threadIdx.x; idx < rows * C; idx += blockDim.x) {
+        const int r = idx / C, c = idx - r * C;
+        const int t = t0 - (ksz - 1) + r;
+        tile[r * CP + c] = (t >= 0 && t < L) ? Sb[(long long)t * C + c] : 0.f;
+    }
+    for (int idx = threadIdx.x; idx < ksz * C; idx += blockDim.x) ws[idx] = w[idx];
+    __syncthreads();
+    const int o = threadIdx.x >> 2, part = threadIdx.x & 3;
+    const int cq = C / 4;
+    float acc = 0.f;
+    for (int j = 0; j < ksz; ++j) {
+        const float* tr = tile + (o + j) * CP + part * cq;
+        const float* wr = ws + j * C + part * cq;
+        for (int c = 0; c < cq; ++c) acc = fmaf(wr[c], tr[c], acc);
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    const int t = t0 + o;
+    if (part == 0 && t < L) out[(long long)b * o_bstride + t] = fminf(1.f, fmaxf(-1.f, acc + bias));
+}
+
+cudaError_t voc_launch_head(const float* S, long long s_bstride, int L, int C, int ksz, const float* w,
+                            float bias, float* out, long long o_bstride, int B, cudaStream_t st) {
+    if (C % 4) return cudaErrorInvalidValue;
+    if (B <= 0 || L <= 0) return cudaSuccess;
+    const size_t smem = ((size_t)(64 + ksz - 1) * (C + 1) + (size_t)ksz * C) * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    dim3 grid((L + 63) / 64, B);
+    head_kernel<<<grid, 256, smem, st>>>(S, s_bstride, L, C, ksz, w, bias, out, o_bstride);
+    return cudaGetLastError();
+}
+
+// =====================================================================================
+// K8: overlap-crossfade stitch + optional PCM16  (dual_npu/vocoder_server.py:101-117,175).
+// Every overlap involves exactly two windows when each non-final window emits >= 2*ov
+// samples (the planner checks this), so all windows are stitched in one launch.
+//   win_meta[w] = {dst, a_len, blended, next_blended, prev_a_len, _}
+// numpy evaluates  result*fade_out  and  chunk*fade_in  as two rounded float32 products
+// followed by a rounded add -- no FMA contraction here, hence the explicit _rn intrinsics.
+// PCM16: float32 multiply by 32767, clip, truncate toward zero (:175).
+// =====================================================================================
+__device__ __forceinline__ short voc_pcm16(float v) {
+    float s = __fmul_rn(v, 32767.0f);
+    s = fminf(32767.0f, fmaxf(-32768.0f, s));
+    return (short)(int)s;    // cvt.rzi: truncation, like numpy astype(int16)
+}
+
+__global__ void stitch_kernel(const float* __restrict__ chunks, long long chunk_stride,
+                              const int* __restrict__ win_meta, int ov,
+                              const float* __restrict__ fade_out, const float* __restrict__ fade_in,
+                              float* __restrict__ out_f32, short* __restrict__ out_i16) {
+    const int w = blockIdx.y;
+    const int dst = win_meta[w * 6 + 0], a_len = win_meta[w * 6 + 1];
+    const int blended = win_meta[w * 6 + 2], next_blended = win_meta[w * 6 + 3];
+    const int prev_a = win_meta[w * 6 + 4];
+    const float* cur = chunks + (long long)w * chunk_stride;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a_len; i += gridDim.x * blockDim.x) {
+        float v;
+        if (blended && i < ov) {
+            const float r = chunks[(long long)(w - 1) * chunk_stride + (prev_a - ov + i)];
+            v = __fadd_rn(__fmul_rn(r, fade_out[i]), __fmul_rn(cur[i], fade_in[i]));
+        } else if (next_blended && i >= a_len - ov) {
+            continue;                     // written by window w+1's blend
+        } else {
+            v = cur[i];
+        }
+        if (out_f32) out_f32[(long long)dst + i] = v;
+        if (out_i16) out_i16[(long long)dst + i] = voc_pcm16(v);
+    }
+}
+
+cudaError_t voc_launch_stitch(const float* chunks, long long chunk_stride, const int* win_meta,
+                              int n_windows, int ov, const float* fade_out, const float* fade_in,
+                              float* out_f32, short* out_i16, int max_a_len, cudaStream_t st) {
+    if (n_windows <= 0 || max_a_len <= 0) return cudaSuccess;
+    int gx = (max_a_len + 1023) / 1024; if (gx < 1) gx = 1;
+    dim3 grid(gx, n_windows);
+    stitch_kernel<<<grid, 256, 0, st>>>(chunks, chunk_stride, win_meta, ov, fade_out, fade_in, out_f32, out_i16);
+    return cudaGetLastError();
+}
+
+// General (sequential) form of one loop iteration of synthesize(): used only when the
+// pairwise condition above does not hold.  blend=1: res[res_len-ov .. res_len) is blended in
+// place with chunk[0..ov), chunk[ov..a_len) is appended; blend=0: chunk is appended.
+__global__ void append_window_kernel(float* __restrict__ res, long long res_len,
+                                     const float* __restrict__ chunk, int a_len, int ov, int blend,
+                                     const float* __restrict__ fade_out, const float* __restrict__ fade_in) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a_len; i += gridDim.x * blockDim.x) {
+        if (blend) {
+            if (i < ov) {
+                const long long d = res_len - ov + i;
+                res[d] = __fadd_rn(__fmul_rn(res[d], fade_out[i]), __fmul_rn(chunk[i], fade_in[i]));
+            } else {
+                res[res_len - ov + i] = chunk[i];
+            }
+        } else {
+            res[res_len + i] = chunk[i];
+        }
+    }
+}
+
+cudaError_t voc_launch_append_window(float* res, long long res_len, const float* chunk, int a_len, int ov,
+                                     int blend, const float* fade_out, const float* fade_in,
+                                     cudaStream_t st) {
+    if (a_len <= 0) return cudaSuccess;
+    append_window_kernel<<<(a_len + 1023) / 1024, 256, 0, st>>>(res, res_len, chunk, a_len, ov, blend,
+                                                               fade_out, fade_in);
+    return cudaGetLastError();
+}
+
+__global__ void pcm16_kernel(const float* __restrict__ in, short* __restrict__ out, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        out[i] = voc_pcm16(in[i]);
+}
+
+cudaError_t voc_launch_pcm16(const float* in, short* out, long long n, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    long long blocks = (n + 1023) / 1024; if (blocks > 148 * 16) blocks = 148 * 16;
+    pcm16_kernel<<<(unsigned)blocks, 256, 0, st>>>(in, out, n);
+    return cudaGetLastError();
+}

@@ -1,0 +1,948 @@
+// Engine + C ABI of the B200 vocoder backend (see include/voc_b200.h for the contract and the
+// reference call sites each entry point replaces).
+//
+// Data layout in HBM: every activation is channels-last FP32 [window][time][channel]; weights
+// are re-laid out once at voc_finalize() into the [tap*K + k][n] matrices the tap-GEMM kernels
+// consume; the RVQ out-projections are folded into the codebooks.  Three large ping-pong
+// buffers (X = residual stream, S = Snake-activated operand, T = intermediate operand) hold
+// the decoder blocks of one *wave* of windows; the tiny front end (RVQ .. conv-in) has its own
+// pool.  Nothing is allocated on the request path.
+#include "voc_common.cuh"
+#include "../../include/voc_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace {
+
+// --------------------------------------------------------------------------------------
+// minimal flat-JSON reader (numbers, booleans, strings, arrays of numbers)
+// --------------------------------------------------------------------------------------
+struct JVal { std::vector<double> nums; std::string str; bool is_str = false; };
+static bool parse_flat_json(const char* s, std::map<std::string, JVal>& out, std::string& err) {
+    const char* p = s;
+    auto ws = [&]() { while (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r') ++p; };
+    auto str = [&](std::string& o) -> bool {
+        if (*p != '"') return false;
+        ++p; o.clear();
+        while (*p && *p != '"') { if (*p == '\\' && p[1]) ++p; o.push_back(*p++); }
+        if (*p != '"') return false;
+        ++p; return true;
+    };
+    auto num = [&](double& v) -> bool {
+        char* e = nullptr; v = strtod(p, &e);
+        if (e == p) return false;
+        p = e; return true;
+    };
+    ws(); if (*p != '{') { err = "config JSON must be an object"; return false; }
+    ++p; ws();
+    if (*p == '}') return true;
+    for (;;) {
+        ws(); std::string key;
+        if (!str(key)) { err = "bad key in config JSON"; return false; }
+        ws(); if (*p != ':') { err = "missing ':' in config JSON"; return false; }
+        ++p; ws();
+        JVal v;
+        if (*p == '"') { v.is_str = true; if (!str(v.str)) { err = "bad string"; return false; } }
+        else if (*p == '[') {
+            ++p; ws();
+            while (*p && *p != ']') { double d; if (!num(d)) { err = "bad array"; return false; }
+                v.nums.push_back(d); ws(); if (*p == ',') { ++p; ws(); } }
+            if (*p != ']') { err = "bad array"; return false; }
+            ++p;
+        } else if (!strncmp(p, "true", 4)) { v.nums.push_back(1); p += 4; }
+        else if (!strncmp(p, "false", 5)) { v.nums.push_back(0); p += 5; }
+        else if (!strncmp(p, "null", 4)) { p += 4; }
+        else { double d; if (!num(d)) { err = "bad value for " + key; return false; } v.nums.push_back(d); }
+        out[key] = v;
+        ws();
+        if (*p == ',') { ++p; continue; }
+        if (*p == '}') return true;
+        err = "bad config JSON near key " + key; return false;
+    }
+}
+
+// --------------------------------------------------------------------------------------
+// architecture (mirror of config.py:VocoderConfig)
+// --------------------------------------------------------------------------------------
+struct Cfg {
+    int codebook_size = 2048, codebook_dim = 256, num_quantizers = 16, num_semantic = 1, rvq_dim = 512;
+    int latent_dim = 1024, pre_conv_kernel = 3;
+    int pre_transformer = 1, xf_hidden = 512, xf_inter = 1024, xf_layers = 8, xf_heads = 16, xf_head_dim = 64;
+    double rope_theta = 10000.0, rms_eps = 1e-5;
+    int sliding_window = 72;
+    std::vector<int> upsampling_ratios{2, 2};
+    int convnext = 1, convnext_mult = 4;
+    double ln_eps = 1e-6;
+    int decoder_dim = 1536;
+    std::vector<int> upsample_rates{8, 5, 4, 3};
+    std::vector<int> dilations{1, 3, 9};
+    int conv_kernel = 7;
+    double snake_eps = 1e-9;
+    int trim_both = 1;
+    int chunk_frames = 64, sample_rate = 24000;
+
+    int attn_dim() const { return xf_heads * xf_head_dim; }
+    int samples_per_frame() const { int p = 1; for (int r : upsampling_ratios) p *= r; for (int r : upsample_rates) p *= r; return p; }
+    int tlen(int L, int s) const { return trim_both ? (L - 1) * s : L * s; }
+    int chunk_samples() const {
+        int t = chunk_frames; for (int r : upsampling_ratios) t *= r;
+        for (int s : upsample_rates) t = tlen(t, s);
+        return t;
+    }
+};
+
+static bool cfg_from_json(const char* js, Cfg& c, std::string& err) {
+    if (!js || !*js) return true;
+    std::map<std::string, JVal> m;
+    if (!parse_flat_json(js, m, err)) return false;
+    auto geti = [&](const char* k, int& v) { auto it = m.find(k); if (it != m.end() && !it->second.nums.empty()) v = (int)it->second.nums[0]; };
+    auto getd = [&](const char* k, double& v) { auto it = m.find(k); if (it != m.end() && !it->second.nums.empty()) v = it->second.nums[0]; };
+    auto getv = [&](const char* k, std::vector<int>& v) { auto it = m.find(k); if (it != m.end() && !it->second.is_str) { v.clear(); for (double d : it->second.nums) v.push_back((int)d); } };
+    geti("codebook_size", c.codebook_size); geti("codebook_dim", c.codebook_dim);
+    geti("num_quantizers", c.num_quantizers); geti("num_semantic", c.num_semantic); geti("rvq_dim", c.rvq_dim);
+    geti("latent_dim", c.latent_dim); geti("pre_conv_kernel", c.pre_conv_kernel);
+    geti("pre_transformer", c.pre_transformer); geti("xf_hidden", c.xf_hidden); geti("xf_inter", c.xf_inter);
+    geti("xf_layers", c.xf_layers); geti("xf_heads", c.xf_heads); geti("xf_head_dim", c.xf_head_dim);
+    getd("rope_theta", c.rope_theta); getd("rms_eps", c.rms_eps); geti("sliding_window", c.sliding_window);
+    getv("upsampling_ratios", c.upsampling_ratios); geti("convnext", c.convnext); geti("convnext_mult", c.convnext_mult);
+    getd("ln_eps", c.ln_eps); geti("decoder_dim", c.decoder_dim); getv("upsample_rates", c.upsample_rates);
+    getv("dilations", c.dilations); geti("conv_kernel", c.conv_kernel); getd("snake_eps", c.snake_eps);
+    geti("chunk_frames", c.chunk_frames); geti("sample_rate", c.sample_rate);
+    auto it = m.find("transconv_trim");
+    if (it != m.end() && it->second.is_str) {
+        if (it->second.str == "both") c.trim_both = 1;
+        else if (it->second.str == "right") c.trim_both = 0;
+        else { err = "transconv_trim must be 'both' or 'right'"; return false; }
+    }
+    if (c.num_quantizers != 16) { err = "the chunk interface carries exactly 16 codebooks per frame"; return false; }
+    if (c.conv_kernel > VOC_MAX_TAPS || c.pre_conv_kernel > VOC_MAX_TAPS) { err = "kernel size > 8 taps"; return false; }
+    if (c.xf_head_dim != 64 && c.xf_head_dim != 32 && c.xf_head_dim != 16) { err = "xf_head_dim must be 16/32/64"; return false; }
+    const int dd = c.decoder_dim >> c.upsample_rates.size();
+    if (dd < 4 || (dd % 4) || (c.decoder_dim % (1 << c.upsample_rates.size()))) { err = "decoder_dim too small"; return false; }
+    if (c.codebook_dim % 4 || c.rvq_dim % 4 || c.latent_dim % 4 || c.xf_hidden % 4 || c.xf_inter % 4) { err = "channel counts must be multiples of 4"; return false; }
+    if (c.chunk_frames < 1 || c.chunk_frames > 4096) { err = "bad chunk_frames"; return false; }
+    return true;
+}
+
+// --------------------------------------------------------------------------------------
+struct DevBuf {
+    float* p = nullptr; size_t n = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+
+struct GemmW {                 // one dense layer, kernel-ready
+    float* W = nullptr;        // [ntaps*K][N]
+    float* bias = nullptr;     // [N] or null
+    int K = 0, N = 0, ntaps = 1;
+    int tap_off[VOC_MAX_TAPS] = {0};
+};
+struct SnakeP { float* a = nullptr; float* invb = nullptr; };
+
+static thread_local std::string g_create_error;
+static void fade_tables(int ov, float* fo, float* fi);
+
+struct Engine {
+    Cfg cfg;
+    int device = 0, wave = 1;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    long long launches = 0;
+    bool finalized = false;
+    int gemm_mode = 0;          // 0 auto, 1 simt, 2 tc
+    bool debug = false;
+
+    std::map<std::string, std::vector<float>> raw;   // host staging until finalize
+    std::vector<float*> owned;                        // device allocations (weights)
+
+    // kernel-ready weights
+    float* rvq_tables = nullptr;                      // [16][codebook][rvq_dim]
+    GemmW pre_conv, xf_in, xf_out, conv_in;
+    struct XfLayer { float *ln1, *ln2, *ls_attn, *ls_mlp; GemmW qkv, o, gu, down; };
+    std::vector<XfLayer> xf;
+    float* xf_norm = nullptr; float* rope_cos = nullptr; float* rope_sin = nullptr;
+    struct Up { GemmW convt; float *dw_w, *dw_b, *ln_w, *ln_b, *gamma; GemmW pw1, pw2; };
+    std::vector<Up> ups;
+    struct RU { GemmW c1, c2; SnakeP s1, s2; };
+    struct Block { SnakeP s_in; SnakeP s_ru0_tiled; GemmW convt; std::vector<RU> ru; int cin, cout, stride; };
+    std::vector<Block> blocks;
+    SnakeP head_snake; float* head_w = nullptr; float head_b = 0.f;
+
+    // activations
+    DevBuf front, big[3], chunks, stitch_f32;
+    float *f_rvq, *f_pre, *f_h, *f_hn, *f_qkv, *f_att, *f_gu, *f_act, *f_x, *f_ln, *f_mid, *f_x2;
+    size_t big_elems = 0;
+    int* d_err = nullptr;
+    int* d_meta = nullptr; size_t meta_cap = 0;
+    float* d_fade_out = nullptr; float* d_fade_in = nullptr;
+    long long* d_codes = nullptr; size_t codes_cap = 0;
+    short* d_pcm = nullptr; size_t pcm_cap = 0;
+    std::map<std::string, std::pair<std::shared_ptr<DevBuf>, size_t>> dbg;
+
+    ~Engine() {
+        for (float* p : owned) cudaFree(p);
+        if (d_err) cudaFree(d_err);
+        if (d_meta) cudaFree(d_meta);
+        if (d_fade_out) cudaFree(d_fade_out);
+        if (d_fade_in) cudaFree(d_fade_in);
+        if (d_codes) cudaFree(d_codes);
+        if (d_pcm) cudaFree(d_pcm);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+#define CK(expr)                                                                         \
+    do { cudaError_t _e = (expr);                                                        \
+         if (_e != cudaSuccess) {                                                        \
+             E->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                \
+             fprintf(stderr, "voc_b200: %s\n", E->err.c_str());                          \
+             return VOC_E_CUDA; } } while (0)
+
+static int fail(Engine* E, int code, const std::string& msg) {
+    E->err = msg;
+    fprintf(stderr, "voc_b200: %s\n", msg.c_str());
+    return code;
+}
+
+static float* upload(Engine* E, const std::vector<float>& v) {
+    float* d = nullptr;
+    if (cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(float)) != cudaSuccess) return nullptr;
+    if (!v.empty() && cudaMemcpy(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(d); return nullptr;
+    }
+    E->owned.push_back(d);
+    return d;
+}
+
+static const std::vector<float>* get_raw(Engine* E, const std::string& name, size_t n) {
+    auto it = E->raw.find(name);
+    if (it == E->raw.end()) { E->err = "missing tensor " + name; return nullptr; }
+    if (it->second.size() != n) { E->err = "tensor " + name + " has wrong size"; return nullptr; }
+    return &it->second;
+}
+
+// Conv1d weight [Co][Ci][K] (+ bias [Co]) -> tap GEMM, causal taps with dilation d
+static bool make_conv(Engine* E, const std::string& p, int Co, int Ci, int K, int dil, bool has_bias, GemmW& g) {
+    auto* w = get_raw(E, p + ".w", (size_t)Co * Ci * K); if (!w) return false;
+    std::vector<float> t((size_t)K * Ci * Co);
+    for (int co = 0; co < Co; ++co) for (int ci = 0; ci < Ci; ++ci) for (int j = 0; j < K; ++j)
+        t[((size_t)j * Ci + ci) * Co + co] = (*w)[((size_t)co * Ci + ci) * K + j];
+    g.W = upload(E, t); g.K = Ci; g.N = Co; g.ntaps = K;
+    for (int j = 0; j < K; ++j) g.tap_off[j] = -(K - 1 - j) * dil;
+    if (has_bias) { auto* b = get_raw(E, p + ".b", Co); if (!b) return false; g.bias = upload(E, *b); if (!g.bias) return false; }
+    return g.W != nullptr;
+}
+// Linear [out][in] (several stacked along out) -> ntaps = 1
+static bool make_linear(Engine* E, const std::vector<std::string>& names, int out_each, int in, const char* bias_name, GemmW& g) {
+    const int N = out_each * (int)names.size();
+    std::vector<float> t((size_t)in * N);
+    for (size_t s = 0; s < names.size(); ++s) {
+        auto* w = get_raw(E, names[s], (size_t)out_each * in); if (!w) return false;
+        for (int o = 0; o < out_each; ++o) for (int i = 0; i < in; ++i)
+            t[(size_t)i * N + s * out_each + o] = (*w)[(size_t)o * in + i];
+    }
+    g.W = upload(E, t); g.K = in; g.N = N; g.ntaps = 1; g.tap_off[0] = 0;
+    if (bias_name) { auto* b = get_raw(E, bias_name, N); if (!b) return false; g.bias = upload(E, *b); if (!g.bias) return false; }
+    return g.W != nullptr;
+}
+// ConvTranspose1d [Ci][Co][k], stride s, k = s (1 tap) or k = 2s (2 taps): N = s*Co
+static bool make_convt(Engine* E, const std::string& p, int Ci, int Co, int k, int s, GemmW& g) {
+    auto* w = get_raw(E, p + ".w", (size_t)Ci * Co * k); if (!w) return false;
+    auto* b = get_raw(E, p + ".b", Co); if (!b) return false;
+    const int taps = k / s, N = s * Co;
+    if (taps * s != k || taps < 1 || taps > 2) { E->err = "transposed conv needs k = s or k = 2s"; return false; }
+    std::vector<float> t((size_t)taps * Ci * N);
+    for (int tap = 0; tap < taps; ++tap) for (int ci = 0; ci < Ci; ++ci) for (int ph = 0; ph < s; ++ph) for (int co = 0; co < Co; ++co)
+        t[((size_t)tap * Ci + ci) * N + ph * Co + co] = (*w)[((size_t)ci * Co + co) * k + ph + tap * s];
+    std::vector<float> bt(N);
+    for (int ph = 0; ph < s; ++ph) for (int co = 0; co < Co; ++co) bt[ph * Co + co] = (*b)[co];
+    g.W = upload(E, t); g.bias = upload(E, bt); g.K = Ci; g.N = N; g.ntaps = taps;
+    g.tap_off[0] = 0; g.tap_off[1] = -1;
+    return g.W && g.bias;
+}
+static bool make_snake(Engine* E, const std::string& p, int C, int tile, SnakeP& sp) {
+    auto* al = get_raw(E, p + ".alpha", C); if (!al) return false;
+    auto* be = get_raw(E, p + ".beta", C); if (!be) return false;
+    std::vector<float> a((size_t)C * tile), ib((size_t)C * tile);
+    for (int r = 0; r < tile; ++r) for (int c = 0; c < C; ++c) {
+        a[(size_t)r * C + c] = expf((*al)[c]);
+        ib[(size_t)r * C + c] = 1.0f / (expf((*be)[c]) + (float)E->cfg.snake_eps);
+    }
+    sp.a = upload(E, a); sp.invb = upload(E, ib);
+    return sp.a && sp.invb;
+}
+static float* upload_named(Engine* E, const std::string& name, size_t n) {
+    auto* v = get_raw(E, name, n); if (!v) return nullptr;
+    return upload(E, *v);
+}
+
+static cudaError_t run_gemm(Engine* E, TapGemmParams& p, cudaStream_t st) {
+    E->launches++;
+    return voc_launch_tapgemm_simt(p, st);
+}
+
+static TapGemmParams gp(const GemmW& g, const float* A, long long a_bs, int a_rows, int a_row0, int M, int B) {
+    TapGemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.A = A; p.a_bstride = a_bs; p.a_rows = a_rows; p.lda = g.K; p.K = g.K; p.a_row0 = a_row0;
+    p.ntaps = g.ntaps; for (int i = 0; i < VOC_MAX_TAPS; ++i) p.tap_off[i] = g.tap_off[i];
+    p.W = g.W; p.N = g.N; p.M = M; p.B = B; p.bias = g.bias;
+    return p;
+}
+static void setY(TapGemmParams& p, float* Y) { p.Y = Y; p.ldy = p.N; p.y_bstride = (long long)p.M * p.N; }
+static void setS(TapGemmParams& p, float* S, const SnakeP& sp) { p.S = S; p.lds = p.N; p.s_bstride = (long long)p.M * p.N; p.sn_a = sp.a; p.sn_invb = sp.invb; }
+static void setR(TapGemmParams& p, const float* R) { p.R = R; p.ldr = p.N; p.r_bstride = (long long)p.M * p.N; }
+
+static int dbg_capture(Engine* E, const char* name, const float* src, size_t n, cudaStream_t st) {
+    if (!E->debug) return VOC_OK;
+    auto b = std::make_shared<DevBuf>();
+    CK(cudaMalloc(&b->p, n * sizeof(float))); b->n = n;
+    CK(cudaMemcpyAsync(b->p, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    E->dbg[name] = {b, n};
+    return VOC_OK;
+}
+
+// --------------------------------------------------------------------------------------
+// finalize: build every kernel-ready tensor
+// --------------------------------------------------------------------------------------
+static int engine_finalize(Engine* E) {
+    const Cfg& c = E->cfg;
+    CK(cudaSetDevice(E->device));
+    E->err.clear();
+#define REQ(x) do { if (!(x)) return fail(E, E->err.rfind("missing", 0) == 0 || E->err.rfind("tensor", 0) == 0 ? VOC_E_STATE : VOC_E_CUDA, E->err.empty() ? std::string("finalize failed: " #x) : E->err); } while (0)
+
+    // ---- RVQ: fold the out-projections into the codebooks with the tap-GEMM itself
+    {
+        const size_t tbl = (size_t)c.codebook_size * c.rvq_dim;
+        float* tables = nullptr;
+        CK(cudaMalloc(&tables, tbl * c.num_quantizers * sizeof(float)));
+        E->owned.push_back(tables);
+        GemmW ps, pa;
+        REQ(make_linear(E, {"rvq.proj_sem.w"}, c.rvq_dim, c.codebook_dim, nullptr, ps));
+        REQ(make_linear(E, {"rvq.proj_ac.w"}, c.rvq_dim, c.codebook_dim, nullptr, pa));
+        for (int q = 0; q < c.num_quantizers; ++q) {
+            float* cb = upload_named(E, "rvq.codebook." + std::to_string(q), (size_t)c.codebook_size * c.codebook_dim);
+            REQ(cb);
+            TapGemmParams p = gp(q < c.num_semantic ? ps : pa, cb, 0, c.codebook_size, 0, c.codebook_size, 1);
+            setY(p, tables + q * tbl);
+            CK(run_gemm(E, p, E->stream));
+        }
+        CK(cudaStreamSynchronize(E->stream));
+        E->rvq_tables = tables;
+    }
+    REQ(make_conv(E, "pre_conv", c.latent_dim, c.rvq_dim, c.pre_conv_kernel, 1, true, E->pre_conv));
+    if (c.pre_transformer) {
+        REQ(make_linear(E, {"xf.in_proj.w"}, c.xf_hidden, c.latent_dim, "xf.in_proj.b", E->xf_in));
+        REQ(make_linear(E, {"xf.out_proj.w"}, c.latent_dim, c.xf_hidden, "xf.out_proj.b", E->xf_out));
+        E->xf.resize(c.xf_layers);
+        for (int l = 0; l < c.xf_layers; ++l) {
+            const std::string p = "xf." + std::to_string(l) + ".";
+            auto& L = E->xf[l];
+            REQ(L.ln1 = upload_named(E, p + "ln1.w", c.xf_hidden));
+            REQ(L.ln2 = upload_named(E, p + "ln2.w", c.xf_hidden));
+            REQ(L.ls_attn = upload_named(E, p + "ls_attn", c.xf_hidden));
+            REQ(L.ls_mlp = upload_named(E, p + "ls_mlp", c.xf_hidden));
+            REQ(make_linear(E, {p + "q.w", p + "k.w", p + "v.w"}, c.attn_dim(), c.xf_hidden, nullptr, L.qkv));
+            REQ(make_linear(E, {p + "o.w"}, c.xf_hidden, c.attn_dim(), nullptr, L.o));
+            REQ(make_linear(E, {p + "gate.w", p + "up.w"}, c.xf_inter, c.xf_hidden, nullptr, L.gu));
+            REQ(make_linear(E, {p + "down.w"}, c.xf_hidden, c.xf_inter, nullptr, L.down));
+        }
+        REQ(E->xf_norm = upload_named(E, "xf.norm.w", c.xf_hidden));
+        // rotary table in float64 then cast, like the oracle (vocoder_oracle.py:rotary_cos_sin)
+        const int T = c.chunk_frames, H2 = c.xf_head_dim / 2;
+        std::vector<float> cs((size_t)T * H2), sn((size_t)T * H2);
+        for (int t = 0; t < T; ++t) for (int d = 0; d < H2; ++d) {
+            const double inv = 1.0 / std::pow(c.rope_theta, (2.0 * d) / c.xf_head_dim);
+            cs[(size_t)t * H2 + d] = (float)std::cos(t * inv);
+            sn[(size_t)t * H2 + d] = (float)std::sin(t * inv);
+        }
+        REQ(E->rope_cos = upload(E, cs)); REQ(E->rope_sin = upload(E, sn));
+    }
+    E->ups.resize(c.upsampling_ratios.size());
+    for (size_t u = 0; u < c.upsampling_ratios.size(); ++u) {
+        const std::string p = "up." + std::to_string(u) + ".";
+        auto& U = E->ups[u];
+        const int C = c.latent_dim, r = c.upsampling_ratios[u];
+        REQ(make_convt(E, p + "convt", C, C, r, r, U.convt));
+        if (c.convnext) {
+            auto* dw = get_raw(E, p + "dw.w", (size_t)C * c.conv_kernel); REQ(dw);
+            std::vector<float> t((size_t)c.conv_kernel * C);
+            for (int ch = 0; ch < C; ++ch) for (int j = 0; j < c.conv_kernel; ++j) t[(size_t)j * C + ch] = (*dw)[(size_t)ch * c.conv_kernel + j];
+            REQ(U.dw_w = upload(E, t));
+            REQ(U.dw_b = upload_named(E, p + "dw.b", C));
+            REQ(U.ln_w = upload_named(E, p + "ln.w", C));
+            REQ(U.ln_b = upload_named(E, p + "ln.b", C));
+            REQ(U.gamma = upload_named(E, p + "gamma", C));
+            const std::string b1 = p + "pw1.b", b2 = p + "pw2.b";
+            REQ(make_linear(E, {p + "pw1.w"}, c.convnext_mult * C, C, b1.c_str(), U.pw1));
+            REQ(make_linear(E, {p + "pw2.w"}, C, c.convnext_mult * C, b2.c_str(), U.pw2));
+        }
+    }
+    REQ(make_conv(E, "dec.conv_in", c.decoder_dim, c.latent_dim, c.conv_kernel, 1, true, E->conv_in));
+    E->blocks.resize(c.upsample_rates.size());
+    for (size_t b = 0; b < c.upsample_rates.size(); ++b) {
+        const std::string p = "dec." + std::to_string(b) + ".";
+        auto& Bk = E->blocks[b];
+        Bk.cin = c.decoder_dim >> b; Bk.cout = c.decoder_dim >> (b + 1); Bk.stride = c.upsample_rates[b];
+        REQ(make_snake(E, p + "snake", Bk.cin, 1, Bk.s_in));
+        REQ(make_convt(E, p + "convt", Bk.cin, Bk.cout, 2 * Bk.stride, Bk.stride, Bk.convt));
+        REQ(make_snake(E, p + "ru.0.snake1", Bk.cout, Bk.stride, Bk.s_ru0_tiled));
+        Bk.ru.resize(c.dilations.size());
+        for (size_t j = 0; j < c.dilations.size(); ++j) {
+            const std::string r = p + "ru." + std::to_string(j) + ".";
+            REQ(make_snake(E, r + "snake1", Bk.cout, 1, Bk.ru[j].s1));
+            REQ(make_snake(E, r + "snake2", Bk.cout, 1, Bk.ru[j].s2));
+            REQ(make_conv(E, r + "conv1", Bk.cout, Bk.cout, c.conv_kernel, c.dilations[j], true, Bk.ru[j].c1));
+            REQ(make_conv(E, r + "conv2", Bk.cout, Bk.cout, 1, 1, true, Bk.ru[j].c2));
+        }
+    }
+    const int ch = c.decoder_dim >> c.upsample_rates.size();
+    REQ(make_snake(E, "head.snake", ch, 1, E->head_snake));
+    {
+        auto* w = get_raw(E, "head.conv.w", (size_t)ch * c.conv_kernel); REQ(w);
+        std::vector<float> t((size_t)c.conv_kernel * ch);
+        for (int cc = 0; cc < ch; ++cc) for (int j = 0; j < c.conv_kernel; ++j) t[(size_t)j * ch + cc] = (*w)[(size_t)cc * c.conv_kernel + j];
+        REQ(E->head_w = upload(E, t));
+        auto* b = get_raw(E, "head.conv.b", 1); REQ(b);
+        E->head_b = (*b)[0];
+    }
+#undef REQ
+    E->raw.clear();
+
+    // ---- activation pools
+    const int W = E->wave, T = c.chunk_frames;
+    int Tup = T; for (int r : c.upsampling_ratios) Tup *= r;
+    size_t off = 0;
+    auto carve = [&](size_t n) { size_t o = off; off += (n + 63) / 64 * 64; return o; };
+    const size_t o_rvq = carve((size_t)W * T * c.rvq_dim), o_pre = carve((size_t)W * T * c.latent_dim),
+                 o_h = carve((size_t)W * T * c.xf_hidden), o_hn = carve((size_t)W * T * c.xf_hidden),
+                 o_qkv = carve((size_t)W * T * 3 * c.attn_dim()), o_att = carve((size_t)W * T * c.attn_dim()),
+                 o_gu = carve((size_t)W * T * 2 * c.xf_inter), o_act = carve((size_t)W * T * c.xf_inter),
+                 o_x = carve((size_t)W * Tup * c.latent_dim), o_x2 = carve((size_t)W * Tup * c.latent_dim),
+                 o_ln = carve((size_t)W * Tup * c.latent_dim),
+                 o_mid = carve((size_t)W * Tup * c.latent_dim * c.convnext_mult);
+    CK(cudaMalloc(&E->front.p, off * sizeof(float))); E->front.n = off;
+    float* f = E->front.p;
+    E->f_rvq = f + o_rvq; E->f_pre = f + o_pre; E->f_h = f + o_h; E->f_hn = f + o_hn; E->f_qkv = f + o_qkv;
+    E->f_att = f + o_att; E->f_gu = f + o_gu; E->f_act = f + o_act; E->f_x = f + o_x; E->f_x2 = f + o_x2;
+    E->f_ln = f + o_ln; E->f_mid = f + o_mid;
+    size_t mx = (size_t)Tup * c.decoder_dim;
+    int L = Tup;
+    for (size_t b = 0; b < c.upsample_rates.size(); ++b) {
+        L = c.tlen(L, c.upsample_rates[b]);
+        if (L < 1) return fail(E, VOC_E_INVALID, "chunk_frames too small for transconv_trim='both'");
+        mx = std::max(mx, (size_t)L * (c.decoder_dim >> (b + 1)));
+    }
+    E->big_elems = mx;
+    for (int i = 0; i < 3; ++i) { CK(cudaMalloc(&E->big[i].p, mx * W * sizeof(float))); E->big[i].n = mx * W; }
+    CK(cudaMalloc(&E->d_err, sizeof(int)));
+    CK(cudaMemset(E->d_err, 0, sizeof(int)));
+
+    // ---- crossfade tables (fade_tables below restates numpy's linspace)
+    {
+        const int ov = 16 * c.samples_per_frame();
+        std::vector<float> fo(ov), fi(ov);
+        fade_tables(ov, fo.data(), fi.data());
+        CK(cudaMalloc(&E->d_fade_out, ov * sizeof(float))); CK(cudaMalloc(&E->d_fade_in, ov * sizeof(float)));
+        CK(cudaMemcpy(E->d_fade_out, fo.data(), ov * sizeof(float), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(E->d_fade_in, fi.data(), ov * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    E->finalized = true;
+    return VOC_OK;
+}
+
+// --------------------------------------------------------------------------------------
+// one wave: windows [w_begin, w_begin + nw) of a request -> chunk_out[nw][Lc]
+// --------------------------------------------------------------------------------------
+static int run_wave(Engine* E, const long long* d_codes, int n_frames, int win_step, int w_begin, int nw,
+                    float* chunk_out, cudaStream_t st) {
+    const Cfg& c = E->cfg;
+    const int T = c.chunk_frames;
+    // K1: RVQ gather-sum
+    E->launches++;
+    CK(voc_launch_rvq_gather(d_codes + (long long)w_begin * win_step * c.num_quantizers,
+                             n_frames - w_begin * win_step, T, win_step, nw, c.num_quantizers,
+                             c.codebook_size, E->rvq_tables, c.rvq_dim, E->f_rvq, E->d_err, st));
+    if (int r = dbg_capture(E, "rvq", E->f_rvq, (size_t)nw * T * c.rvq_dim, st)) return r;
+    // K2: pre-conv
+    {
+        TapGemmParams p = gp(E->pre_conv, E->f_rvq, (long long)T * c.rvq_dim, T, 0, T, nw);
+        setY(p, E->f_pre);
+        CK(run_gemm(E, p, st));
+    }
+    if (int r = dbg_capture(E, "pre_conv", E->f_pre, (size_t)nw * T * c.latent_dim, st)) return r;
+    float* x = E->f_pre;                 // [nw][T][latent]
+    if (c.pre_transformer) {
+        const int rows = nw * T, H = c.xf_hidden, A = c.attn_dim();
+        { TapGemmParams p = gp(E->xf_in, x, 0, rows, 0, rows, 1); setY(p, E->f_h); CK(run_gemm(E, p, st)); }
+        for (int l = 0; l < c.xf_layers; ++l) {
+            auto& Ly = E->xf[l];
+            E->launches++; CK(voc_launch_rmsnorm(E->f_h, Ly.ln1, E->f_hn, rows, H, (float)c.rms_eps, st));
+            { TapGemmParams p = gp(Ly.qkv, E->f_hn, 0, rows, 0, rows, 1); setY(p, E->f_qkv); CK(run_gemm(E, p, st)); }
+            E->launches++; CK(voc_launch_attention(E->f_qkv, E->f_att, nw, T, c.xf_heads, c.xf_head_dim, E->rope_cos, E->rope_sin, c.sliding_window, st));
+            { TapGemmParams p = gp(Ly.o, E->f_att, 0, rows, 0, rows, 1); p.scale = Ly.ls_attn; setR(p, E->f_h); setY(p, E->f_h); CK(run_gemm(E, p, st)); }
+            E->launches++; CK(voc_launch_rmsnorm(E->f_h, Ly.ln2, E->f_hn, rows, H, (float)c.rms_eps, st));
+            { TapGemmParams p = gp(Ly.gu, E->f_hn, 0, rows, 0, rows, 1); setY(p, E->f_gu); CK(run_gemm(E, p, st)); }
+            E->launches++; CK(voc_launch_swiglu(E->f_gu, E->f_act, rows, c.xf_inter, st));
+            { TapGemmParams p = gp(Ly.down, E->f_act, 0, rows, 0, rows, 1); p.scale = Ly.ls_mlp; setR(p, E->f_h); setY(p, E->f_h); CK(run_gemm(E, p, st)); }
+            (void)A;
+        }
+        E->launches++; CK(voc_launch_rmsnorm(E->f_h, E->xf_norm, E->f_hn, rows, H, (float)c.rms_eps, st));
+        { TapGemmParams p = gp(E->xf_out, E->f_hn, 0, rows, 0, rows, 1); setY(p, E->f_x); CK(run_gemm(E, p, st)); }
+        x = E->f_x;
+        if (int r = dbg_capture(E, "xf", x, (size_t)nw * T * c.latent_dim, st)) return r;
+    }
+    // K3: upsample stages (k = s transposed conv = GEMM + interleave, then ConvNeXt)
+    int L = T;
+    float* other = (x == E->f_x) ? E->f_x2 : E->f_x;
+    for (size_t u = 0; u < E->ups.size(); ++u) {
+        auto& U = E->ups[u];
+        const int C = c.latent_dim, r = c.upsampling_ratios[u];
+        { TapGemmParams p = gp(U.convt, x, (long long)L * C, L, 0, L, nw); setY(p, other); CK(run_gemm(E, p, st)); }
+        L *= r;
+        std::swap(x, other);              // x: [nw][L][C]
+        if (c.convnext) {
+            E->launches++; CK(voc_launch_dwconv_ln(x, U.dw_w, U.dw_b, U.ln_w, U.ln_b, E->f_ln, nw, L, C, c.conv_kernel, (float)c.ln_eps, st));
+            const int rows = nw * L;
+            { TapGemmParams p = gp(U.pw1, E->f_ln, 0, rows, 0, rows, 1); p.act = VOC_ACT_GELU; setY(p, E->f_mid); CK(run_gemm(E, p, st)); }
+            { TapGemmParams p = gp(U.pw2, E->f_mid, 0, rows, 0, rows, 1); p.scale = U.gamma; setR(p, x); setY(p, x); CK(run_gemm(E, p, st)); }
+        }
+        if (other == E->f_pre) other = (x == E->f_x) ? E->f_x2 : E->f_x;
+        char nm[32]; snprintf(nm, sizeof nm, "up%d", (int)u);
+        if (int r2 = dbg_capture(E, nm, x, (size_t)nw * L * C, st)) return r2;
+    }
+    // K4: decoder conv-in, emits only Snake_0(conv_in(x)) -- the operand of block 0
+    float* bX = E->big[0].p; float* bS = E->big[1].p; float* bT = E->big[2].p;
+    {
+        TapGemmParams p = gp(E->conv_in, x, (long long)L * c.latent_dim, L, 0, L, nw);
+        setS(p, bS, E->blocks[0].s_in);
+        if (E->debug) setY(p, bX);
+        CK(run_gemm(E, p, st));
+        if (E->debug) if (int r = dbg_capture(E, "conv_in", bX, (size_t)nw * L * c.decoder_dim, st)) return r;
+    }
+    // K5/K6: decoder blocks
+    for (size_t b = 0; b < E->blocks.size(); ++b) {
+        auto& Bk = E->blocks[b];
+        const int Lout = c.tlen(L, Bk.stride);
+        const int Mrows = Lout / Bk.stride;                 // GEMM rows (one per input step)
+        const int row0 = c.trim_both ? 1 : 0;
+        {   // Snake'd input (bS, [nw][L][cin]) -> X' (bX) and Snake1_ru0(X') (bT)
+            TapGemmParams p = gp(Bk.convt, bS, (long long)L * Bk.cin, L, row0, Mrows, nw);
+            setY(p, bX); setS(p, bT, Bk.s_ru0_tiled);
+            CK(run_gemm(E, p, st));
+        }
+        L = Lout;
+        std::swap(bS, bT);                                   // bS = Snake1(X'), bT free
+        const int C = Bk.cout;
+        for (size_t j = 0; j < Bk.ru.size(); ++j) {
+            auto& R = Bk.ru[j];
+            {   // conv k7 dilated on Snake1(x) -> Snake2(.) only
+                TapGemmParams p = gp(R.c1, bS, (long long)L * C, L, 0, L, nw);
+                setS(p, bT, R.s2);
+                CK(run_gemm(E, p, st));
+            }
+            {   // conv k1 + residual -> x (in place) and the next consumer's Snake
+                TapGemmParams p = gp(R.c2, bT, (long long)L * C, L, 0, L, nw);
+                setR(p, bX);
+                const bool last_ru = (j + 1 == Bk.ru.size());
+                const SnakeP& nxt = !last_ru ? Bk.ru[j + 1].s1
+                                  : (b + 1 < E->blocks.size() ? E->blocks[b + 1].s_in : E->head_snake);
+                setS(p, bS, nxt);
+                if (!last_ru || E->debug) setY(p, bX);        // the residual stream ends with the block
+                CK(run_gemm(E, p, st));
+            }
+        }
+        char nm[32]; snprintf(nm, sizeof nm, "dec%d", (int)b);
+        if (E->debug) if (int r = dbg_capture(E, nm, bX, (size_t)nw * L * C, st)) return r;
+    }
+    // K7: head
+    const int ch = c.decoder_dim >> c.upsample_rates.size();
+    E->launches++;
+    CK(voc_launch_head(bS, (long long)L * ch, L, ch, c.conv_kernel, E->head_w, E->head_b, chunk_out, L, nw, st));
+    return VOC_OK;
+}
+
+static int check_codes_flag(Engine* E, cudaStream_t st) {
+    int flag = 0;
+    CK(cudaMemcpyAsync(&flag, E->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (flag) {
+        CK(cudaMemsetAsync(E->d_err, 0, sizeof(int), st));
+        return fail(E, VOC_E_INVALID, "audio code outside [0, codebook_size)");
+    }
+    return VOC_OK;
+}
+
+static int run_windows(Engine* E, const long long* d_codes, int n_frames, int win_step, int w0, int w1,
+                       float* chunk_out, cudaStream_t st) {
+    const long long Lc = E->cfg.chunk_samples();
+    for (int w = w0; w < w1; w += E->wave) {
+        const int nw = std::min(E->wave, w1 - w);
+        int r = run_wave(E, d_codes, n_frames, win_step, w, nw, chunk_out + (long long)(w - w0) * Lc, st);
+        if (r) return r;
+    }
+    return VOC_OK;
+}
+
+// --------------------------------------------------------------------------------------
+// the chunk / stitch plan of VocoderServer.synthesize (vocoder_server.py:73-121)
+// --------------------------------------------------------------------------------------
+struct Plan {
+    int n_windows = 0, step = 0, ov = 0;
+    std::vector<int> start, len, a_len, blended; std::vector<long long> dst;
+    long long total = 0;
+    bool pairwise = true;
+};
+static Plan make_plan_raw(int mt, long long Lc, int n) {
+    Plan P;
+    const int spt = 1920;                                 // SAMPLES_PER_TOKEN is a constant there (:30)
+    P.ov = 16 * spt; P.step = mt - 16;
+    if (n <= mt) {
+        P.n_windows = 1; P.step = mt; P.start = {0}; P.len = {n};
+        P.a_len = {(int)std::min<long long>(Lc, (long long)n * spt)}; P.blended = {0}; P.dst = {0};
+        P.total = P.a_len[0];
+        return P;
+    }
+    long long total = 0;
+    for (int s = 0; s < n; s += P.step) {
+        const int ln = std::min(s + mt, n) - s;
+        const int a = (int)std::min<long long>(Lc, (long long)ln * spt);
+        int bl = 0; long long d;
+        if (s == 0) { d = 0; total = a; }
+        else if (total >= P.ov && a >= P.ov) { bl = 1; d = total - P.ov; total = total + a - P.ov; }
+        else { d = total; total += a; }
+        P.start.push_back(s); P.len.push_back(ln); P.a_len.push_back(a); P.blended.push_back(bl); P.dst.push_back(d);
+    }
+    P.n_windows = (int)P.start.size(); P.total = total;
+    // the single-launch stitcher needs every blend to read un-blended samples of window w-1
+    for (int w = 1; w < P.n_windows; ++w)
+        if (P.blended[w]) {
+            const int need = P.ov + (P.blended[w - 1] ? P.ov : 0);
+            if (P.a_len[w - 1] < need) P.pairwise = false;
+        }
+    return P;
+}
+
+static Plan make_plan(const Cfg& c, int n) { return make_plan_raw(c.chunk_frames, c.chunk_samples(), n); }
+
+static void fade_tables(int ov, float* fo, float* fi) {
+    // exactly as numpy builds them (vocoder_server.py:108-109): linspace in float64
+    // (i*step + start, last element := stop), cast to f32; fade_in = 1 - fade_out in f32
+    const double step = (0.0 - 1.0) / (double)(ov - 1);
+    for (int i = 0; i < ov; ++i) {
+        volatile double prod = (double)i * step;           // keep mul and add separately rounded
+        double y = prod + 1.0;
+        if (i == ov - 1) y = 0.0;
+        fo[i] = (float)y;
+        fi[i] = 1.0f - fo[i];
+    }
+}
+
+static int ensure_i(Engine* E, size_t n) {
+    if (E->meta_cap >= n) return VOC_OK;
+    if (E->d_meta) cudaFree(E->d_meta);
+    E->d_meta = nullptr; E->meta_cap = 0;
+    CK(cudaMalloc(&E->d_meta, n * sizeof(int))); E->meta_cap = n;
+    return VOC_OK;
+}
+static int ensure_buf(Engine* E, DevBuf& b, size_t n) {
+    if (b.n >= n) return VOC_OK;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.n = 0;
+    CK(cudaMalloc(&b.p, n * sizeof(float))); b.n = n;
+    return VOC_OK;
+}
+
+// windows [w0,w1) of the plan -> output samples they own, written to out (offset *out_off)
+static int synth_range(Engine* E, const long long* d_codes, int n, int w0, int w1, float* d_f32, short* d_i16,
+                       long long cap, long long* out_off, long long* n_out, cudaStream_t st) {
+    if (!E->finalized) return fail(E, VOC_E_STATE, "voc_finalize has not been called");
+    if (n <= 0 || n > 10000) return fail(E, VOC_E_INVALID, "n_tokens must be in 1..10000 (vocoder_server.py:149)");
+    CK(cudaSetDevice(E->device));
+    const Plan P = make_plan(E->cfg, n);
+    if (w0 < 0) w0 = 0;
+    if (w1 > P.n_windows) w1 = P.n_windows;
+    if (w0 >= w1) { if (out_off) *out_off = 0; if (n_out) *n_out = 0; return VOC_OK; }
+    const long long Lc = E->cfg.chunk_samples();
+    const bool whole = (w0 == 0 && w1 == P.n_windows);
+    if (!P.pairwise && !whole) return fail(E, VOC_E_INVALID, "window ranges need the pairwise-overlap regime");
+    // owned output span
+    const long long o_begin = P.dst[w0];
+    long long o_end;
+    if (w1 == P.n_windows) o_end = P.total;
+    else o_end = P.dst[w1];                         // next range starts at its first window's dst
+    const long long cnt = o_end - o_begin;
+    if (cnt > cap) return fail(E, VOC_E_INVALID, "output buffer too small");
+    const int wc0 = (w0 > 0 && P.blended[w0]) ? w0 - 1 : w0;   // recompute the neighbour for the blend
+    const int nwc = w1 - wc0;
+    if (int r = ensure_buf(E, E->chunks, (size_t)nwc * Lc)) return r;
+    if (int r = run_windows(E, d_codes, n, P.step, wc0, w1, E->chunks.p, st)) return r;
+    if (P.pairwise) {
+        std::vector<int> meta((size_t)nwc * 6);
+        int max_a = 0;
+        for (int w = wc0; w < w1; ++w) {
+            int* m = &meta[(size_t)(w - wc0) * 6];
+            const bool owned = w >= w0;
+            m[0] = (int)(P.dst[w] - o_begin);
+            m[1] = owned ? P.a_len[w] : 0;           // the recomputed neighbour writes nothing
+            m[2] = P.blended[w];
+            // the trailing ov of the last owned window belongs to the next range's first window
+            m[3] = (w + 1 < P.n_windows) ? P.blended[w + 1] : 0;
+            m[4] = w > 0 ? P.a_len[w - 1] : 0;
+            m[5] = 0;
+            max_a = std::max(max_a, m[1]);
+        }
+        if (int r = ensure_i(E, meta.size())) return r;
+        CK(cudaMemcpyAsync(E->d_meta, meta.data(), meta.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        E->launches++;
+        CK(voc_launch_stitch(E->chunks.p, Lc, E->d_meta, nwc, P.ov, E->d_fade_out, E->d_fade_in, d_f32, d_i16, max_a, st));
+        // (cudaMemcpyAsync from pageable memory returns once `meta` has been staged)
+    } else {
+        // general regime (window shorter than two overlaps): replay the loop on the device
+        float* res = d_f32;
+        if (!res) { if (int r = ensure_buf(E, E->stitch_f32, (size_t)P.total)) return r; res = E->stitch_f32.p; }
+        long long len = 0;
+        for (int w = 0; w < P.n_windows; ++w) {
+            E->launches++;
+            CK(voc_launch_append_window(res, len, E->chunks.p + (long long)w * Lc, P.a_len[w], P.ov, P.blended[w], E->d_fade_out, E->d_fade_in, st));
+            len = P.blended[w] ? len + P.a_len[w] - P.ov : len + P.a_len[w];
+        }
+        if (d_i16) { E->launches++; CK(voc_launch_pcm16(res, d_i16, P.total, st)); }
+    }
+    if (out_off) *out_off = o_begin;
+    if (n_out) *n_out = cnt;
+    return VOC_OK;
+}
+
+static int ensure_codes(Engine* E, size_t n) {
+    if (E->codes_cap >= n) return VOC_OK;
+    if (E->d_codes) cudaFree(E->d_codes);
+    E->d_codes = nullptr; E->codes_cap = 0;
+    CK(cudaMalloc(&E->d_codes, n * sizeof(long long))); E->codes_cap = n;
+    return VOC_OK;
+}
+
+}  // namespace
+
+// ======================================================================================
+// C ABI
+// ======================================================================================
+extern "C" {
+
+int voc_abi_version(void) { return 1; }
+
+void* voc_create(const char* cfg_json, int device, int wave) {
+    auto E = std::make_unique<Engine>();
+    std::string err;
+    if (!cfg_from_json(cfg_json, E->cfg, err)) { g_create_error = err; fprintf(stderr, "voc_create: %s\n", err.c_str()); return nullptr; }
+    if (wave < 1) wave = 1;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+        g_create_error = std::string("no usable CUDA device (there is no CPU fallback): ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device ordinal out of range");
+        fprintf(stderr, "voc_create: %s\n", g_create_error.c_str());
+        return nullptr;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+        g_create_error = "device is not sm_100 (this library is built for B200 only)";
+        fprintf(stderr, "voc_create: %s\n", g_create_error.c_str());
+        return nullptr;
+    }
+    E->device = device; E->wave = wave;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        g_create_error = "cudaSetDevice / stream creation failed";
+        fprintf(stderr, "voc_create: %s\n", g_create_error.c_str());
+        return nullptr;
+    }
+    return E.release();
+}
+
+void voc_destroy(void* h) {
+    if (!h) return;
+    Engine* E = (Engine*)h;
+    cudaSetDevice(E->device);
+    cudaDeviceSynchronize();
+    delete E;
+}
+
+int voc_set_tensor(void* h, const char* name, const float* data, long long n_elem) {
+    Engine* E = (Engine*)h;
+    if (!E || !name || !data || n_elem <= 0) return VOC_E_INVALID;
+    if (E->finalized) return fail(E, VOC_E_STATE, "voc_set_tensor after voc_finalize");
+    E->raw[name].assign(data, data + n_elem);
+    return VOC_OK;
+}
+
+int voc_finalize(void* h) {
+    Engine* E = (Engine*)h;
+    if (!E) return VOC_E_INVALID;
+    if (E->finalized) return fail(E, VOC_E_STATE, "already finalized");
+    return engine_finalize(E);
+}
+
+int voc_max_tokens(void* h) { return h ? ((Engine*)h)->cfg.chunk_frames : VOC_E_INVALID; }
+long long voc_chunk_samples(void* h) { return h ? ((Engine*)h)->cfg.chunk_samples() : VOC_E_INVALID; }
+long long voc_out_samples(void* h, int n) {
+    if (!h || n <= 0) return VOC_E_INVALID;
+    return make_plan(((Engine*)h)->cfg, n).total;
+}
+int voc_num_windows(void* h, int n) {
+    if (!h || n <= 0) return VOC_E_INVALID;
+    return make_plan(((Engine*)h)->cfg, n).n_windows;
+}
+
+int voc_infer_chunks_dev(void* h, const long long* d_codes, int B, float* d_out, void* stream) {
+    Engine* E = (Engine*)h;
+    if (!E) return VOC_E_INVALID;
+    if (!E->finalized) return fail(E, VOC_E_STATE, "voc_finalize has not been called");
+    if (!d_codes || !d_out || B <= 0) return fail(E, VOC_E_INVALID, "bad argument");
+    CK(cudaSetDevice(E->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : E->stream;
+    const int T = E->cfg.chunk_frames;
+    return run_windows(E, d_codes, B * T, T, 0, B, d_out, st);
+}
+
+int voc_infer_chunks(void* h, const long long* codes, int B, float* out) {
+    Engine* E = (Engine*)h;
+    if (!E) return VOC_E_INVALID;
+    if (!E->finalized) return fail(E, VOC_E_STATE, "voc_finalize has not been called");
+    if (!codes || !out || B <= 0) return fail(E, VOC_E_INVALID, "bad argument");
+    CK(cudaSetDevice(E->device));
+    const int T = E->cfg.chunk_frames;
+    const long long Lc = E->cfg.chunk_samples();
+    const size_t nc = (size_t)B * T * 16;
+    if (int r = ensure_codes(E, nc)) return r;
+    if (int r = ensure_buf(E, E->chunks, (size_t)B * Lc)) return r;
+    CK(cudaMemcpyAsync(E->d_codes, codes, nc * sizeof(long long), cudaMemcpyHostToDevice, E->stream));
+    if (int r = run_windows(E, E->d_codes, B * T, T, 0, B, E->chunks.p, E->stream)) return r;
+    if (int r = check_codes_flag(E, E->stream)) return r;
+    CK(cudaMemcpyAsync(out, E->chunks.p, (size_t)B * Lc * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
+    CK(cudaStreamSynchronize(E->stream));
+    return VOC_OK;
+}
+
+int voc_synthesize_range_dev(void* h, const long long* d_codes, int n_tokens, int w0, int w1, float* d_out_f32,
+                             short* d_out_i16, long long cap, long long* out_offset, long long* n_out, void* stream) {
+    Engine* E = (Engine*)h;
+    if (!E) return VOC_E_INVALID;
+    if (!d_codes || (!d_out_f32 && !d_out_i16)) return fail(E, VOC_E_INVALID, "bad argument");
+    cudaStream_t st = stream ? (cudaStream_t)stream : E->stream;
+    return synth_range(E, d_codes, n_tokens, w0, w1, d_out_f32, d_out_i16, cap, out_offset, n_out, st);
+}
+
+int voc_synthesize_dev(void* h, const long long* d_codes, int n_tokens, float* d_out_f32, short* d_out_i16,
+                       long long cap, long long* n_out, void* stream) {
+    long long off = 0;
+    return voc_synthesize_range_dev(h, d_codes, n_tokens, 0, 1 << 30, d_out_f32, d_out_i16, cap, &off, n_out, stream);
+}
+
+static int synth_host(void* h, const long long* codes, int n, float* of, short* oi, long long cap, long long* n_out) {
+    Engine* E = (Engine*)h;
+    if (!E) return VOC_E_INVALID;
+    if (!E->finalized) return fail(E, VOC_E_STATE, "voc_finalize has not been called");
+    if (!codes || (!of && !oi) || !n_out) return fail(E, VOC_E_INVALID, "bad argument");
+    if (n <= 0 || n > 10000) return fail(E, VOC_E_INVALID, "n_tokens must be in 1..10000 (vocoder_server.py:149)");
+    CK(cudaSetDevice(E->device));
+    const long long total = make_plan(E->cfg, n).total;
+    if (total > cap) return fail(E, VOC_E_INVALID, "output buffer too small");
+    if (int r = ensure_codes(E, (size_t)n * 16)) return r;
+    CK(cudaMemcpyAsync(E->d_codes, codes, (size_t)n * 16 * sizeof(long long), cudaMemcpyHostToDevice, E->stream));
+    float* df = nullptr; short* di = nullptr;
+    if (of) { if (int r = ensure_buf(E, E->stitch_f32, (size_t)total)) return r; df = E->stitch_f32.p; }
+    if (oi) {
+        if (E->pcm_cap < (size_t)total) {
+            if (E->d_pcm) cudaFree(E->d_pcm);
+            E->d_pcm = nullptr; E->pcm_cap = 0;
+            CK(cudaMalloc(&E->d_pcm, (size_t)total * sizeof(short))); E->pcm_cap = (size_t)total;
+        }
+        di = E->d_pcm;
+    }
+    long long off = 0, cnt = 0;
+    if (int r = synth_range(E, E->d_codes, n, 0, 1 << 30, df, di, total, &off, &cnt, E->stream)) return r;
+    if (int r = check_codes_flag(E, E->stream)) return r;
+    if (of) CK(cudaMemcpyAsync(of, df, (size_t)cnt * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
+    if (oi) CK(cudaMemcpyAsync(oi, di, (size_t)cnt * sizeof(short), cudaMemcpyDeviceToHost, E->stream));
+    CK(cudaStreamSynchronize(E->stream));
+    *n_out = cnt;
+    return VOC_OK;
+}
+
+int voc_synthesize_f32(void* h, const long long* codes, int n_tokens, float* out, long long cap, long long* n_out) {
+    return synth_host(h, codes, n_tokens, out, nullptr, cap, n_out);
+}
+int voc_synthesize_pcm16(void* h, const long long* codes, int n_tokens, short* out, long long cap, long long* n_out) {
+    return synth_host(h, codes, n_tokens, nullptr, out, cap, n_out);
+}
+
+int voc_check_dev(void* h, void* stream) {
+    Engine* E = (Engine*)h;
+    if (!E) return VOC_E_INVALID;
+    CK(cudaSetDevice(E->device));
+    return check_codes_flag(E, stream ? (cudaStream_t)stream : E->stream);
+}
+
+int voc_plan(int max_tokens, long long chunk_samples, int n_tokens, int meta_cap, int* meta,
+             long long* total, int* pairwise) {
+    if (max_tokens < 17 || chunk_samples < 1 || n_tokens < 1) return VOC_E_INVALID;
+    const Plan P = make_plan_raw(max_tokens, chunk_samples, n_tokens);
+    if (total) *total = P.total;
+    if (pairwise) *pairwise = P.pairwise ? 1 : 0;
+    if (meta) {
+        if (meta_cap < P.n_windows * 6) return VOC_E_INVALID;
+        for (int w = 0; w < P.n_windows; ++w) {
+            int* m = meta + (size_t)w * 6;
+            m[0] = (int)P.dst[w]; m[1] = P.a_len[w]; m[2] = P.blended[w];
+            m[3] = (w + 1 < P.n_windows) ? P.blended[w + 1] : 0;
+            m[4] = w > 0 ? P.a_len[w - 1] : 0; m[5] = P.start[w];
+        }
+    }
+    return P.n_windows;
+}
+
+int voc_fade_tables(int ov, float* fade_out, float* fade_in) {
+    if (ov < 2 || !fade_out || !fade_in) return VOC_E_INVALID;
+    fade_tables(ov, fade_out, fade_in);
+    return VOC_OK;
+}
+
+const char* voc_last_error(void* h) {
+    if (!h) return g_create_error.c_str();
+    return ((Engine*)h)->err.c_str();
+}
+long long voc_kernel_launches(void* h) { return h ? ((Engine*)h)->launches : 0; }
+
+int voc_set_option(void* h, const char* key, const char* value) {
+    Engine* E = (Engine*)h;
+    if (!E || !key || !value) return VOC_E_INVALID;
+    const std::string k = key, v = value;
+    if (k == "gemm") {
+        if (v == "auto") E->gemm_mode = 0; else if (v == "simt") E->gemm_mode = 1; else if (v == "tc") E->gemm_mode = 2;
+        else return fail(E, VOC_E_INVALID, "gemm must be auto|simt|tc");
+        return VOC_OK;
+    }
+    if (k == "debug") { E->debug = (v == "1"); if (!E->debug) E->dbg.clear(); return VOC_OK; }
+    return fail(E, VOC_E_INVALID, "unknown option " + k);
+}
+
+long long voc_debug_stage(void* h, const char* name, float* out, long long cap) {
+    Engine* E = (Engine*)h;
+    if (!E || !name) return VOC_E_INVALID;
+    auto it = E->dbg.find(name);
+    if (it == E->dbg.end()) return fail(E, VOC_E_STATE, std::string("no captured stage ") + name);
+    const long long n = (long long)it->second.second;
+    if (!out) return n;
+    if (n > cap) return fail(E, VOC_E_INVALID, "buffer too small");
+    CK(cudaSetDevice(E->device));
+    CK(cudaStreamSynchronize(E->stream));
+    CK(cudaMemcpy(out, it->second.first->p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return n;
+}
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle.
+
+Gate (BASELINE.json north_star): SNR >= 60 dB and max-abs <= 1e-4 on the float output of a
+window; bit-exact for the integer/index work (stitch plan, crossfade, PCM16).
+"""
+import numpy as np
+import pytest
+
+from oracle import stitch_oracle as SO
+from oracle import vocoder_oracle as VO
+
+pytestmark = pytest.mark.gpu
+
+SNR_GATE_DB = 60.0
+MAXABS_GATE = 1e-4
+
+
+def _codes(cfg, shape, seed=1):
+    return np.random.default_rng(seed).integers(0, cfg.codebook_size, shape, dtype=np.int64)
+
+
+def _report(tag, ref, got):
+    snr = VO.snr_db(ref, got)
+    mx = float(np.abs(ref.astype(np.float64) - got).max())
+    print(f"{tag}: SNR {snr:.1f} dB max-abs {mx:.3e} ref-rms {float(np.sqrt((ref.astype(np.float64) ** 2).mean())):.3f}")
+    return snr, mx
+
+
+@pytest.mark.parametrize("trim", ["both", "right"])
+def test_tiny_stages(pkg, backend, trim):
+    """Every stage of a small architecture, so a failure names the first wrong kernel."""
+    cfg = pkg.VocoderConfig.tiny(transconv_trim=trim, chunk_frames=12)
+    w = pkg.init_weights(cfg, 0)
+    codes = _codes(cfg, (3, cfg.chunk_frames, 16))
+    voc = backend.Vocoder(cfg, w, wave=2)          # 3 windows in waves of 2 -> ragged last wave
+    voc.set_option("debug", "1")
+    taps = {}
+    ref, _ = VO.forward(codes, VO.Weights(w), cfg, taps)
+    got = voc.infer_chunks(codes)
+    # debug stages hold the last wave = window 2 only
+    for name in ["rvq", "pre_conv", "xf", "up0", "up1", "conv_in", "dec0", "dec1", "dec2", "dec3"]:
+        t = taps[name][2:3].permute(0, 2, 1).contiguous().numpy()
+        g = voc.debug_stage(name).reshape(t.shape)
+        snr, mx = _report(f"[{trim}] {name}", t, g)
+        assert snr > 90.0, name
+    snr, mx = _report(f"[{trim}] out", ref.numpy(), got)
+    assert got.shape == (3, cfg.chunk_samples())
+    assert snr >= SNR_GATE_DB and mx <= MAXABS_GATE
+    voc.close()
+
+
+def test_default_arch_short_window(pkg, backend):
+    cfg = pkg.VocoderConfig(chunk_frames=8)
+    w = pkg.init_weights(cfg, 0)
+    codes = _codes(cfg, (2, 8, 16))
+    voc = backend.Vocoder(cfg, w, wave=2)
+    got = voc.infer_chunks(codes)
+    ref, _ = VO.forward(codes, VO.Weights(w), cfg)
+    snr, mx = _report("default/8", ref.numpy(), got)
+    assert snr >= SNR_GATE_DB and mx <= MAXABS_GATE
+    voc.close()
+
+
+@pytest.fixture(scope="module")
+def full_model(pkg, backend):
+    cfg = pkg.VocoderConfig()
+    w = pkg.init_weights(cfg, 0)
+    voc = backend.Vocoder(cfg, w, wave=4)
+    yield cfg, w, voc
+    voc.close()
+
+
+def test_full_chunk_parity(full_model):
+    """BASELINE config: one 64-frame x 16-codebook window, default architecture."""
+    cfg, w, voc = full_model
+    codes = _codes(cfg, (1, 64, 16))
+    got = voc.infer_chunks(codes)
+    ref, lengths = VO.forward(codes, VO.Weights(w), cfg)
+    ref = ref.numpy()
+    assert got.shape == ref.shape == (1, cfg.chunk_samples())
+    snr, mx = _report("full/64", ref, got)
+    rms = float(np.sqrt((got.astype(np.float64) ** 2).mean()))
+    clamp = float((np.abs(got) >= 1.0).mean())
+    print(f"output rms {rms:.3f}, clamp fraction {clamp:.5f}")
+    assert 0.05 < rms < 0.5 and clamp < 0.01          # non-degenerate signal
+    assert snr >= SNR_GATE_DB and mx <= MAXABS_GATE
+
+
+def test_batch_invariance(full_model):
+    """A window's result does not depend on its batch-mates or its wave."""
+    cfg, w, voc = full_model
+    codes = _codes(cfg, (6, 64, 16), seed=5)
+    a = voc.infer_chunks(codes)
+    b = voc.infer_chunks(codes[4:5])
+    assert np.array_equal(a[4], b[0])
+
+
+def test_code_out_of_range_is_an_error(full_model, backend):
+    cfg, w, voc = full_model
+    codes = _codes(cfg, (1, 64, 16))
+    codes[0, 3, 7] = cfg.codebook_size
+    with pytest.raises(backend.VocoderError) as e:
+        voc.infer_chunks(codes)
+    assert e.value.code == backend.VOC_E_INVALID
+    codes[0, 3, 7] = -1
+    with pytest.raises(backend.VocoderError):
+        voc.synthesize(codes[0])
+    # and the handle keeps working afterwards
+    codes[0, 3, 7] = 0
+    voc.infer_chunks(codes)
+
+
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 97, 111, 112, 113, 200])
+def test_synthesize_equals_reference_stitching(full_model, n):
+    """Level 2 == level 1 + the reference's Python loop (vocoder_server.py:73-121), bit for bit,
+    including the short-last-window duplication quirk and the PCM16 truncation."""
+    cfg, w, voc = full_model
+    codes = _codes(cfg, (n, 16), seed=n)
+    chunk_fn = lambda padded: voc.infer_chunks(padded)[0]
+    ref = SO.synthesize(codes, chunk_fn, cfg.chunk_frames)
+    got = voc.synthesize(codes)
+    assert got.shape == ref.shape
+    assert np.array_equal(got, ref)
+    assert np.array_equal(voc.synthesize_pcm16(codes), SO.to_pcm16(ref))
+
+
+def test_window_ranges_tile_the_output(full_model):
+    import torch
+    cfg, w, voc = full_model
+    n = 500
+    codes = _codes(cfg, (n, 16), seed=9)
+    full = voc.synthesize_pcm16(codes)
+    nw = voc.num_windows(n)
+    d_codes = torch.from_numpy(codes).cuda()
+    out = np.zeros_like(full)
+    covered = 0
+    for (a, b) in [(0, 3), (3, 4), (4, 9), (9, nw)]:
+        buf = torch.zeros(len(full), dtype=torch.int16, device="cuda")
+        off, cnt = voc.synthesize_range_dev(d_codes, n, a, b, d_out_i16=buf, cap=len(full))
+        voc.check_dev()
+        assert off == covered
+        out[off:off + cnt] = buf[:cnt].cpu().numpy()
+        covered += cnt
+    assert covered == len(full)
+    assert np.array_equal(out, full)
