@@ -213,7 +213,9 @@ static int fail(Engine* E, int code, const std::string& msg) {
 static float* upload(Engine* E, const std::vector<float>& v) {
     float* d = nullptr;
     if (cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(float)) != cudaSuccess) return nullptr;
-    if (!v.empty() && cudaMemcpy(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+    // stream-ordered with the finalize-time kernels: a plain cudaMemcpy from pageable memory may
+    // return before the DMA lands and is not ordered against a non-blocking stream
+    if (!v.empty() && cudaMemcpyAsync(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice, E->stream) != cudaSuccess) {
         cudaFree(d); return nullptr;
     }
     E->owned.push_back(d);
@@ -442,7 +444,6 @@ static int engine_finalize(Engine* E) {
     E->big_elems = mx;
     for (int i = 0; i < 3; ++i) { CK(cudaMalloc(&E->big[i].p, mx * W * sizeof(float))); E->big[i].n = mx * W; }
     CK(cudaMalloc(&E->d_err, sizeof(int)));
-    CK(cudaMemset(E->d_err, 0, sizeof(int)));
 
     // ---- crossfade tables (fade_tables below restates numpy's linspace)
     {
@@ -450,9 +451,12 @@ static int engine_finalize(Engine* E) {
         std::vector<float> fo(ov), fi(ov);
         fade_tables(ov, fo.data(), fi.data());
         CK(cudaMalloc(&E->d_fade_out, ov * sizeof(float))); CK(cudaMalloc(&E->d_fade_in, ov * sizeof(float)));
-        CK(cudaMemcpy(E->d_fade_out, fo.data(), ov * sizeof(float), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(E->d_fade_in, fi.data(), ov * sizeof(float), cudaMemcpyHostToDevice));
+        CK(cudaMemcpyAsync(E->d_fade_out, fo.data(), ov * sizeof(float), cudaMemcpyHostToDevice, E->stream));
+        CK(cudaMemcpyAsync(E->d_fade_in, fi.data(), ov * sizeof(float), cudaMemcpyHostToDevice, E->stream));
+        CK(cudaStreamSynchronize(E->stream));
     }
+    CK(cudaMemsetAsync(E->d_err, 0, sizeof(int), E->stream));
+    CK(cudaDeviceSynchronize());       // weights are visible to any stream the caller brings
     E->finalized = true;
     return VOC_OK;
 }

@@ -50,13 +50,24 @@ def test_tiny_stages(pkg, backend, trim):
 
 
 def test_default_arch_short_window(pkg, backend):
+    """Default (full-width) architecture on 8-frame windows, stage by stage."""
     cfg = pkg.VocoderConfig(chunk_frames=8)
     w = pkg.init_weights(cfg, 0)
     codes = _codes(cfg, (2, 8, 16))
     voc = backend.Vocoder(cfg, w, wave=2)
+    voc.set_option("debug", "1")
+    taps = {}
+    ref, _ = VO.forward(codes, VO.Weights(w), cfg, taps)
     got = voc.infer_chunks(codes)
-    ref, _ = VO.forward(codes, VO.Weights(w), cfg)
-    snr, mx = _report("default/8", ref.numpy(), got)
+    bad = []
+    for name in ["rvq", "pre_conv", "xf", "up0", "up1", "conv_in", "dec0", "dec1", "dec2", "dec3"]:
+        t = taps[name].permute(0, 2, 1).contiguous().numpy()
+        g = voc.debug_stage(name).reshape(t.shape)
+        snr, mx = _report(f"default/8 {name}", t, g)
+        if snr < 90.0:
+            bad.append(name)
+    snr, mx = _report("default/8 out", ref.numpy(), got)
+    assert not bad, bad
     assert snr >= SNR_GATE_DB and mx <= MAXABS_GATE
     voc.close()
 
