@@ -230,6 +230,19 @@ class Vocoder:
                                                    C.byref(off), C.byref(n), stream))
         return off.value, n.value
 
+    def synthesize_range_pcm16(self, codes: np.ndarray, w0: int, w1: int):
+        """Windows [w0, w1) of one request: (offset, int16 CUDA tensor of the span they own).
+        torch is used only to hold device memory."""
+        import torch
+        codes = self._codes2d(codes)
+        dev = torch.device("cuda", self.device)
+        d_codes = torch.from_numpy(codes).to(dev)
+        cap = self.out_samples(len(codes))
+        buf = torch.empty(cap, dtype=torch.int16, device=dev)
+        off, cnt = self.synthesize_range_dev(d_codes, len(codes), w0, w1, d_out_i16=buf, cap=cap)
+        self.check_dev()
+        return off, buf[:cnt]
+
     def check_dev(self, stream: int = 0):
         """Synchronise `stream` and raise if a *_dev call met an out-of-range code."""
         self._ck(self.lib.voc_check_dev(self._h, stream))

@@ -356,7 +356,7 @@ static int engine_finalize(Engine* E) {
             REQ(make_linear(E, {p + "down.w"}, c.xf_hidden, c.xf_inter, nullptr, L.down));
         }
         REQ(E->xf_norm = upload_named(E, "xf.norm.w", c.xf_hidden));
-        // rotary table in float64 then cast, like the oracle (vocoder_oracle.py:rotary_cos_sin)
+        // rotary table evaluated in float64 then cast to float32 (angles t * theta^(-2d/hd))
         const int T = c.chunk_frames, H2 = c.xf_head_dim / 2;
         std::vector<float> cs((size_t)T * H2), sn((size_t)T * H2);
         for (int t = 0; t < T; ++t) for (int d = 0; d < H2; ++d) {

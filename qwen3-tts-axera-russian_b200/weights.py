@@ -108,7 +108,7 @@ def _rng(seed: int, name: str) -> np.random.Generator:
     return np.random.default_rng([seed, zlib.crc32(name.encode())])
 
 
-# Gains chosen once by running the oracle (oracle/precision_study.py --calibrate) so that,
+# Gains chosen once from a CPU run of the graph so that,
 # for the default architecture and seed 0, every stage stays O(1), the output RMS is
 # ~0.1-0.3 and < 1 % of the samples reach the clamp.
 _RESIDUAL_GAIN = 0.5      # conv2 of a residual unit / o_proj / down_proj / pwconv2

@@ -1,0 +1,68 @@
+"""The C-ABI library loads and exports exactly what include/voc_b200.h declares; host-only
+entry points behave; compute entry points fail loudly without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "voc_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(voc_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported(backend):
+    lib = ctypes.CDLL(backend.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/voc_b200.h but not exported"
+    assert sorted(backend.SIGNATURES) == names, "backend.SIGNATURES and the header disagree"
+    assert lib.voc_abi_version() == 1
+
+
+def test_no_torch_types_in_the_boundary():
+    src = open(os.path.join(ROOT, "include", "voc_b200.h")).read()
+    assert "torch" not in re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    assert "at::" not in src and "c10::" not in src
+
+
+def test_plan_rejects_bad_arguments(backend):
+    lib = backend.load_library()
+    assert lib.voc_plan(64, 122880, 0, 0, None, None, None) == backend.VOC_E_INVALID
+    assert lib.voc_plan(8, 122880, 10, 0, None, None, None) == backend.VOC_E_INVALID
+    small = np.zeros(6, dtype=np.int32)
+    assert lib.voc_plan(64, 122880, 200, small.size, small.ctypes.data, None, None) == backend.VOC_E_INVALID
+
+
+def test_create_fails_loudly_without_gpu(backend, pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(backend.VocoderError) as e:
+        backend.Vocoder(pkg.VocoderConfig.tiny())
+    assert e.value.code == backend.VOC_E_CUDA
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_bad_config_is_rejected(backend):
+    lib = backend.load_library()
+    assert not lib.voc_create(b'{"transconv_trim": "left"}', 0, 1)
+    assert b"transconv_trim" in lib.voc_last_error(None)
+    assert not lib.voc_create(b'{"num_quantizers": 8}', 0, 1)
+    assert not lib.voc_create(b'not json', 0, 1)
+
+
+def test_product_never_imports_the_oracle():
+    pkg_dir = os.path.join(ROOT, "qwen3-tts-axera-russian_b200")
+    for dirpath, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f
+                assert "stitch_oracle" not in txt and "vocoder_oracle" not in txt, f
