@@ -109,8 +109,17 @@ int voc_fade_tables(int ov, float* fade_out, float* fade_in);
 /* ---- diagnostics ---------------------------------------------------------------------*/
 const char* voc_last_error(void* h);       /* NULL handle: error of the last failed voc_create */
 long long   voc_kernel_launches(void* h);  /* kernels launched by this handle so far            */
-/* Options: "gemm" = "auto" | "simt" | "tc"   (kernel family for the dense layers)          */
+/* Options: "gemm" = "auto" | "simt" | "tc"   (kernel family for the dense layers)
+ *          "profile" = "0" | "1", "debug" = "0" | "1"                                      */
 int         voc_set_option(void* h, const char* key, const char* value);
+/* The handle's own stream (cudaStream_t as void*), so a caller can bracket the host entry
+ * points with CUDA events.                                                                */
+void*       voc_stream(void* h);
+/* Per-launch CUDA-event profile.  After voc_set_option(h,"profile","1") every kernel launch is
+ * bracketed by an event pair; voc_profile_report synchronises, aggregates by layer tag and
+ * writes a JSON array [{"tag","calls","ms","flops","bytes"}...] (algorithmic FLOPs / bytes of
+ * the launches) into buf, clearing the records.  buf = NULL returns the size needed.        */
+long long   voc_profile_report(void* h, char* buf, long long cap);
 /* Intermediate activations for parity tests: copies stage `name` ("rvq","pre_conv","xf",
  * "up0","up1","conv_in_s","dec0".."dec3") of the last wave into `out` (channels-last
  * [windows][time][channels]); returns the element count or a negative error.               */

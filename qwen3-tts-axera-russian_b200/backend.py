@@ -52,6 +52,8 @@ SIGNATURES = {
     "voc_last_error": (C.c_char_p, [C.c_void_p]),
     "voc_kernel_launches": (C.c_longlong, [C.c_void_p]),
     "voc_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
+    "voc_stream": (C.c_void_p, [C.c_void_p]),
+    "voc_profile_report": (C.c_longlong, [C.c_void_p, C.c_void_p, C.c_longlong]),
     "voc_debug_stage": (C.c_longlong, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_longlong]),
 }
 
@@ -246,6 +248,23 @@ class Vocoder:
     def check_dev(self, stream: int = 0):
         """Synchronise `stream` and raise if a *_dev call met an out-of-range code."""
         self._ck(self.lib.voc_check_dev(self._h, stream))
+
+    @property
+    def stream(self) -> int:
+        """The handle's cudaStream_t (as an int) for event bracketing of the host entry points."""
+        return int(self.lib.voc_stream(self._h) or 0)
+
+    def profile_report(self):
+        """Aggregated per-layer CUDA-event timings since the last call (needs profile=1)."""
+        import json
+        n = self.lib.voc_profile_report(self._h, None, 0)
+        if n < 0:
+            self._ck(int(n))
+        buf = C.create_string_buffer(int(n))
+        n2 = self.lib.voc_profile_report(self._h, buf, n)
+        if n2 < 0:
+            self._ck(int(n2))
+        return json.loads(buf.value.decode() or "[]")
 
     def debug_stage(self, name: str) -> np.ndarray:
         n = self.lib.voc_debug_stage(self._h, name.encode(), None, 0)

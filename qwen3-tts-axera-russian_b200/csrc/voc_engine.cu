@@ -185,6 +185,17 @@ struct Engine {
     short* d_pcm = nullptr; size_t pcm_cap = 0;
     std::map<std::string, std::pair<std::shared_ptr<DevBuf>, size_t>> dbg;
 
+    // per-launch CUDA-event profile (option "profile" = "1"), read by voc_profile_report
+    bool profile = false;
+    struct ProfRec { const char* tag; double flops, bytes; cudaEvent_t e0, e1; };
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> ev_pool;
+    std::string prof_json;
+    cudaEvent_t take_event() {
+        if (!ev_pool.empty()) { cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e; }
+        cudaEvent_t e = nullptr; cudaEventCreate(&e); return e;
+    }
+
     ~Engine() {
         for (float* p : owned) cudaFree(p);
         if (d_err) cudaFree(d_err);
@@ -193,8 +204,23 @@ struct Engine {
         if (d_fade_in) cudaFree(d_fade_in);
         if (d_codes) cudaFree(d_codes);
         if (d_pcm) cudaFree(d_pcm);
+        for (auto& r : prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+        for (auto e : ev_pool) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
     }
+};
+
+// RAII bracket: records an event pair around one kernel launch when profiling is on
+struct ProfScope {
+    Engine* E; cudaStream_t st; cudaEvent_t e1 = nullptr;
+    ProfScope(Engine* E_, cudaStream_t st_, const char* tag, double flops, double bytes) : E(E_), st(st_) {
+        E->launches++;
+        if (!E->profile) return;
+        cudaEvent_t e0 = E->take_event(); e1 = E->take_event();
+        cudaEventRecord(e0, st);
+        E->prof.push_back({tag, flops, bytes, e0, e1});
+    }
+    ~ProfScope() { if (e1) cudaEventRecord(e1, st); }
 };
 
 #define CK(expr)                                                                         \
@@ -284,8 +310,14 @@ static float* upload_named(Engine* E, const std::string& name, size_t n) {
     return upload(E, *v);
 }
 
-static cudaError_t run_gemm(Engine* E, TapGemmParams& p, cudaStream_t st) {
-    E->launches++;
+static cudaError_t run_gemm(Engine* E, TapGemmParams& p, cudaStream_t st, const char* tag = "gemm.other") {
+    const double flops = 2.0 * p.B * (double)p.M * p.N * p.K * p.ntaps;
+    // algorithmic bytes: A once, W once, outputs / residual once
+    double bytes = 4.0 * ((double)p.B * p.M * p.K + (double)p.ntaps * p.K * p.N);
+    if (p.Y) bytes += 4.0 * p.B * (double)p.M * p.N;
+    if (p.S) bytes += 4.0 * p.B * (double)p.M * p.N;
+    if (p.R) bytes += 4.0 * p.B * (double)p.M * p.N;
+    ProfScope ps(E, st, tag, flops, bytes);
     return voc_launch_tapgemm_simt(p, st);
 }
 
@@ -468,37 +500,40 @@ static int run_wave(Engine* E, const long long* d_codes, int n_frames, int win_s
                     float* chunk_out, cudaStream_t st) {
     const Cfg& c = E->cfg;
     const int T = c.chunk_frames;
+#define KLAUNCH(tag, flops, bytes, call) do { ProfScope _ps(E, st, tag, flops, bytes); CK(call); } while (0)
+#define GEMM(tag, p) CK(run_gemm(E, p, st, tag))
     // K1: RVQ gather-sum
-    E->launches++;
-    CK(voc_launch_rvq_gather(d_codes + (long long)w_begin * win_step * c.num_quantizers,
-                             n_frames - w_begin * win_step, T, win_step, nw, c.num_quantizers,
-                             c.codebook_size, E->rvq_tables, c.rvq_dim, E->f_rvq, E->d_err, st));
+    KLAUNCH("rvq_gather", 0.0, 4.0 * nw * T * c.rvq_dim * (c.num_quantizers + 1.0),
+            voc_launch_rvq_gather(d_codes + (long long)w_begin * win_step * c.num_quantizers,
+                                  n_frames - w_begin * win_step, T, win_step, nw, c.num_quantizers,
+                                  c.codebook_size, E->rvq_tables, c.rvq_dim, E->f_rvq, E->d_err, st));
     if (int r = dbg_capture(E, "rvq", E->f_rvq, (size_t)nw * T * c.rvq_dim, st)) return r;
     // K2: pre-conv
     {
         TapGemmParams p = gp(E->pre_conv, E->f_rvq, (long long)T * c.rvq_dim, T, 0, T, nw);
         setY(p, E->f_pre);
-        CK(run_gemm(E, p, st));
+        GEMM("pre_conv", p);
     }
     if (int r = dbg_capture(E, "pre_conv", E->f_pre, (size_t)nw * T * c.latent_dim, st)) return r;
     float* x = E->f_pre;                 // [nw][T][latent]
     if (c.pre_transformer) {
         const int rows = nw * T, H = c.xf_hidden, A = c.attn_dim();
-        { TapGemmParams p = gp(E->xf_in, x, 0, rows, 0, rows, 1); setY(p, E->f_h); CK(run_gemm(E, p, st)); }
+        const double nb = 8.0 * rows * H;
+        { TapGemmParams p = gp(E->xf_in, x, 0, rows, 0, rows, 1); setY(p, E->f_h); GEMM("xf.gemm", p); }
         for (int l = 0; l < c.xf_layers; ++l) {
             auto& Ly = E->xf[l];
-            E->launches++; CK(voc_launch_rmsnorm(E->f_h, Ly.ln1, E->f_hn, rows, H, (float)c.rms_eps, st));
-            { TapGemmParams p = gp(Ly.qkv, E->f_hn, 0, rows, 0, rows, 1); setY(p, E->f_qkv); CK(run_gemm(E, p, st)); }
-            E->launches++; CK(voc_launch_attention(E->f_qkv, E->f_att, nw, T, c.xf_heads, c.xf_head_dim, E->rope_cos, E->rope_sin, c.sliding_window, st));
-            { TapGemmParams p = gp(Ly.o, E->f_att, 0, rows, 0, rows, 1); p.scale = Ly.ls_attn; setR(p, E->f_h); setY(p, E->f_h); CK(run_gemm(E, p, st)); }
-            E->launches++; CK(voc_launch_rmsnorm(E->f_h, Ly.ln2, E->f_hn, rows, H, (float)c.rms_eps, st));
-            { TapGemmParams p = gp(Ly.gu, E->f_hn, 0, rows, 0, rows, 1); setY(p, E->f_gu); CK(run_gemm(E, p, st)); }
-            E->launches++; CK(voc_launch_swiglu(E->f_gu, E->f_act, rows, c.xf_inter, st));
-            { TapGemmParams p = gp(Ly.down, E->f_act, 0, rows, 0, rows, 1); p.scale = Ly.ls_mlp; setR(p, E->f_h); setY(p, E->f_h); CK(run_gemm(E, p, st)); }
-            (void)A;
+            KLAUNCH("xf.norm", 0.0, nb, voc_launch_rmsnorm(E->f_h, Ly.ln1, E->f_hn, rows, H, (float)c.rms_eps, st));
+            { TapGemmParams p = gp(Ly.qkv, E->f_hn, 0, rows, 0, rows, 1); setY(p, E->f_qkv); GEMM("xf.gemm", p); }
+            KLAUNCH("xf.attn", 4.0 * nw * c.xf_heads * (double)T * T * c.xf_head_dim / 2, 16.0 * rows * A,
+                    voc_launch_attention(E->f_qkv, E->f_att, nw, T, c.xf_heads, c.xf_head_dim, E->rope_cos, E->rope_sin, c.sliding_window, st));
+            { TapGemmParams p = gp(Ly.o, E->f_att, 0, rows, 0, rows, 1); p.scale = Ly.ls_attn; setR(p, E->f_h); setY(p, E->f_h); GEMM("xf.gemm", p); }
+            KLAUNCH("xf.norm", 0.0, nb, voc_launch_rmsnorm(E->f_h, Ly.ln2, E->f_hn, rows, H, (float)c.rms_eps, st));
+            { TapGemmParams p = gp(Ly.gu, E->f_hn, 0, rows, 0, rows, 1); setY(p, E->f_gu); GEMM("xf.gemm", p); }
+            KLAUNCH("xf.swiglu", 0.0, 12.0 * rows * c.xf_inter, voc_launch_swiglu(E->f_gu, E->f_act, rows, c.xf_inter, st));
+            { TapGemmParams p = gp(Ly.down, E->f_act, 0, rows, 0, rows, 1); p.scale = Ly.ls_mlp; setR(p, E->f_h); setY(p, E->f_h); GEMM("xf.gemm", p); }
         }
-        E->launches++; CK(voc_launch_rmsnorm(E->f_h, E->xf_norm, E->f_hn, rows, H, (float)c.rms_eps, st));
-        { TapGemmParams p = gp(E->xf_out, E->f_hn, 0, rows, 0, rows, 1); setY(p, E->f_x); CK(run_gemm(E, p, st)); }
+        KLAUNCH("xf.norm", 0.0, nb, voc_launch_rmsnorm(E->f_h, E->xf_norm, E->f_hn, rows, H, (float)c.rms_eps, st));
+        { TapGemmParams p = gp(E->xf_out, E->f_hn, 0, rows, 0, rows, 1); setY(p, E->f_x); GEMM("xf.gemm", p); }
         x = E->f_x;
         if (int r = dbg_capture(E, "xf", x, (size_t)nw * T * c.latent_dim, st)) return r;
     }
@@ -508,14 +543,15 @@ static int run_wave(Engine* E, const long long* d_codes, int n_frames, int win_s
     for (size_t u = 0; u < E->ups.size(); ++u) {
         auto& U = E->ups[u];
         const int C = c.latent_dim, r = c.upsampling_ratios[u];
-        { TapGemmParams p = gp(U.convt, x, (long long)L * C, L, 0, L, nw); setY(p, other); CK(run_gemm(E, p, st)); }
+        { TapGemmParams p = gp(U.convt, x, (long long)L * C, L, 0, L, nw); setY(p, other); GEMM("up.convt", p); }
         L *= r;
         std::swap(x, other);              // x: [nw][L][C]
         if (c.convnext) {
-            E->launches++; CK(voc_launch_dwconv_ln(x, U.dw_w, U.dw_b, U.ln_w, U.ln_b, E->f_ln, nw, L, C, c.conv_kernel, (float)c.ln_eps, st));
+            KLAUNCH("up.dwconv_ln", 2.0 * nw * L * C * c.conv_kernel, 8.0 * nw * L * C,
+                    voc_launch_dwconv_ln(x, U.dw_w, U.dw_b, U.ln_w, U.ln_b, E->f_ln, nw, L, C, c.conv_kernel, (float)c.ln_eps, st));
             const int rows = nw * L;
-            { TapGemmParams p = gp(U.pw1, E->f_ln, 0, rows, 0, rows, 1); p.act = VOC_ACT_GELU; setY(p, E->f_mid); CK(run_gemm(E, p, st)); }
-            { TapGemmParams p = gp(U.pw2, E->f_mid, 0, rows, 0, rows, 1); p.scale = U.gamma; setR(p, x); setY(p, x); CK(run_gemm(E, p, st)); }
+            { TapGemmParams p = gp(U.pw1, E->f_ln, 0, rows, 0, rows, 1); p.act = VOC_ACT_GELU; setY(p, E->f_mid); GEMM("up.pw1", p); }
+            { TapGemmParams p = gp(U.pw2, E->f_mid, 0, rows, 0, rows, 1); p.scale = U.gamma; setR(p, x); setY(p, x); GEMM("up.pw2", p); }
         }
         if (other == E->f_pre) other = (x == E->f_x) ? E->f_x2 : E->f_x;
         char nm[32]; snprintf(nm, sizeof nm, "up%d", (int)u);
@@ -527,19 +563,23 @@ static int run_wave(Engine* E, const long long* d_codes, int n_frames, int win_s
         TapGemmParams p = gp(E->conv_in, x, (long long)L * c.latent_dim, L, 0, L, nw);
         setS(p, bS, E->blocks[0].s_in);
         if (E->debug) setY(p, bX);
-        CK(run_gemm(E, p, st));
+        GEMM("conv_in", p);
         if (E->debug) if (int r = dbg_capture(E, "conv_in", bX, (size_t)nw * L * c.decoder_dim, st)) return r;
     }
     // K5/K6: decoder blocks
+    static const char* const T_CONVT[] = {"dec0.convt", "dec1.convt", "dec2.convt", "dec3.convt", "decN.convt"};
+    static const char* const T_C7[] = {"dec0.ru.conv7", "dec1.ru.conv7", "dec2.ru.conv7", "dec3.ru.conv7", "decN.ru.conv7"};
+    static const char* const T_C1[] = {"dec0.ru.conv1", "dec1.ru.conv1", "dec2.ru.conv1", "dec3.ru.conv1", "decN.ru.conv1"};
     for (size_t b = 0; b < E->blocks.size(); ++b) {
         auto& Bk = E->blocks[b];
+        const size_t ti = std::min<size_t>(b, 4);
         const int Lout = c.tlen(L, Bk.stride);
         const int Mrows = Lout / Bk.stride;                 // GEMM rows (one per input step)
         const int row0 = c.trim_both ? 1 : 0;
         {   // Snake'd input (bS, [nw][L][cin]) -> X' (bX) and Snake1_ru0(X') (bT)
             TapGemmParams p = gp(Bk.convt, bS, (long long)L * Bk.cin, L, row0, Mrows, nw);
             setY(p, bX); setS(p, bT, Bk.s_ru0_tiled);
-            CK(run_gemm(E, p, st));
+            GEMM(T_CONVT[ti], p);
         }
         L = Lout;
         std::swap(bS, bT);                                   // bS = Snake1(X'), bT free
@@ -549,7 +589,7 @@ static int run_wave(Engine* E, const long long* d_codes, int n_frames, int win_s
             {   // conv k7 dilated on Snake1(x) -> Snake2(.) only
                 TapGemmParams p = gp(R.c1, bS, (long long)L * C, L, 0, L, nw);
                 setS(p, bT, R.s2);
-                CK(run_gemm(E, p, st));
+                GEMM(T_C7[ti], p);
             }
             {   // conv k1 + residual -> x (in place) and the next consumer's Snake
                 TapGemmParams p = gp(R.c2, bT, (long long)L * C, L, 0, L, nw);
@@ -559,7 +599,7 @@ static int run_wave(Engine* E, const long long* d_codes, int n_frames, int win_s
                                   : (b + 1 < E->blocks.size() ? E->blocks[b + 1].s_in : E->head_snake);
                 setS(p, bS, nxt);
                 if (!last_ru || E->debug) setY(p, bX);        // the residual stream ends with the block
-                CK(run_gemm(E, p, st));
+                GEMM(T_C1[ti], p);
             }
         }
         char nm[32]; snprintf(nm, sizeof nm, "dec%d", (int)b);
@@ -567,8 +607,10 @@ static int run_wave(Engine* E, const long long* d_codes, int n_frames, int win_s
     }
     // K7: head
     const int ch = c.decoder_dim >> c.upsample_rates.size();
-    E->launches++;
-    CK(voc_launch_head(bS, (long long)L * ch, L, ch, c.conv_kernel, E->head_w, E->head_b, chunk_out, L, nw, st));
+    KLAUNCH("head", 2.0 * nw * L * ch * c.conv_kernel, 4.0 * nw * L * (ch + 1.0),
+            voc_launch_head(bS, (long long)L * ch, L, ch, c.conv_kernel, E->head_w, E->head_b, chunk_out, L, nw, st));
+#undef KLAUNCH
+#undef GEMM
     return VOC_OK;
 }
 
@@ -704,8 +746,10 @@ static int synth_range(Engine* E, const long long* d_codes, int n, int w0, int w
         }
         if (int r = ensure_i(E, meta.size())) return r;
         CK(cudaMemcpyAsync(E->d_meta, meta.data(), meta.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-        E->launches++;
-        CK(voc_launch_stitch(E->chunks.p, Lc, E->d_meta, nwc, P.ov, E->d_fade_out, E->d_fade_in, d_f32, d_i16, max_a, st));
+        {
+            ProfScope ps(E, st, "stitch", 0.0, (double)cnt * (4.0 + (d_f32 ? 4.0 : 0.0) + (d_i16 ? 2.0 : 0.0)));
+            CK(voc_launch_stitch(E->chunks.p, Lc, E->d_meta, nwc, P.ov, E->d_fade_out, E->d_fade_in, d_f32, d_i16, max_a, st));
+        }
         // (cudaMemcpyAsync from pageable memory returns once `meta` has been staged)
     } else {
         // general regime (window shorter than two overlaps): replay the loop on the device
@@ -931,8 +975,47 @@ int voc_set_option(void* h, const char* key, const char* value) {
         else return fail(E, VOC_E_INVALID, "gemm must be auto|simt|tc");
         return VOC_OK;
     }
+    if (k == "profile") { E->profile = (v == "1"); return VOC_OK; }
     if (k == "debug") { E->debug = (v == "1"); if (!E->debug) E->dbg.clear(); return VOC_OK; }
     return fail(E, VOC_E_INVALID, "unknown option " + k);
+}
+
+void* voc_stream(void* h) { return h ? (void*)((Engine*)h)->stream : nullptr; }
+
+long long voc_profile_report(void* h, char* buf, long long cap) {
+    Engine* E = (Engine*)h;
+    if (!E) return VOC_E_INVALID;
+    CK(cudaSetDevice(E->device));
+    if (!E->prof.empty()) {
+        CK(cudaDeviceSynchronize());
+        struct Agg { long long calls = 0; double ms = 0, flops = 0, bytes = 0; };
+        std::map<std::string, Agg> agg;
+        for (auto& r : E->prof) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, r.e0, r.e1));
+            Agg& a = agg[r.tag]; a.calls++; a.ms += ms; a.flops += r.flops; a.bytes += r.bytes;
+            E->ev_pool.push_back(r.e0); E->ev_pool.push_back(r.e1);
+        }
+        E->prof.clear();
+        std::string js = "[";
+        char tmp[512];
+        bool first = true;
+        for (auto& kv : agg) {
+            snprintf(tmp, sizeof tmp, "%s{\"tag\":\"%s\",\"calls\":%lld,\"ms\":%.6f,\"flops\":%.6e,\"bytes\":%.6e}",
+                     first ? "" : ",", kv.first.c_str(), kv.second.calls, kv.second.ms, kv.second.flops, kv.second.bytes);
+            js += tmp; first = false;
+        }
+        js += "]";
+        E->prof_json = js;
+    } else if (E->prof_json.empty()) {
+        E->prof_json = "[]";
+    }
+    const long long need = (long long)E->prof_json.size() + 1;
+    if (!buf) return need;
+    if (cap < need) return fail(E, VOC_E_INVALID, "buffer too small");
+    memcpy(buf, E->prof_json.c_str(), (size_t)need);
+    E->prof_json.clear();
+    return need;
 }
 
 long long voc_debug_stage(void* h, const char* name, float* out, long long cap) {
