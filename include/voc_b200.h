@@ -109,7 +109,11 @@ int voc_fade_tables(int ov, float* fade_out, float* fade_in);
 /* ---- diagnostics ---------------------------------------------------------------------*/
 const char* voc_last_error(void* h);       /* NULL handle: error of the last failed voc_create */
 long long   voc_kernel_launches(void* h);  /* kernels launched by this handle so far            */
-/* Options: "gemm" = "auto" | "simt" | "tc"   (kernel family for the dense layers)
+/* Options: "gemm" = "auto" | "simt" | "tc": kernel family of the dense layers.  "tc" (= "auto")
+ *            runs them as tcgen05 tensor-core tiles on split-fp16 operands with FP32 accumulation;
+ *            "simt" is the all-float32 CUDA-core path (the on-device cross-check).
+ *          "tc_flags" = experiment switches (bit 0 no tap reuse, bit 2 force 32-wide K chunks,
+ *            bits 8.. = MMAs accumulated in the tensor core per round-to-nearest flush)
  *          "profile" = "0" | "1", "debug" = "0" | "1"                                      */
 int         voc_set_option(void* h, const char* key, const char* value);
 /* The handle's own stream (cudaStream_t as void*), so a caller can bracket the host entry
@@ -124,6 +128,20 @@ long long   voc_profile_report(void* h, char* buf, long long cap);
  * "up0","up1","conv_in_s","dec0".."dec3") of the last wave into `out` (channels-last
  * [windows][time][channels]); returns the element count or a negative error.               */
 long long   voc_debug_stage(void* h, const char* name, float* out, long long cap);
+
+/* Kernel-level test / micro-benchmark hook: one "tap GEMM" (the contraction every dense layer of
+ * the graph maps onto: causal dilated Conv1d, phase-decomposed ConvTranspose1d, Linear) on caller
+ * data, through the FP32 CUDA-core kernel (mode 0), the CUDA-core kernel on split-fp16 operands
+ * (mode 1) or the tcgen05 kernel (mode 2).  Layouts: A [B][a_rows][K], W [ntaps*K][N],
+ * R / Y / S [B][M][N]; optional pointers may be NULL.  iters > 0 times that many launches with
+ * CUDA events (*ms = mean milliseconds).  Returns 0, a negative error, or 1 if mode 2 does not
+ * take the shape.  No reference counterpart: ONNX Runtime's operators are not individually
+ * callable from dual_npu/vocoder_server.py.                                                   */
+int voc_test_tapgemm(int device, int mode, int tc_flags, int B, int a_rows, int K, int N, int M,
+                     int a_row0, int ntaps, const int* tap_off, const float* A, const float* W,
+                     const float* bias, const float* scale, int act_kind, const float* R,
+                     const float* sn_a, const float* sn_invb, float* Y, float* S, int iters,
+                     float* ms);
 
 #ifdef __cplusplus
 }

@@ -55,6 +55,8 @@ SIGNATURES = {
     "voc_stream": (C.c_void_p, [C.c_void_p]),
     "voc_profile_report": (C.c_longlong, [C.c_void_p, C.c_void_p, C.c_longlong]),
     "voc_debug_stage": (C.c_longlong, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_longlong]),
+    "voc_test_tapgemm": (C.c_int, [C.c_int] * 10 + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 5
+                         + [C.c_int, C.c_void_p]),
 }
 
 _lib = None
@@ -109,6 +111,30 @@ def fade_tables(ov: int):
     if rc:
         raise VocoderError(rc, "voc_fade_tables: bad argument")
     return fo, fi
+
+
+def test_tapgemm(mode: int, A: np.ndarray, W: np.ndarray, tap_off, M: int, a_row0: int = 0, bias=None,
+                 scale=None, act: int = 0, R=None, sn_a=None, sn_invb=None, want_y: bool = True,
+                 want_s: bool = False, tc_flags: int = 0, iters: int = 0, device: int = 0):
+    """One tap-GEMM through ``voc_test_tapgemm`` (see include/voc_b200.h).  A [B, a_rows, K] f32,
+    W [ntaps*K, N] f32.  Returns (rc, Y or None, S or None, ms)."""
+    lib = load_library()
+    A = np.ascontiguousarray(A, dtype=np.float32)
+    W = np.ascontiguousarray(W, dtype=np.float32)
+    B, a_rows, K = A.shape
+    ntaps = len(tap_off)
+    N = W.shape[1]
+    assert W.shape[0] == ntaps * K
+    to = np.asarray(tap_off, dtype=np.int32)
+    f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+    bias, scale, R, sn_a, sn_invb = f(bias), f(scale), f(R), f(sn_a), f(sn_invb)
+    Y = np.zeros((B, M, N), dtype=np.float32) if want_y else None
+    S = np.zeros((B, M, N), dtype=np.float32) if want_s else None
+    ms = C.c_float(0.0)
+    rc = lib.voc_test_tapgemm(device, mode, tc_flags, B, a_rows, K, N, M, a_row0, ntaps, to.ctypes.data,
+                              A.ctypes.data, W.ctypes.data, _ptr(bias), _ptr(scale), act, _ptr(R), _ptr(sn_a),
+                              _ptr(sn_invb), _ptr(Y), _ptr(S), iters, C.addressof(ms))
+    return rc, Y, S, ms.value
 
 
 def _ptr(a) -> int:

@@ -26,7 +26,7 @@ template <int VN> __device__ __forceinline__ void vstore(float* dst, const float
     else                   *reinterpret_cast<float2*>(dst) = make_float2(src[0], src[1]);
 }
 
-template <int BM, int BN, int VN, int CN>
+template <int BM, int BN, int VN, int CN, bool ASPLIT>
 __global__ void __launch_bounds__(256)
 tapgemm_simt_kernel(const __grid_constant__ TapGemmParams p) {
     static_assert(BN == 16 * VN * CN, "BN = 16*VN*CN");
@@ -44,7 +44,7 @@ tapgemm_simt_kernel(const __grid_constant__ TapGemmParams p) {
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN, b = blockIdx.z;
-    const float* __restrict__ A = p.A + (long long)b * p.a_bstride;
+    const float* __restrict__ A = ASPLIT ? nullptr : p.A + (long long)b * p.a_bstride;
     const float* __restrict__ W = p.W;
     const int kIters = (p.K + BK - 1) / BK;
     const int nIt = p.ntaps * kIters;
@@ -68,8 +68,20 @@ tapgemm_simt_kernel(const __grid_constant__ TapGemmParams p) {
             const int gr = m0 + row + roff;
             const int gk = k0 + kq * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gr >= 0 && gr < p.a_rows && gk < p.K)
-                v = *reinterpret_cast<const float4*>(A + (long long)gr * p.lda + gk);
+            if (gr >= 0 && gr < p.a_rows && gk < p.K) {
+                if (ASPLIT) {       // operand stored as two fp16 planes: x = hi + lo (exact in fp32)
+                    const long long o = (long long)b * p.a_bstride + (long long)gr * p.lda + gk;
+                    const uint2 h = *reinterpret_cast<const uint2*>(p.A_hi + o);
+                    const uint2 l = *reinterpret_cast<const uint2*>(p.A_lo + o);
+                    const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&h.x));
+                    const float2 h1 = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+                    const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&l.x));
+                    const float2 l1 = __half22float2(*reinterpret_cast<const __half2*>(&l.y));
+                    v = make_float4(h0.x + l0.x, h0.y + l0.y, h1.x + l1.x, h1.y + l1.y);
+                } else {
+                    v = *reinterpret_cast<const float4*>(A + (long long)gr * p.lda + gk);
+                }
+            }
             ra[i] = v;
         }
 #pragma unroll
@@ -141,7 +153,8 @@ tapgemm_simt_kernel(const __grid_constant__ TapGemmParams p) {
         for (int v = 0; v < VN; ++v) { bias[v] = 0.f; scl[v] = 1.f; sa[v] = 1.f; sb[v] = 1.f; }
         if (p.bias) vload<VN>(bias, p.bias + n);
         if (p.scale) vload<VN>(scl, p.scale + n);
-        if (p.S) { vload<VN>(sa, p.sn_a + n); vload<VN>(sb, p.sn_invb + n); }
+        const bool haveS = p.S || p.S_hi;
+        if (haveS && p.sn_a) { vload<VN>(sa, p.sn_a + n); vload<VN>(sb, p.sn_invb + n); }
 #pragma unroll
         for (int r = 0; r < RM; ++r)
 #pragma unroll
@@ -162,11 +175,24 @@ tapgemm_simt_kernel(const __grid_constant__ TapGemmParams p) {
                     for (int q = 0; q < VN; ++q) v[q] += rr[q];
                 }
                 if (p.Y) vstore<VN>(p.Y + (long long)b * p.y_bstride + (long long)m * p.ldy + n, v);
-                if (p.S) {
+                if (haveS) {
                     float s[VN];
 #pragma unroll
-                    for (int q = 0; q < VN; ++q) s[q] = voc_snake(v[q], sa[q], sb[q]);
-                    vstore<VN>(p.S + (long long)b * p.s_bstride + (long long)m * p.lds + n, s);
+                    for (int q = 0; q < VN; ++q) s[q] = p.sn_a ? voc_snake(v[q], sa[q], sb[q]) : v[q];
+                    const long long so = (long long)b * p.s_bstride + (long long)m * p.lds + n;
+                    if (p.S) vstore<VN>(p.S + so, s);
+                    if (p.S_hi) {
+                        __half2 h[VN / 2], l[VN / 2];
+#pragma unroll
+                        for (int q = 0; q < VN / 2; ++q) voc_split2(s[2 * q], s[2 * q + 1], h[q], l[q]);
+                        if constexpr (VN == 4) {
+                            *reinterpret_cast<uint2*>(p.S_hi + so) = *reinterpret_cast<const uint2*>(h);
+                            *reinterpret_cast<uint2*>(p.S_lo + so) = *reinterpret_cast<const uint2*>(l);
+                        } else {
+                            *reinterpret_cast<__half2*>(p.S_hi + so) = h[0];
+                            *reinterpret_cast<__half2*>(p.S_lo + so) = l[0];
+                        }
+                    }
                 }
             }
     }
@@ -175,7 +201,8 @@ tapgemm_simt_kernel(const __grid_constant__ TapGemmParams p) {
 template <int BM, int BN, int VN, int CN>
 cudaError_t launch_cfg(const TapGemmParams& p, cudaStream_t st) {
     dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN, p.B);
-    tapgemm_simt_kernel<BM, BN, VN, CN><<<grid, 256, 0, st>>>(p);
+    if (p.A_hi) tapgemm_simt_kernel<BM, BN, VN, CN, true><<<grid, 256, 0, st>>>(p);
+    else        tapgemm_simt_kernel<BM, BN, VN, CN, false><<<grid, 256, 0, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -190,6 +217,25 @@ cudaError_t voc_launch_tapgemm_simt(const TapGemmParams& p, cudaStream_t st) {
     return launch_cfg<64, 32, 2, 1>(p, st);
 }
 
+// store 4 consecutive values of an activation tensor in whichever format it is kept in
+__device__ __forceinline__ void act_store4(const VocAct& o, long long idx, float4 v) {
+    if (o.f) *reinterpret_cast<float4*>(o.f + idx) = v;
+    if (o.hi) {
+        __half2 h[2], l[2];
+        voc_split2(v.x, v.y, h[0], l[0]);
+        voc_split2(v.z, v.w, h[1], l[1]);
+        *reinterpret_cast<uint2*>(o.hi + idx) = *reinterpret_cast<const uint2*>(h);
+        *reinterpret_cast<uint2*>(o.lo + idx) = *reinterpret_cast<const uint2*>(l);
+    }
+}
+__device__ __forceinline__ void act_store1(const VocAct& o, long long idx, float v) {
+    if (o.f) o.f[idx] = v;
+    if (o.hi) voc_split1(v, o.hi[idx], o.lo[idx]);
+}
+__device__ __forceinline__ float act_load1(const VocAct& o, long long idx) {
+    return o.f ? o.f[idx] : __half2float(o.hi[idx]) + __half2float(o.lo[idx]);
+}
+
 // =====================================================================================
 // K1: RVQ codebook gather + sum.  tables = the out-projections folded into
 // the codebooks: tables[q][code][:] = P_{sem|ac} * E_q[code]  (dim floats).
@@ -199,7 +245,7 @@ cudaError_t voc_launch_tapgemm_simt(const TapGemmParams& p, cudaStream_t st) {
 // =====================================================================================
 __global__ void rvq_gather_kernel(const long long* __restrict__ codes, int n_frames, int frames_per_win,
                                   int win_step, int n_q, int codebook_size,
-                                  const float* __restrict__ tables, int dim, float* __restrict__ out,
+                                  const float* __restrict__ tables, int dim, VocAct out,
                                   int* err_flag) {
     const int w = blockIdx.y, t = blockIdx.x;
     const long long src = (long long)w * win_step + t;
@@ -214,13 +260,13 @@ __global__ void rvq_gather_kernel(const long long* __restrict__ codes, int n_fra
                 tables + ((long long)q * codebook_size + c) * dim + d);
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
-        *reinterpret_cast<float4*>(out + row_out * dim + d) = acc;
+        act_store4(out, row_out * dim + d, acc);
     }
 }
 
 cudaError_t voc_launch_rvq_gather(const long long* codes, int n_frames, int frames_per_win, int win_step,
                                   int n_windows, int n_q, int codebook_size, const float* tables,
-                                  int dim, float* out, int* err_flag, cudaStream_t st) {
+                                  int dim, VocAct out, int* err_flag, cudaStream_t st) {
     if (dim % 4) return cudaErrorInvalidValue;
     int threads = dim / 4; if (threads > 256) threads = 256; if (threads < 32) threads = 32;
     dim3 grid(frames_per_win, n_windows);
@@ -233,7 +279,7 @@ cudaError_t voc_launch_rvq_gather(const long long* codes, int n_frames, int fram
 // RMSNorm over channels, one warp per row (sibling :3458-3476)
 // =====================================================================================
 __global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                               float* __restrict__ y, int rows, int C, float eps) {
+                               VocAct y, int rows, int C, float eps) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -246,16 +292,15 @@ __global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restr
 #pragma unroll
     for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     const float inv = rsqrtf(ss / (float)C + eps);
-    float* yr = y + (long long)row * C;
     for (int c = lane * 4; c < C; c += 128) {
         const float4 v = *reinterpret_cast<const float4*>(xr + c);
         const float4 g = *reinterpret_cast<const float4*>(w + c);
-        *reinterpret_cast<float4*>(yr + c) =
-            make_float4(g.x * (v.x * inv), g.y * (v.y * inv), g.z * (v.z * inv), g.w * (v.w * inv));
+        act_store4(y, (long long)row * C + c,
+                   make_float4(g.x * (v.x * inv), g.y * (v.y * inv), g.z * (v.z * inv), g.w * (v.w * inv)));
     }
 }
 
-cudaError_t voc_launch_rmsnorm(const float* x, const float* w, float* y, int rows, int C, float eps,
+cudaError_t voc_launch_rmsnorm(const float* x, const float* w, VocAct y, int rows, int C, float eps,
                                cudaStream_t st) {
     if (C % 4) return cudaErrorInvalidValue;
     if (rows <= 0) return cudaSuccess;
@@ -269,7 +314,7 @@ cudaError_t voc_launch_rmsnorm(const float* x, const float* w, float* y, int row
 // =====================================================================================
 __global__ void dwconv_ln_kernel(const float* __restrict__ x, const float* __restrict__ dw_w,
                                  const float* __restrict__ dw_b, const float* __restrict__ ln_w,
-                                 const float* __restrict__ ln_b, float* __restrict__ y, int L, int C,
+                                 const float* __restrict__ ln_b, VocAct y, int L, int C,
                                  int ksz, float eps) {
     extern __shared__ float sh[];          // C floats + 32 reduction slots
     float* h = sh;
@@ -301,12 +346,12 @@ __global__ void dwconv_ln_kernel(const float* __restrict__ x, const float* __res
     for (int c = threadIdx.x; c < C; c += blockDim.x) { const float d = h[c] - mean; lvar += d * d; }
     const float var = block_sum(lvar) / (float)C;
     const float inv = rsqrtf(var + eps);
-    float* yr = y + ((long long)b * L + t) * C;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) yr[c] = (h[c] - mean) * inv * ln_w[c] + ln_b[c];
+    const long long yo = ((long long)b * L + t) * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) act_store1(y, yo + c, (h[c] - mean) * inv * ln_w[c] + ln_b[c]);
 }
 
 cudaError_t voc_launch_dwconv_ln(const float* x, const float* dw_w, const float* dw_b, const float* ln_w,
-                                 const float* ln_b, float* y, int B, int L, int C, int ksz, float eps,
+                                 const float* ln_b, VocAct y, int B, int L, int C, int ksz, float eps,
                                  cudaStream_t st) {
     if (B <= 0 || L <= 0) return cudaSuccess;
     dim3 grid(L, B);
@@ -322,7 +367,7 @@ cudaError_t voc_launch_dwconv_ln(const float* x, const float* dw_w, const float*
 // =====================================================================================
 template <int HD>
 __global__ void __launch_bounds__(64)
-attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int T, int heads,
+attention_kernel(const float* __restrict__ qkv, VocAct out, int T, int heads,
                  const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, int window) {
     constexpr int H2 = HD / 2;
     __shared__ float Ks[64][HD + 1];
@@ -397,13 +442,14 @@ attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int T, 
     }
     if (qvalid) {
         const float inv = 1.f / l;
-        float* orow = out + ((long long)b * T + qi) * A + hh * HD;
+        const long long oo = ((long long)b * T + qi) * A + hh * HD;
 #pragma unroll
-        for (int d = 0; d < HD; ++d) orow[d] = o[d] * inv;
+        for (int d = 0; d < HD; d += 4)
+            act_store4(out, oo + d, make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv));
     }
 }
 
-cudaError_t voc_launch_attention(const float* qkv, float* out, int B, int T, int heads, int head_dim,
+cudaError_t voc_launch_attention(const float* qkv, VocAct out, int B, int T, int heads, int head_dim,
                                  const float* rope_cos, const float* rope_sin, int window,
                                  cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
@@ -418,17 +464,17 @@ cudaError_t voc_launch_attention(const float* qkv, float* out, int B, int T, int
 }
 
 // SwiGLU gate: out[r][i] = silu(gu[r][i]) * gu[r][inter+i]     (sibling :3442-3455)
-__global__ void swiglu_kernel(const float* __restrict__ gu, float* __restrict__ out, long long total,
+__global__ void swiglu_kernel(const float* __restrict__ gu, VocAct out, long long total,
                               int inter) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const long long r = i / inter;
     const int c = (int)(i - r * inter);
     const float g = gu[r * 2 * inter + c], u = gu[r * 2 * inter + inter + c];
-    out[i] = (g / (1.f + expf(-g))) * u;
+    act_store1(out, i, (g / (1.f + expf(-g))) * u);
 }
 
-cudaError_t voc_launch_swiglu(const float* gu, float* out, long long rows, int inter, cudaStream_t st) {
+cudaError_t voc_launch_swiglu(const float* gu, VocAct out, long long rows, int inter, cudaStream_t st) {
     const long long total = rows * inter;
     if (total <= 0) return cudaSuccess;
     swiglu_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(gu, out, total, inter);
@@ -442,7 +488,7 @@ cudaError_t voc_launch_swiglu(const float* gu, float* out, long long rows, int i
 // share one output sample (C/4 channels each) and reduce by shuffle.
 // =====================================================================================
 __global__ void __launch_bounds__(256)
-head_kernel(const float* __restrict__ S, long long s_bstride, int L, int C, int ksz,
+head_kernel(VocAct S, long long s_bstride, int L, int C, int ksz,
             const float* __restrict__ w /*[k][C]*/, float bias, float* __restrict__ out,
             long long o_bstride) {
     extern __shared__ float sh[];
@@ -451,12 +497,12 @@ head_kernel(const float* __restrict__ S, long long s_bstride, int L, int C, int 
     float* tile = sh;                       // (TT + ksz - 1) x CP
     float* ws = sh + (TT + ksz - 1) * CP;   // ksz x C
     const int b = blockIdx.y, t0 = blockIdx.x * TT;
-    const float* Sb = S + (long long)b * s_bstride;
+    const long long sb = (long long)b * s_bstride;
     const int rows = TT + ksz - 1;
     for (int idx = threadIdx.x; idx < rows * C; idx += blockDim.x) {
         const int r = idx / C, c = idx - r * C;
         const int t = t0 - (ksz - 1) + r;
-        tile[r * CP + c] = (t >= 0 && t < L) ? Sb[(long long)t * C + c] : 0.f;
+        tile[r * CP + c] = (t >= 0 && t < L) ? act_load1(S, sb + (long long)t * C + c) : 0.f;
     }
     for (int idx = threadIdx.x; idx < ksz * C; idx += blockDim.x) ws[idx] = w[idx];
     __syncthreads();
@@ -474,7 +520,7 @@ head_kernel(const float* __restrict__ S, long long s_bstride, int L, int C, int 
     if (part == 0 && t < L) out[(long long)b * o_bstride + t] = fminf(1.f, fmaxf(-1.f, acc + bias));
 }
 
-cudaError_t voc_launch_head(const float* S, long long s_bstride, int L, int C, int ksz, const float* w,
+cudaError_t voc_launch_head(VocAct S, long long s_bstride, int L, int C, int ksz, const float* w,
                             float bias, float* out, long long o_bstride, int B, cudaStream_t st) {
     if (C % 4) return cudaErrorInvalidValue;
     if (B <= 0 || L <= 0) return cudaSuccess;
@@ -576,5 +622,18 @@ cudaError_t voc_launch_pcm16(const float* in, short* out, long long n, cudaStrea
     if (n <= 0) return cudaSuccess;
     long long blocks = (n + 1023) / 1024; if (blocks > 148 * 16) blocks = 148 * 16;
     pcm16_kernel<<<(unsigned)blocks, 256, 0, st>>>(in, out, n);
+    return cudaGetLastError();
+}
+
+__global__ void unsplit_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, float* __restrict__ out,
+                               long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = __half2float(hi[i]) + __half2float(lo[i]);
+}
+
+cudaError_t voc_launch_unsplit(const __half* hi, const __half* lo, float* out, long long n, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    long long blocks = (n + 255) / 256; if (blocks > 148 * 16) blocks = 148 * 16;
+    unsplit_kernel<<<(unsigned)blocks, 256, 0, st>>>(hi, lo, out, n);
     return cudaGetLastError();
 }

@@ -1,0 +1,533 @@
+// Tensor-core tap-GEMM for sm_100a: tcgen05.mma with the accumulator in TMEM, operands staged in
+// shared memory by TMA, FP32-exact to ~2^-22 through a three-pass split-fp16 product.
+//
+//   acc[b, m, n] = sum_tap sum_k  A[b, m + a_row0 + tap_off[tap], k] * W[tap, n, k]
+//
+// (the contraction every dense layer of the vocoder maps onto; see voc_common.cuh).  M = time is
+// the MMA M dimension (128 rows per tile), N = output channels, both operands K-major:
+//   * A: activations, channels-last, two fp16 planes (hi, lo); 4-D tensor map {K, rows, window,
+//     plane}.  Rows outside [0, rows) -- the causal left padding and the tile overhang -- are
+//     zero-filled by the TMA unit, so there is no padding pass and no bounds code.
+//   * B: weights, two fp16 planes [plane][tap][N][K] of W * 2^wexp (the power-of-two scale keeps the
+//     lo plane out of the fp16 subnormals; the epilogue multiplies by 2^-wexp, which is exact).
+//   * D += Ahi*Bhi + Ahi*Blo + Alo*Bhi, FP32 accumulation in TMEM (north_star: "accumulation stays
+//     FP32"; measured 91 dB / 2.5e-5 end to end, oracle/precision_study.py).
+//
+// Tap reuse: for a k-tap causal conv the 128-row A tile *plus its halo of span = (k-1)*dilation
+// rows* is loaded once per K-chunk ("the time-axis halo staged in shared memory", north_star (3));
+// tap j then reads it through a shared-memory descriptor whose start address is shifted by
+// (tap_off[j] - min_off) rows.  That start is not aligned to the 8-row swizzle period; measured on
+// B200 the swizzle is applied to absolute shared-memory address bits, so the descriptor's base
+// offset stays 0 (tests/test_gpu_tapgemm.py).  Weights are streamed per (tap, K-chunk).
+//
+// One persistent CTA per SM, 10 warps: warp 0 = TMA producer, warp 1 = MMA issuer (one thread),
+// warps 2-9 = epilogue (TMEM -> registers -> bias / GELU / LayerScale / residual / SnakeBeta ->
+// float32 residual stream and split-fp16 operand for the next layer).  Two TMEM buffers let the
+// drain of one accumulation segment overlap the MMAs of the next.
+#include "voc_common.cuh"
+
+#include <cuda.h>
+
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int EPI_WARPS = 8;
+constexpr int TC_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int MAX_STAGES = 8;
+
+struct TcArgs {
+    int M, N, K, B, ntaps, a_row0;
+    int tap_off[VOC_MAX_TAPS];
+    int a_reuse, a_min_off, a_box_rows, seg_iters;
+    int m_tiles, n_tiles, k_chunks, total_tiles;
+    int SA, SB;
+    float wscale;
+    const float* bias;  int act;  const float* scale;
+    const float* R;  long long r_bstride;  int ldr;
+    float* Y;        long long y_bstride;  int ldy;
+    __half* S_hi;  __half* S_lo;  long long s_bstride;  int lds;
+    const float* sn_a;  const float* sn_invb;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* b, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a pipeline bug traps (an error the host sees) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+    if (mbar_try_wait(b, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(b, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("voc_b200 tc_gemm: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address and byte
+// offsets in 16-byte units, version 1 (Blackwell), LBO unused for swizzled K-major layouts,
+// SBO = one 8-row swizzle group, layout 2 = SWIZZLE_128B / 4 = SWIZZLE_64B.
+// Base offset (bits 49-51) stays 0 even for starts that are not aligned to the swizzle period.
+template <int BK>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
+    constexpr uint64_t SBO = (8u * BK * 2u) >> 4;
+    constexpr uint64_t LAYOUT = (BK == 64) ? 2 : 4;
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | (SBO << 32) | (1ull << 46) | (LAYOUT << 61);
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// ---------------------------------------------------------------------------------------------
+template <int BN, int BK>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ TcArgs a) {
+    static_assert(BN % 32 == 0 && BN >= 32 && BN <= 192, "UMMA N; BN/2 columns per epilogue thread");
+    static_assert(BK == 64 || BK == 32, "one swizzle atom per K-chunk");
+    constexpr int HN = BN / 2;                                // columns per epilogue thread
+    constexpr uint32_t ROWB = BK * 2;                         // bytes of one shared-memory row
+    constexpr uint32_t B_PLANE = BN * ROWB, B_STAGE = 2 * B_PLANE;
+    constexpr uint32_t TMEM_COLS = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = F16, both K-major
+    constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_a_full[MAX_STAGES], bar_a_empty[MAX_STAGES];
+    __shared__ __align__(8) uint64_t bar_b_full[MAX_STAGES], bar_b_empty[MAX_STAGES];
+    __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2];
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_plane = (uint32_t)a.a_box_rows * ROWB, a_stage = 2 * a_plane;
+    const uint32_t smA = smem_base, smB = smem_base + (uint32_t)a.SA * a_stage;
+    const int iters_per_tile = a.k_chunks * a.ntaps;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int i = 0; i < a.SA; ++i) { mbar_init(&bar_a_full[i], 1); mbar_init(&bar_a_empty[i], 1); }
+        for (int i = 0; i < a.SB; ++i) { mbar_init(&bar_b_full[i], 1); mbar_init(&bar_b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], EPI_WARPS); }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 1) tmem_alloc(&tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            int sa = 0, pa = 0, sb = 0, pb = 0;
+            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+                const int n_tile = tile % a.n_tiles, ml = tile / a.n_tiles;
+                const int m_tile = ml % a.m_tiles, b = ml / a.m_tiles;
+                const int row0 = m_tile * BM + a.a_row0, n0 = n_tile * BN;
+                for (int kc = 0; kc < a.k_chunks; ++kc) {
+                    for (int tap = 0; tap < a.ntaps; ++tap) {
+                        if (tap == 0 || !a.a_reuse) {
+                            mbar_wait(&bar_a_empty[sa], pa ^ 1);
+                            mbar_expect_tx(&bar_a_full[sa], a_stage);
+                            tma_load_4d(smA + sa * a_stage, &tmA, &bar_a_full[sa], kc * BK,
+                                        row0 + (a.a_reuse ? a.a_min_off : a.tap_off[tap]), b, 0);
+                            if (++sa == a.SA) { sa = 0; pa ^= 1; }
+                        }
+                        mbar_wait(&bar_b_empty[sb], pb ^ 1);
+                        mbar_expect_tx(&bar_b_full[sb], B_STAGE);
+                        tma_load_4d(smB + sb * B_STAGE, &tmB, &bar_b_full[sb], kc * BK, n0, tap, 0);
+                        if (++sb == a.SB) { sb = 0; pb ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ==================================
+        // The tensor core's FP32 accumulator truncates (measured: a shrink of ~0.25 ulp per
+        // accumulation, i.e. -23 dB end to end over chains of up to 1008 MMAs), so a TMEM buffer
+        // only ever holds a *segment* of seg_iters stages; the epilogue warps add the segments in
+        // registers with round-to-nearest.  Within a stage the two small cross terms go first.
+        if (lane == 0) {
+            int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pas = 0, cur_a = 0;
+            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+                uint32_t tmem_acc = 0, accum = 0;
+                int it = 0;
+                for (int kc = 0; kc < a.k_chunks; ++kc) {
+                    for (int tap = 0; tap < a.ntaps; ++tap, ++it) {
+                        if (it % a.seg_iters == 0) {
+                            mbar_wait(&bar_acc_empty[as], pas ^ 1);
+                            tc_fence_after();
+                            tmem_acc = tmem_base + (uint32_t)(as * BN);
+                            accum = 0;
+                        }
+                        if (tap == 0 || !a.a_reuse) {
+                            mbar_wait(&bar_a_full[sa], pa);
+                            cur_a = sa;
+                        }
+                        mbar_wait(&bar_b_full[sb], pb);
+                        tc_fence_after();
+                        // tap reuse: the descriptor simply starts row_off rows into the halo tile.  The
+                        // swizzle is a function of the absolute shared-memory address, so no base-offset
+                        // correction is applied (the documented (addr >> 7) & 7 value yields garbage).
+                        const uint32_t row_off = a.a_reuse ? (uint32_t)(a.tap_off[tap] - a.a_min_off) : 0u;
+                        const uint32_t a_base = smA + cur_a * a_stage + row_off * ROWB;
+                        const uint32_t b_base = smB + sb * B_STAGE;
+#pragma unroll
+                        for (int pass = 0; pass < 3; ++pass) {
+                            // (A plane, B plane): (hi,lo), (lo,hi), (hi,hi)
+                            const uint32_t ap = a_base + (pass == 1 ? a_plane : 0u);
+                            const uint32_t bp = b_base + (pass == 0 ? B_PLANE : 0u);
+#pragma unroll
+                            for (int ks = 0; ks < BK / 16; ++ks) {
+                                mma_f16_ss(tmem_acc, make_smem_desc<BK>(ap + ks * 32), make_smem_desc<BK>(bp + ks * 32),
+                                           IDESC, accum);
+                                accum = 1;
+                            }
+                        }
+                        mma_commit(&bar_b_empty[sb]);
+                        if (++sb == a.SB) { sb = 0; pb ^= 1; }
+                        if (tap == a.ntaps - 1 || !a.a_reuse) {
+                            mma_commit(&bar_a_empty[cur_a]);
+                            if (++sa == a.SA) { sa = 0; pa ^= 1; }
+                        }
+                        if ((it + 1) % a.seg_iters == 0 || it + 1 == iters_per_tile) {
+                            mma_commit(&bar_acc_full[as]);
+                            as ^= 1; if (as == 0) pas ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+        // ================================ epilogue ====================================
+        const int q = warp & 3;                       // the TMEM lane quadrant this warp can read
+        const int h = (warp - 2) >> 2;                // which half of the tile's columns
+        const int nseg = (iters_per_tile + a.seg_iters - 1) / a.seg_iters;
+        int as = 0, pas = 0;
+        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+            const int n_tile = tile % a.n_tiles, ml = tile / a.n_tiles;
+            const int m_tile = ml % a.m_tiles, b = ml / a.m_tiles;
+            const int m = m_tile * BM + q * 32 + lane, n0 = n_tile * BN + h * HN;
+            float acc[HN];
+#pragma unroll
+            for (int j = 0; j < HN; ++j) acc[j] = 0.f;
+            for (int seg = 0; seg < nseg; ++seg) {
+                mbar_wait(&bar_acc_full[as], pas);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + h * HN);
+#pragma unroll
+                for (int c = 0; c < HN; c += 32) {
+                    uint32_t r0[16], r1[16];
+                    tmem_ld16(taddr + c, r0);
+                    if (c + 16 < HN) tmem_ld16(taddr + c + 16, r1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[c + j] += __uint_as_float(r0[j]);
+                    if (c + 16 < HN) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) acc[c + 16 + j] += __uint_as_float(r1[j]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_acc_empty[as]);
+                as ^= 1; if (as == 0) pas ^= 1;
+            }
+            if (m >= a.M) continue;
+            const float* Rrow = a.R ? a.R + (long long)b * a.r_bstride + (long long)m * a.ldr + n0 : nullptr;
+            float* Yrow = a.Y ? a.Y + (long long)b * a.y_bstride + (long long)m * a.ldy + n0 : nullptr;
+            const long long soff = (long long)b * a.s_bstride + (long long)m * a.lds + n0;
+#pragma unroll
+            for (int g = 0; g < HN; g += 8) {
+                const int n = n0 + g;
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = acc[g + j] * a.wscale;
+                if (a.bias) {
+                    const float4 b0 = ldg4(a.bias + n), b1 = ldg4(a.bias + n + 4);
+                    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                }
+                if (a.act == VOC_ACT_GELU) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = voc_gelu(v[j]);
+                }
+                if (a.scale) {
+                    const float4 s0 = ldg4(a.scale + n), s1 = ldg4(a.scale + n + 4);
+                    v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w;
+                    v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
+                }
+                if (Rrow) {
+                    const float4 r0 = *reinterpret_cast<const float4*>(Rrow + g);
+                    const float4 r1 = *reinterpret_cast<const float4*>(Rrow + g + 4);
+                    v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
+                    v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+                }
+                if (Yrow) {
+                    *reinterpret_cast<float4*>(Yrow + g) = make_float4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<float4*>(Yrow + g + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                }
+                if (a.S_hi) {
+                    if (a.sn_a) {
+                        const float4 a0 = ldg4(a.sn_a + n), a1 = ldg4(a.sn_a + n + 4);
+                        const float4 i0 = ldg4(a.sn_invb + n), i1 = ldg4(a.sn_invb + n + 4);
+                        v[0] = voc_snake(v[0], a0.x, i0.x); v[1] = voc_snake(v[1], a0.y, i0.y);
+                        v[2] = voc_snake(v[2], a0.z, i0.z); v[3] = voc_snake(v[3], a0.w, i0.w);
+                        v[4] = voc_snake(v[4], a1.x, i1.x); v[5] = voc_snake(v[5], a1.y, i1.y);
+                        v[6] = voc_snake(v[6], a1.z, i1.z); v[7] = voc_snake(v[7], a1.w, i1.w);
+                    }
+                    __half2 hh[4], ll[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) voc_split2(v[2 * j], v[2 * j + 1], hh[j], ll[j]);
+                    *reinterpret_cast<uint4*>(a.S_hi + soff + g) = *reinterpret_cast<const uint4*>(hh);
+                    *reinterpret_cast<uint4*>(a.S_lo + soff + g) = *reinterpret_cast<const uint4*>(ll);
+                }
+            }
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor maps (cuTensorMapEncodeTiled, resolved at run time so the library links
+// against cudart only), stage planning, launch
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+using MapKey = std::tuple<const void*, long long, long long, long long, long long, long long, long long, int, int, int>;
+std::mutex g_map_mu;
+std::map<MapKey, CUtensorMap> g_maps;
+
+// 4-D fp16 tensor {d0 (contiguous), d1, d2, 2 planes}, box {bk, box_rows, 1, 2}
+bool get_map(const void* base, long long d0, long long d1, long long d2, long long s1, long long s2, long long s3,
+             int bk, int box_rows, CUtensorMap* out) {
+    const MapKey key{base, d0, d1, d2, s1, s2, s3, bk, box_rows, 0};
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return true; }
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2, 2};
+    const cuuint64_t strides[3] = {(cuuint64_t)s1, (cuuint64_t)s2, (cuuint64_t)s3};   // bytes, dims 1..3
+    const cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)box_rows, 1, 2};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUtensorMap m;
+    const CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        fprintf(stderr, "voc_b200: cuTensorMapEncodeTiled failed (%d) dims {%lld,%lld,%lld,2} strides {%lld,%lld,%lld} box {%d,%d}\n",
+                (int)r, d0, d1, d2, s1, s2, s3, bk, box_rows);
+        return false;
+    }
+    g_maps[key] = m;
+    *out = m;
+    return true;
+}
+
+int pick_bn(int N) {
+    static const int cand[] = {192, 128, 96, 64, 32};
+    for (int c : cand) if (N % c == 0) return c;
+    return 0;
+}
+
+constexpr int SMEM_BUDGET = 232448 - 1024 - 1024;   // opt-in maximum minus alignment slack and static smem
+
+template <int BN, int BK>
+cudaError_t launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, int grid, size_t smem,
+                        cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             232448 - 1024);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    tapgemm_tc_kernel<BN, BK><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, a);
+    return cudaGetLastError();
+}
+
+template <int BK>
+cudaError_t launch_bn(int BN, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, int grid, size_t smem,
+                      cudaStream_t st) {
+    switch (BN) {
+        case 192: return launch_inst<192, BK>(tmA, tmB, a, grid, smem, st);
+        case 128: return launch_inst<128, BK>(tmA, tmB, a, grid, smem, st);
+        case 96:  return launch_inst<96, BK>(tmA, tmB, a, grid, smem, st);
+        case 64:  return launch_inst<64, BK>(tmA, tmB, a, grid, smem, st);
+        case 32:  return launch_inst<32, BK>(tmA, tmB, a, grid, smem, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace
+
+bool voc_tc_eligible(const TapGemmParams& p) {
+    if (!p.A_hi || !p.A_lo || !p.Wtc || p.S) return false;
+    if (p.K % 8 || p.lda % 8 || p.N % 32 || p.K < 16) return false;
+    if (p.ntaps < 1 || p.ntaps > VOC_MAX_TAPS) return false;
+    if (p.Y && (p.ldy % 4)) return false;
+    if (p.R && (p.ldr % 4)) return false;
+    if (p.S_hi && (p.lds % 8 || p.s_bstride % 8)) return false;
+    if (p.B > 1 && (p.a_bstride % 8)) return false;
+    if ((p.A_lo - p.A_hi) % 8 || p.A_lo <= p.A_hi || p.wtc_plane % 8) return false;
+    if ((reinterpret_cast<uintptr_t>(p.A_hi) | reinterpret_cast<uintptr_t>(p.Wtc)) & 15) return false;
+    int mn = 0, mx = 0;
+    for (int i = 0; i < p.ntaps; ++i) { mn = std::min(mn, p.tap_off[i]); mx = std::max(mx, p.tap_off[i]); }
+    if (mx - mn > 112) return false;           // halo tile: 128 + span rows <= 256 (one TMA box)
+    return encode_fn() != nullptr;
+}
+
+void voc_tc_clear_cache() {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    g_maps.clear();
+}
+
+cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int num_sms, int flags) {
+    if (!voc_tc_eligible(p)) return cudaErrorNotSupported;
+    if (p.M <= 0 || p.B <= 0) return cudaSuccess;
+    const int BN = pick_bn(p.N);
+    int BK = (p.K % 64 == 0 || p.K % 64 > 32) ? 64 : 32;
+    if (flags & VOC_TC_BK32) BK = 32;
+
+    TcArgs a;
+    memset(&a, 0, sizeof(a));
+    a.M = p.M; a.N = p.N; a.K = p.K; a.B = p.B; a.ntaps = p.ntaps; a.a_row0 = p.a_row0;
+    int mn = p.tap_off[0], mx = p.tap_off[0];
+    for (int i = 0; i < p.ntaps; ++i) { a.tap_off[i] = p.tap_off[i]; mn = std::min(mn, p.tap_off[i]); mx = std::max(mx, p.tap_off[i]); }
+    a.a_reuse = (p.ntaps > 1 && !(flags & VOC_TC_NO_REUSE)) ? 1 : 0;
+    a.a_min_off = mn;
+    a.a_box_rows = a.a_reuse ? ((BM + (mx - mn) + 15) / 16) * 16 : BM;
+    // MMAs accumulated in the tensor core before a round-to-nearest flush (bits 8.. of flags, default 12)
+    const int seg_mmas = (flags >> 8) > 0 ? (flags >> 8) : 12;
+    a.seg_iters = std::max(1, seg_mmas / (3 * BK / 16));
+    a.m_tiles = (p.M + BM - 1) / BM; a.n_tiles = p.N / BN; a.k_chunks = (p.K + BK - 1) / BK;
+    a.total_tiles = a.m_tiles * a.n_tiles * p.B;
+    a.wscale = p.wscale;
+    a.bias = p.bias; a.act = p.act; a.scale = p.scale;
+    a.R = p.R; a.r_bstride = p.r_bstride; a.ldr = p.ldr;
+    a.Y = p.Y; a.y_bstride = p.y_bstride; a.ldy = p.ldy;
+    a.S_hi = p.S_hi; a.S_lo = p.S_lo; a.s_bstride = p.s_bstride; a.lds = p.lds;
+    a.sn_a = p.sn_a; a.sn_invb = p.sn_invb;
+
+    // stage plan
+    const int a_stage = 2 * a.a_box_rows * BK * 2, b_stage = 2 * BN * BK * 2;
+    if (a.a_reuse) {
+        a.SA = 2;
+        a.SB = std::min(MAX_STAGES, (SMEM_BUDGET - a.SA * a_stage) / b_stage);
+    } else {
+        a.SA = a.SB = std::min(MAX_STAGES, SMEM_BUDGET / (a_stage + b_stage));
+    }
+    if (a.SB < 2 || a.SA < 1) return cudaErrorNotSupported;
+    const size_t smem = (size_t)a.SA * a_stage + (size_t)a.SB * b_stage + 1024;
+
+    // tensor maps
+    CUtensorMap tmA, tmB;
+    const long long a_bs = p.B > 1 ? p.a_bstride : (long long)p.a_rows * p.lda;
+    const long long a_plane = (long long)(p.A_lo - p.A_hi);
+    if (a_plane % 8 || a_plane <= 0) return cudaErrorInvalidValue;
+    if (!get_map(p.A_hi, p.K, p.a_rows, p.B, (long long)p.lda * 2, a_bs * 2, a_plane * 2, BK, a.a_box_rows, &tmA))
+        return cudaErrorInvalidValue;
+    if (!get_map(p.Wtc, p.K, p.N, p.ntaps, (long long)p.K * 2, (long long)p.N * p.K * 2, p.wtc_plane * 2, BK, BN, &tmB))
+        return cudaErrorInvalidValue;
+
+    const int grid = std::min(a.total_tiles, num_sms > 0 ? num_sms : 148);
+    if (BK == 64) return launch_bn<64>(BN, tmA, tmB, a, grid, smem, st);
+    return launch_bn<32>(BN, tmA, tmB, a, grid, smem, st);
+}

@@ -1,6 +1,7 @@
 // Shared declarations for the B200 vocoder library (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -29,8 +30,17 @@
 // Epilogue:  v = acc + bias[n];  act;  v *= scale[n];  v += R[b,m,n];
 //            Y[b,m,n] = v (optional);   S[b,m,n] = snake(v; sn_a[n], sn_invb[n]) (optional).
 // ------------------------------------------------------------------------------------
+//
+// Operand formats.  The FP32 CUDA-core path keeps every operand in float32.  The tensor-core
+// path keeps every *GEMM operand* as two float16 planes (hi = fp16(x), lo = fp16(x - hi)), which
+// occupy exactly the bytes of the float32 tensor they replace; three tcgen05 MMAs
+// (hi*hi + hi*lo + lo*hi) with FP32 accumulation in TMEM then reproduce the FP32 product to
+// ~2^-22 relative (oracle/precision_study.py: 91 dB / 2.5e-5 on the full window, against the
+// 60 dB / 1e-4 gate; a single bf16 or tf32 pass fails it).  The residual stream (Y, R) is
+// always float32.  A_hi/A_lo (when non-null) replace A; S_hi/S_lo replace S.
 struct TapGemmParams {
     const float* A;  long long a_bstride;  int a_rows;  int lda;  int K;
+    const __half* A_hi;  const __half* A_lo;
     int a_row0;  int ntaps;  int tap_off[VOC_MAX_TAPS];
     const float* W;      // SIMT path: [ntaps*K][N], n contiguous
     int N;  int M;  int B;
@@ -40,7 +50,10 @@ struct TapGemmParams {
     const float* R;  long long r_bstride;  int ldr;
     float* Y;        long long y_bstride;  int ldy;
     float* S;        long long s_bstride;  int lds;
-    const float* sn_a;  const float* sn_invb;   // [N]: exp(alpha), 1/(exp(beta)+eps)
+    __half* S_hi;  __half* S_lo;                // split-fp16 form of S (same strides)
+    const float* sn_a;  const float* sn_invb;   // [N]: exp(alpha), 1/(exp(beta)+eps); null = S is v itself
+    // tensor-core form of the weights (tc_gemm.cu): two fp16 planes [2][ntaps][N][K] of W * 2^wexp
+    const __half* Wtc;  long long wtc_plane;  float wscale;   // wscale = 2^-wexp
 };
 
 enum { VOC_ACT_NONE = 0, VOC_ACT_GELU = 1 };
@@ -72,21 +85,48 @@ __device__ __forceinline__ float voc_gelu(float x) {
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
 }
 
+// fp32 -> (hi, lo) float16 pair; saturating so that a stray huge activation cannot become inf
+__device__ __forceinline__ void voc_split2(float a, float b, __half2& hi, __half2& lo) {
+    a = fminf(65504.f, fmaxf(-65504.f, a));
+    b = fminf(65504.f, fmaxf(-65504.f, b));
+    hi = __floats2half2_rn(a, b);
+    const float2 h = __half22float2(hi);
+    lo = __floats2half2_rn(a - h.x, b - h.y);
+}
+__device__ __forceinline__ void voc_split1(float a, __half& hi, __half& lo) {
+    a = fminf(65504.f, fmaxf(-65504.f, a));
+    hi = __float2half_rn(a);
+    lo = __float2half_rn(a - __half2float(hi));
+}
+
+// An activation tensor as the kernels see it: float32 (f) or split float16 (hi, lo).
+struct VocAct {
+    float* f;  __half* hi;  __half* lo;
+};
+
+// host-side launch wrappers (tc_gemm.cu): returns cudaErrorNotSupported when the shape is not
+// eligible for the tensor-core kernel (the caller then uses the CUDA-core kernel)
+bool voc_tc_eligible(const TapGemmParams& p);
+cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int num_sms, int flags);
+void voc_tc_clear_cache();
+// flags: bit 0 no tap reuse, bit 2 force 32-wide K chunks, bits 8.. MMAs per accumulation segment
+enum { VOC_TC_NO_REUSE = 1, VOC_TC_BK32 = 4 };
+
 // host-side launch wrappers (simt_kernels.cu)
 cudaError_t voc_launch_tapgemm_simt(const TapGemmParams& p, cudaStream_t st);
 cudaError_t voc_launch_rvq_gather(const long long* codes, int n_frames, int frames_per_win, int win_step,
                                   int n_windows, int n_q, int codebook_size, const float* tables,
-                                  int dim, float* out, int* err_flag, cudaStream_t st);
-cudaError_t voc_launch_rmsnorm(const float* x, const float* w, float* y, int rows, int C, float eps,
+                                  int dim, VocAct out, int* err_flag, cudaStream_t st);
+cudaError_t voc_launch_rmsnorm(const float* x, const float* w, VocAct y, int rows, int C, float eps,
                                cudaStream_t st);
 cudaError_t voc_launch_dwconv_ln(const float* x, const float* dw_w, const float* dw_b, const float* ln_w,
-                                 const float* ln_b, float* y, int B, int L, int C, int ksz, float eps,
+                                 const float* ln_b, VocAct y, int B, int L, int C, int ksz, float eps,
                                  cudaStream_t st);
-cudaError_t voc_launch_attention(const float* qkv, float* out, int B, int T, int heads, int head_dim,
+cudaError_t voc_launch_attention(const float* qkv, VocAct out, int B, int T, int heads, int head_dim,
                                  const float* rope_cos, const float* rope_sin, int window,
                                  cudaStream_t st);
-cudaError_t voc_launch_swiglu(const float* gu, float* out, long long rows, int inter, cudaStream_t st);
-cudaError_t voc_launch_head(const float* S, long long s_bstride, int L, int C, int ksz, const float* w,
+cudaError_t voc_launch_swiglu(const float* gu, VocAct out, long long rows, int inter, cudaStream_t st);
+cudaError_t voc_launch_head(VocAct S, long long s_bstride, int L, int C, int ksz, const float* w,
                             float bias, float* out, long long o_bstride, int B, cudaStream_t st);
 cudaError_t voc_launch_stitch(const float* chunks, long long chunk_stride, const int* win_meta,
                               int n_windows, int ov, const float* fade_out, const float* fade_in,
@@ -95,3 +135,5 @@ cudaError_t voc_launch_append_window(float* res, long long res_len, const float*
                                      int blend, const float* fade_out, const float* fade_in,
                                      cudaStream_t st);
 cudaError_t voc_launch_pcm16(const float* in, short* out, long long n, cudaStream_t st);
+// split-fp16 -> float32 (debug captures of operand tensors)
+cudaError_t voc_launch_unsplit(const __half* hi, const __half* lo, float* out, long long n, cudaStream_t st);

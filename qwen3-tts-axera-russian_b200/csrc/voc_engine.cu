@@ -138,7 +138,10 @@ struct DevBuf {
 };
 
 struct GemmW {                 // one dense layer, kernel-ready
-    float* W = nullptr;        // [ntaps*K][N]
+    float* W = nullptr;        // CUDA-core form  [ntaps*K][N]
+    __half* Wtc = nullptr;     // tensor-core form [2 planes][ntaps][N][K] of W * 2^wexp (hi, lo)
+    long long wtc_plane = 0;   // elements per plane
+    float wscale = 1.f;        // 2^-wexp
     float* bias = nullptr;     // [N] or null
     int K = 0, N = 0, ntaps = 1;
     int tap_off[VOC_MAX_TAPS] = {0};
@@ -155,11 +158,15 @@ struct Engine {
     std::string err;
     long long launches = 0;
     bool finalized = false;
-    int gemm_mode = 0;          // 0 auto, 1 simt, 2 tc
+    int gemm_mode = 0;          // 0 auto (= tc), 1 simt (FP32 CUDA cores), 2 tc (tcgen05, split fp16)
+    int tc_flags = 0;           // VOC_TC_* experiment switches
+    int num_sms = 148;
     bool debug = false;
+    bool tc() const { return gemm_mode != 1; }
+    std::map<const float*, size_t> cap;              // capacity (elements) of every activation buffer
 
     std::map<std::string, std::vector<float>> raw;   // host staging until finalize
-    std::vector<float*> owned;                        // device allocations (weights)
+    std::vector<void*> owned;                         // device allocations (weights)
 
     // kernel-ready weights
     float* rvq_tables = nullptr;                      // [16][codebook][rvq_dim]
@@ -197,7 +204,7 @@ struct Engine {
     }
 
     ~Engine() {
-        for (float* p : owned) cudaFree(p);
+        for (void* p : owned) cudaFree(p);
         if (d_err) cudaFree(d_err);
         if (d_meta) cudaFree(d_meta);
         if (d_fade_out) cudaFree(d_fade_out);
@@ -248,6 +255,41 @@ static float* upload(Engine* E, const std::vector<float>& v) {
     return d;
 }
 
+// Tensor-core form of a weight matrix given its CUDA-core form t[(tap*K + k)*N + n]:
+// two fp16 planes [plane][tap][n][k] of t * 2^wexp, wexp chosen so that max|t| * 2^wexp is in
+// [2^11, 2^12): hi is far from overflow and lo = fp16(w - hi) stays a normal number for every
+// weight within 2^-14 of the largest.
+static bool make_wtc(Engine* E, const std::vector<float>& t, GemmW& g) {
+    const size_t n = t.size();
+    float mx = 0.f;
+    for (float v : t) mx = std::max(mx, std::fabs(v));
+    int wexp = 0;
+    if (mx > 0.f && std::isfinite(mx)) { int e; std::frexp(mx, &e); wexp = 12 - e; }   // mx = f * 2^e, f in [0.5,1)
+    const float up = std::ldexp(1.0f, wexp);
+    g.wscale = std::ldexp(1.0f, -wexp);
+    g.wtc_plane = (long long)n;
+    std::vector<__half> h(2 * n);
+    const int K = g.K, N = g.N;
+    for (int tap = 0; tap < g.ntaps; ++tap)
+        for (int k = 0; k < K; ++k) {
+            const float* src = &t[((size_t)tap * K + k) * N];
+            for (int nn = 0; nn < N; ++nn) {
+                const float w = src[nn] * up;
+                const __half hi = __float2half_rn(w);
+                const __half lo = __float2half_rn(w - __half2float(hi));
+                const size_t o = ((size_t)tap * N + nn) * K + k;
+                h[o] = hi; h[n + o] = lo;
+            }
+        }
+    __half* d = nullptr;
+    if (cudaMalloc(&d, h.size() * sizeof(__half)) != cudaSuccess) return false;
+    E->owned.push_back(d);
+    if (cudaMemcpyAsync(d, h.data(), h.size() * sizeof(__half), cudaMemcpyHostToDevice, E->stream) != cudaSuccess) return false;
+    if (cudaStreamSynchronize(E->stream) != cudaSuccess) return false;     // h goes out of scope
+    g.Wtc = d;
+    return true;
+}
+
 static const std::vector<float>* get_raw(Engine* E, const std::string& name, size_t n) {
     auto it = E->raw.find(name);
     if (it == E->raw.end()) { E->err = "missing tensor " + name; return nullptr; }
@@ -262,6 +304,7 @@ static bool make_conv(Engine* E, const std::string& p, int Co, int Ci, int K, in
     for (int co = 0; co < Co; ++co) for (int ci = 0; ci < Ci; ++ci) for (int j = 0; j < K; ++j)
         t[((size_t)j * Ci + ci) * Co + co] = (*w)[((size_t)co * Ci + ci) * K + j];
     g.W = upload(E, t); g.K = Ci; g.N = Co; g.ntaps = K;
+    if (!make_wtc(E, t, g)) return false;
     for (int j = 0; j < K; ++j) g.tap_off[j] = -(K - 1 - j) * dil;
     if (has_bias) { auto* b = get_raw(E, p + ".b", Co); if (!b) return false; g.bias = upload(E, *b); if (!g.bias) return false; }
     return g.W != nullptr;
@@ -276,6 +319,7 @@ static bool make_linear(Engine* E, const std::vector<std::string>& names, int ou
             t[(size_t)i * N + s * out_each + o] = (*w)[(size_t)o * in + i];
     }
     g.W = upload(E, t); g.K = in; g.N = N; g.ntaps = 1; g.tap_off[0] = 0;
+    if (!make_wtc(E, t, g)) return false;
     if (bias_name) { auto* b = get_raw(E, bias_name, N); if (!b) return false; g.bias = upload(E, *b); if (!g.bias) return false; }
     return g.W != nullptr;
 }
@@ -291,6 +335,7 @@ static bool make_convt(Engine* E, const std::string& p, int Ci, int Co, int k, i
     std::vector<float> bt(N);
     for (int ph = 0; ph < s; ++ph) for (int co = 0; co < Co; ++co) bt[ph * Co + co] = (*b)[co];
     g.W = upload(E, t); g.bias = upload(E, bt); g.K = Ci; g.N = N; g.ntaps = taps;
+    if (!make_wtc(E, t, g)) return false;
     g.tap_off[0] = 0; g.tap_off[1] = -1;
     return g.W && g.bias;
 }
@@ -318,26 +363,49 @@ static cudaError_t run_gemm(Engine* E, TapGemmParams& p, cudaStream_t st, const 
     if (p.S) bytes += 4.0 * p.B * (double)p.M * p.N;
     if (p.R) bytes += 4.0 * p.B * (double)p.M * p.N;
     ProfScope ps(E, st, tag, flops, bytes);
+    if (E->tc() && voc_tc_eligible(p)) {
+        const cudaError_t e = voc_launch_tapgemm_tc(p, st, E->num_sms, E->tc_flags);
+        if (e != cudaErrorNotSupported) return e;
+        (void)cudaGetLastError();
+    }
     return voc_launch_tapgemm_simt(p, st);
 }
 
-static TapGemmParams gp(const GemmW& g, const float* A, long long a_bs, int a_rows, int a_row0, int M, int B) {
+// An activation buffer in the format of the current mode: float32 on the CUDA-core path, two
+// fp16 planes (hi at the base, lo `capacity` halves later -- the same bytes) on the tensor path.
+static VocAct act(Engine* E, float* base) {
+    VocAct a{nullptr, nullptr, nullptr};
+    if (!E->tc()) { a.f = base; return a; }
+    a.hi = reinterpret_cast<__half*>(base);
+    a.lo = a.hi + E->cap.at(base);
+    return a;
+}
+static VocAct act_f32(float* base) { return VocAct{base, nullptr, nullptr}; }
+
+static TapGemmParams gp(const GemmW& g, VocAct A, long long a_bs, int a_rows, int a_row0, int M, int B) {
     TapGemmParams p;
     memset(&p, 0, sizeof(p));
-    p.A = A; p.a_bstride = a_bs; p.a_rows = a_rows; p.lda = g.K; p.K = g.K; p.a_row0 = a_row0;
+    p.A = A.f; p.A_hi = A.hi; p.A_lo = A.lo;
+    p.a_bstride = a_bs; p.a_rows = a_rows; p.lda = g.K; p.K = g.K; p.a_row0 = a_row0;
     p.ntaps = g.ntaps; for (int i = 0; i < VOC_MAX_TAPS; ++i) p.tap_off[i] = g.tap_off[i];
-    p.W = g.W; p.N = g.N; p.M = M; p.B = B; p.bias = g.bias;
+    p.W = g.W; p.Wtc = g.Wtc; p.wtc_plane = g.wtc_plane; p.wscale = g.wscale;
+    p.N = g.N; p.M = M; p.B = B; p.bias = g.bias;
     return p;
 }
 static void setY(TapGemmParams& p, float* Y) { p.Y = Y; p.ldy = p.N; p.y_bstride = (long long)p.M * p.N; }
-static void setS(TapGemmParams& p, float* S, const SnakeP& sp) { p.S = S; p.lds = p.N; p.s_bstride = (long long)p.M * p.N; p.sn_a = sp.a; p.sn_invb = sp.invb; }
+// S = snake(v) (sp given) or v itself (sp null), in the operand format of the mode
+static void setS(TapGemmParams& p, VocAct S, const SnakeP* sp) {
+    p.S = S.f; p.S_hi = S.hi; p.S_lo = S.lo; p.lds = p.N; p.s_bstride = (long long)p.M * p.N;
+    p.sn_a = sp ? sp->a : nullptr; p.sn_invb = sp ? sp->invb : nullptr;
+}
 static void setR(TapGemmParams& p, const float* R) { p.R = R; p.ldr = p.N; p.r_bstride = (long long)p.M * p.N; }
 
-static int dbg_capture(Engine* E, const char* name, const float* src, size_t n, cudaStream_t st) {
+static int dbg_capture(Engine* E, const char* name, VocAct src, size_t n, cudaStream_t st) {
     if (!E->debug) return VOC_OK;
     auto b = std::make_shared<DevBuf>();
     CK(cudaMalloc(&b->p, n * sizeof(float))); b->n = n;
-    CK(cudaMemcpyAsync(b->p, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (src.f) CK(cudaMemcpyAsync(b->p, src.f, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    else CK(voc_launch_unsplit(src.hi, src.lo, b->p, (long long)n, st));
     E->dbg[name] = {b, n};
     return VOC_OK;
 }
@@ -363,7 +431,7 @@ static int engine_finalize(Engine* E) {
         for (int q = 0; q < c.num_quantizers; ++q) {
             float* cb = upload_named(E, "rvq.codebook." + std::to_string(q), (size_t)c.codebook_size * c.codebook_dim);
             REQ(cb);
-            TapGemmParams p = gp(q < c.num_semantic ? ps : pa, cb, 0, c.codebook_size, 0, c.codebook_size, 1);
+            TapGemmParams p = gp(q < c.num_semantic ? ps : pa, act_f32(cb), 0, c.codebook_size, 0, c.codebook_size, 1);
             setY(p, tables + q * tbl);
             CK(run_gemm(E, p, E->stream));
         }
@@ -466,6 +534,11 @@ static int engine_finalize(Engine* E) {
     E->f_rvq = f + o_rvq; E->f_pre = f + o_pre; E->f_h = f + o_h; E->f_hn = f + o_hn; E->f_qkv = f + o_qkv;
     E->f_att = f + o_att; E->f_gu = f + o_gu; E->f_act = f + o_act; E->f_x = f + o_x; E->f_x2 = f + o_x2;
     E->f_ln = f + o_ln; E->f_mid = f + o_mid;
+    E->cap[E->f_rvq] = (size_t)W * T * c.rvq_dim;      E->cap[E->f_pre] = (size_t)W * T * c.latent_dim;
+    E->cap[E->f_hn] = (size_t)W * T * c.xf_hidden;     E->cap[E->f_att] = (size_t)W * T * c.attn_dim();
+    E->cap[E->f_act] = (size_t)W * T * c.xf_inter;     E->cap[E->f_x] = (size_t)W * Tup * c.latent_dim;
+    E->cap[E->f_x2] = (size_t)W * Tup * c.latent_dim;  E->cap[E->f_ln] = (size_t)W * Tup * c.latent_dim;
+    E->cap[E->f_mid] = (size_t)W * Tup * c.latent_dim * c.convnext_mult;
     size_t mx = (size_t)Tup * c.decoder_dim;
     int L = Tup;
     for (size_t b = 0; b < c.upsample_rates.size(); ++b) {
@@ -474,7 +547,10 @@ static int engine_finalize(Engine* E) {
         mx = std::max(mx, (size_t)L * (c.decoder_dim >> (b + 1)));
     }
     E->big_elems = mx;
-    for (int i = 0; i < 3; ++i) { CK(cudaMalloc(&E->big[i].p, mx * W * sizeof(float))); E->big[i].n = mx * W; }
+    for (int i = 0; i < 3; ++i) {
+        CK(cudaMalloc(&E->big[i].p, mx * W * sizeof(float))); E->big[i].n = mx * W;
+        E->cap[E->big[i].p] = mx * W;
+    }
     CK(cudaMalloc(&E->d_err, sizeof(int)));
 
     // ---- crossfade tables (fade_tables below restates numpy's linspace)
@@ -502,69 +578,77 @@ static int run_wave(Engine* E, const long long* d_codes, int n_frames, int win_s
     const int T = c.chunk_frames;
 #define KLAUNCH(tag, flops, bytes, call) do { ProfScope _ps(E, st, tag, flops, bytes); CK(call); } while (0)
 #define GEMM(tag, p) CK(run_gemm(E, p, st, tag))
+    // Operand tensors (everything a GEMM reads) are in the mode's operand format -- act(); the
+    // residual streams (f_h, the up-sampled x while ConvNeXt needs it, bX) and the tensors the
+    // non-GEMM kernels read (f_qkv, f_gu) stay float32.
     // K1: RVQ gather-sum
     KLAUNCH("rvq_gather", 0.0, 4.0 * nw * T * c.rvq_dim * (c.num_quantizers + 1.0),
             voc_launch_rvq_gather(d_codes + (long long)w_begin * win_step * c.num_quantizers,
                                   n_frames - w_begin * win_step, T, win_step, nw, c.num_quantizers,
-                                  c.codebook_size, E->rvq_tables, c.rvq_dim, E->f_rvq, E->d_err, st));
-    if (int r = dbg_capture(E, "rvq", E->f_rvq, (size_t)nw * T * c.rvq_dim, st)) return r;
+                                  c.codebook_size, E->rvq_tables, c.rvq_dim, act(E, E->f_rvq), E->d_err, st));
+    if (int r = dbg_capture(E, "rvq", act(E, E->f_rvq), (size_t)nw * T * c.rvq_dim, st)) return r;
     // K2: pre-conv
     {
-        TapGemmParams p = gp(E->pre_conv, E->f_rvq, (long long)T * c.rvq_dim, T, 0, T, nw);
-        setY(p, E->f_pre);
+        TapGemmParams p = gp(E->pre_conv, act(E, E->f_rvq), (long long)T * c.rvq_dim, T, 0, T, nw);
+        setS(p, act(E, E->f_pre), nullptr);
         GEMM("pre_conv", p);
     }
-    if (int r = dbg_capture(E, "pre_conv", E->f_pre, (size_t)nw * T * c.latent_dim, st)) return r;
-    float* x = E->f_pre;                 // [nw][T][latent]
+    if (int r = dbg_capture(E, "pre_conv", act(E, E->f_pre), (size_t)nw * T * c.latent_dim, st)) return r;
+    float* x = E->f_pre;                 // [nw][T][latent], operand format
     if (c.pre_transformer) {
         const int rows = nw * T, H = c.xf_hidden, A = c.attn_dim();
         const double nb = 8.0 * rows * H;
-        { TapGemmParams p = gp(E->xf_in, x, 0, rows, 0, rows, 1); setY(p, E->f_h); GEMM("xf.gemm", p); }
+        { TapGemmParams p = gp(E->xf_in, act(E, x), 0, rows, 0, rows, 1); setY(p, E->f_h); GEMM("xf.gemm", p); }
         for (int l = 0; l < c.xf_layers; ++l) {
             auto& Ly = E->xf[l];
-            KLAUNCH("xf.norm", 0.0, nb, voc_launch_rmsnorm(E->f_h, Ly.ln1, E->f_hn, rows, H, (float)c.rms_eps, st));
-            { TapGemmParams p = gp(Ly.qkv, E->f_hn, 0, rows, 0, rows, 1); setY(p, E->f_qkv); GEMM("xf.gemm", p); }
+            KLAUNCH("xf.norm", 0.0, nb, voc_launch_rmsnorm(E->f_h, Ly.ln1, act(E, E->f_hn), rows, H, (float)c.rms_eps, st));
+            { TapGemmParams p = gp(Ly.qkv, act(E, E->f_hn), 0, rows, 0, rows, 1); setY(p, E->f_qkv); GEMM("xf.gemm", p); }
             KLAUNCH("xf.attn", 4.0 * nw * c.xf_heads * (double)T * T * c.xf_head_dim / 2, 16.0 * rows * A,
-                    voc_launch_attention(E->f_qkv, E->f_att, nw, T, c.xf_heads, c.xf_head_dim, E->rope_cos, E->rope_sin, c.sliding_window, st));
-            { TapGemmParams p = gp(Ly.o, E->f_att, 0, rows, 0, rows, 1); p.scale = Ly.ls_attn; setR(p, E->f_h); setY(p, E->f_h); GEMM("xf.gemm", p); }
-            KLAUNCH("xf.norm", 0.0, nb, voc_launch_rmsnorm(E->f_h, Ly.ln2, E->f_hn, rows, H, (float)c.rms_eps, st));
-            { TapGemmParams p = gp(Ly.gu, E->f_hn, 0, rows, 0, rows, 1); setY(p, E->f_gu); GEMM("xf.gemm", p); }
-            KLAUNCH("xf.swiglu", 0.0, 12.0 * rows * c.xf_inter, voc_launch_swiglu(E->f_gu, E->f_act, rows, c.xf_inter, st));
-            { TapGemmParams p = gp(Ly.down, E->f_act, 0, rows, 0, rows, 1); p.scale = Ly.ls_mlp; setR(p, E->f_h); setY(p, E->f_h); GEMM("xf.gemm", p); }
+                    voc_launch_attention(E->f_qkv, act(E, E->f_att), nw, T, c.xf_heads, c.xf_head_dim, E->rope_cos, E->rope_sin, c.sliding_window, st));
+            { TapGemmParams p = gp(Ly.o, act(E, E->f_att), 0, rows, 0, rows, 1); p.scale = Ly.ls_attn; setR(p, E->f_h); setY(p, E->f_h); GEMM("xf.gemm", p); }
+            KLAUNCH("xf.norm", 0.0, nb, voc_launch_rmsnorm(E->f_h, Ly.ln2, act(E, E->f_hn), rows, H, (float)c.rms_eps, st));
+            { TapGemmParams p = gp(Ly.gu, act(E, E->f_hn), 0, rows, 0, rows, 1); setY(p, E->f_gu); GEMM("xf.gemm", p); }
+            KLAUNCH("xf.swiglu", 0.0, 12.0 * rows * c.xf_inter, voc_launch_swiglu(E->f_gu, act(E, E->f_act), rows, c.xf_inter, st));
+            { TapGemmParams p = gp(Ly.down, act(E, E->f_act), 0, rows, 0, rows, 1); p.scale = Ly.ls_mlp; setR(p, E->f_h); setY(p, E->f_h); GEMM("xf.gemm", p); }
         }
-        KLAUNCH("xf.norm", 0.0, nb, voc_launch_rmsnorm(E->f_h, E->xf_norm, E->f_hn, rows, H, (float)c.rms_eps, st));
-        { TapGemmParams p = gp(E->xf_out, E->f_hn, 0, rows, 0, rows, 1); setY(p, E->f_x); GEMM("xf.gemm", p); }
+        KLAUNCH("xf.norm", 0.0, nb, voc_launch_rmsnorm(E->f_h, E->xf_norm, act(E, E->f_hn), rows, H, (float)c.rms_eps, st));
+        { TapGemmParams p = gp(E->xf_out, act(E, E->f_hn), 0, rows, 0, rows, 1); setS(p, act(E, E->f_x), nullptr); GEMM("xf.gemm", p); }
         x = E->f_x;
-        if (int r = dbg_capture(E, "xf", x, (size_t)nw * T * c.latent_dim, st)) return r;
+        if (int r = dbg_capture(E, "xf", act(E, x), (size_t)nw * T * c.latent_dim, st)) return r;
     }
     // K3: upsample stages (k = s transposed conv = GEMM + interleave, then ConvNeXt)
     int L = T;
-    float* other = (x == E->f_x) ? E->f_x2 : E->f_x;
     for (size_t u = 0; u < E->ups.size(); ++u) {
         auto& U = E->ups[u];
         const int C = c.latent_dim, r = c.upsampling_ratios[u];
-        { TapGemmParams p = gp(U.convt, x, (long long)L * C, L, 0, L, nw); setY(p, other); GEMM("up.convt", p); }
+        float* d1 = (x == E->f_x) ? E->f_x2 : E->f_x;        // transposed-conv output
+        float* d2 = (d1 == E->f_x) ? E->f_x2 : E->f_x;       // ConvNeXt output (x is dead by then)
+        {
+            TapGemmParams p = gp(U.convt, act(E, x), (long long)L * C, L, 0, L, nw);
+            if (c.convnext) setY(p, d1); else setS(p, act(E, d1), nullptr);
+            GEMM("up.convt", p);
+        }
         L *= r;
-        std::swap(x, other);              // x: [nw][L][C]
+        x = d1;                           // [nw][L][C]
         if (c.convnext) {
             KLAUNCH("up.dwconv_ln", 2.0 * nw * L * C * c.conv_kernel, 8.0 * nw * L * C,
-                    voc_launch_dwconv_ln(x, U.dw_w, U.dw_b, U.ln_w, U.ln_b, E->f_ln, nw, L, C, c.conv_kernel, (float)c.ln_eps, st));
+                    voc_launch_dwconv_ln(d1, U.dw_w, U.dw_b, U.ln_w, U.ln_b, act(E, E->f_ln), nw, L, C, c.conv_kernel, (float)c.ln_eps, st));
             const int rows = nw * L;
-            { TapGemmParams p = gp(U.pw1, E->f_ln, 0, rows, 0, rows, 1); p.act = VOC_ACT_GELU; setY(p, E->f_mid); GEMM("up.pw1", p); }
-            { TapGemmParams p = gp(U.pw2, E->f_mid, 0, rows, 0, rows, 1); p.scale = U.gamma; setR(p, x); setY(p, x); GEMM("up.pw2", p); }
+            { TapGemmParams p = gp(U.pw1, act(E, E->f_ln), 0, rows, 0, rows, 1); p.act = VOC_ACT_GELU; setS(p, act(E, E->f_mid), nullptr); GEMM("up.pw1", p); }
+            { TapGemmParams p = gp(U.pw2, act(E, E->f_mid), 0, rows, 0, rows, 1); p.scale = U.gamma; setR(p, d1); setS(p, act(E, d2), nullptr); GEMM("up.pw2", p); }
+            x = d2;
         }
-        if (other == E->f_pre) other = (x == E->f_x) ? E->f_x2 : E->f_x;
         char nm[32]; snprintf(nm, sizeof nm, "up%d", (int)u);
-        if (int r2 = dbg_capture(E, nm, x, (size_t)nw * L * C, st)) return r2;
+        if (int r2 = dbg_capture(E, nm, act(E, x), (size_t)nw * L * C, st)) return r2;
     }
     // K4: decoder conv-in, emits only Snake_0(conv_in(x)) -- the operand of block 0
     float* bX = E->big[0].p; float* bS = E->big[1].p; float* bT = E->big[2].p;
     {
-        TapGemmParams p = gp(E->conv_in, x, (long long)L * c.latent_dim, L, 0, L, nw);
-        setS(p, bS, E->blocks[0].s_in);
+        TapGemmParams p = gp(E->conv_in, act(E, x), (long long)L * c.latent_dim, L, 0, L, nw);
+        setS(p, act(E, bS), &E->blocks[0].s_in);
         if (E->debug) setY(p, bX);
         GEMM("conv_in", p);
-        if (E->debug) if (int r = dbg_capture(E, "conv_in", bX, (size_t)nw * L * c.decoder_dim, st)) return r;
+        if (E->debug) if (int r = dbg_capture(E, "conv_in", act_f32(bX), (size_t)nw * L * c.decoder_dim, st)) return r;
     }
     // K5/K6: decoder blocks
     static const char* const T_CONVT[] = {"dec0.convt", "dec1.convt", "dec2.convt", "dec3.convt", "decN.convt"};
@@ -577,8 +661,8 @@ static int run_wave(Engine* E, const long long* d_codes, int n_frames, int win_s
         const int Mrows = Lout / Bk.stride;                 // GEMM rows (one per input step)
         const int row0 = c.trim_both ? 1 : 0;
         {   // Snake'd input (bS, [nw][L][cin]) -> X' (bX) and Snake1_ru0(X') (bT)
-            TapGemmParams p = gp(Bk.convt, bS, (long long)L * Bk.cin, L, row0, Mrows, nw);
-            setY(p, bX); setS(p, bT, Bk.s_ru0_tiled);
+            TapGemmParams p = gp(Bk.convt, act(E, bS), (long long)L * Bk.cin, L, row0, Mrows, nw);
+            setY(p, bX); setS(p, act(E, bT), &Bk.s_ru0_tiled);
             GEMM(T_CONVT[ti], p);
         }
         L = Lout;
@@ -587,28 +671,28 @@ static int run_wave(Engine* E, const long long* d_codes, int n_frames, int win_s
         for (size_t j = 0; j < Bk.ru.size(); ++j) {
             auto& R = Bk.ru[j];
             {   // conv k7 dilated on Snake1(x) -> Snake2(.) only
-                TapGemmParams p = gp(R.c1, bS, (long long)L * C, L, 0, L, nw);
-                setS(p, bT, R.s2);
+                TapGemmParams p = gp(R.c1, act(E, bS), (long long)L * C, L, 0, L, nw);
+                setS(p, act(E, bT), &R.s2);
                 GEMM(T_C7[ti], p);
             }
             {   // conv k1 + residual -> x (in place) and the next consumer's Snake
-                TapGemmParams p = gp(R.c2, bT, (long long)L * C, L, 0, L, nw);
+                TapGemmParams p = gp(R.c2, act(E, bT), (long long)L * C, L, 0, L, nw);
                 setR(p, bX);
                 const bool last_ru = (j + 1 == Bk.ru.size());
                 const SnakeP& nxt = !last_ru ? Bk.ru[j + 1].s1
                                   : (b + 1 < E->blocks.size() ? E->blocks[b + 1].s_in : E->head_snake);
-                setS(p, bS, nxt);
+                setS(p, act(E, bS), &nxt);
                 if (!last_ru || E->debug) setY(p, bX);        // the residual stream ends with the block
                 GEMM(T_C1[ti], p);
             }
         }
         char nm[32]; snprintf(nm, sizeof nm, "dec%d", (int)b);
-        if (E->debug) if (int r = dbg_capture(E, nm, bX, (size_t)nw * L * C, st)) return r;
+        if (E->debug) if (int r = dbg_capture(E, nm, act_f32(bX), (size_t)nw * L * C, st)) return r;
     }
     // K7: head
     const int ch = c.decoder_dim >> c.upsample_rates.size();
     KLAUNCH("head", 2.0 * nw * L * ch * c.conv_kernel, 4.0 * nw * L * (ch + 1.0),
-            voc_launch_head(bS, (long long)L * ch, L, ch, c.conv_kernel, E->head_w, E->head_b, chunk_out, L, nw, st));
+            voc_launch_head(act(E, bS), (long long)L * ch, L, ch, c.conv_kernel, E->head_w, E->head_b, chunk_out, L, nw, st));
 #undef KLAUNCH
 #undef GEMM
     return VOC_OK;
@@ -803,7 +887,10 @@ void* voc_create(const char* cfg_json, int device, int wave) {
         fprintf(stderr, "voc_create: %s\n", g_create_error.c_str());
         return nullptr;
     }
-    E->device = device; E->wave = wave;
+    E->device = device; E->wave = wave; E->num_sms = prop.multiProcessorCount;
+    // experiment hooks (the documented switch is voc_set_option)
+    if (const char* g = getenv("VOC_GEMM")) E->gemm_mode = !strcmp(g, "simt") ? 1 : !strcmp(g, "tc") ? 2 : 0;
+    if (const char* f = getenv("VOC_TC_FLAGS")) E->tc_flags = atoi(f);
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking) != cudaSuccess) {
         g_create_error = "cudaSetDevice / stream creation failed";
         fprintf(stderr, "voc_create: %s\n", g_create_error.c_str());
@@ -975,6 +1062,7 @@ int voc_set_option(void* h, const char* key, const char* value) {
         else return fail(E, VOC_E_INVALID, "gemm must be auto|simt|tc");
         return VOC_OK;
     }
+    if (k == "tc_flags") { E->tc_flags = atoi(v.c_str()); return VOC_OK; }
     if (k == "profile") { E->profile = (v == "1"); return VOC_OK; }
     if (k == "debug") { E->debug = (v == "1"); if (!E->debug) E->dbg.clear(); return VOC_OK; }
     return fail(E, VOC_E_INVALID, "unknown option " + k);
@@ -1030,6 +1118,90 @@ long long voc_debug_stage(void* h, const char* name, float* out, long long cap) 
     CK(cudaStreamSynchronize(E->stream));
     CK(cudaMemcpy(out, it->second.first->p, n * sizeof(float), cudaMemcpyDeviceToHost));
     return n;
+}
+
+
+// ---- kernel-level hook: one tap-GEMM on caller data, through either kernel family -------------
+// mode 0 = CUDA cores, float32 operands; 1 = CUDA cores, split-fp16 operands; 2 = tcgen05.
+// A [B][a_rows][K], W [ntaps*K][N] (CUDA-core layout), R / Y / S [B][M][N]; any of bias, scale, R,
+// sn_a, sn_invb, Y, S may be NULL.  iters > 0 additionally times `iters` back-to-back launches with
+// CUDA events and stores the mean milliseconds in *ms.  Returns 0, a negative VOC_E_*, or 1 when
+// mode 2 was asked for a shape the tensor-core kernel does not take.
+int voc_test_tapgemm(int device, int mode, int tc_flags, int B, int a_rows, int K, int N, int M, int a_row0,
+                     int ntaps, const int* tap_off, const float* A, const float* W, const float* bias,
+                     const float* scale, int act_kind, const float* R, const float* sn_a, const float* sn_invb,
+                     float* Y, float* S, int iters, float* ms) {
+    if (!A || !W || !tap_off || ntaps < 1 || ntaps > VOC_MAX_TAPS || B < 1 || M < 1) return VOC_E_INVALID;
+    Engine EE; Engine* E = &EE;
+    E->device = device;
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    E->num_sms = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking));
+    E->gemm_mode = mode == 0 ? 1 : 2;
+    E->tc_flags = tc_flags;
+    GemmW g; g.K = K; g.N = N; g.ntaps = ntaps;
+    for (int i = 0; i < ntaps; ++i) g.tap_off[i] = tap_off[i];
+    std::vector<float> wt(W, W + (size_t)ntaps * K * N);
+    g.W = upload(E, wt);
+    if (!g.W || !make_wtc(E, wt, g)) return fail(E, VOC_E_CUDA, "weight upload failed");
+    auto up = [&](const float* h, size_t n) -> float* { if (!h) return nullptr; return upload(E, std::vector<float>(h, h + n)); };
+    g.bias = up(bias, N);
+    float* d_scale = up(scale, N);
+    float* d_R = up(R, (size_t)B * M * N);
+    SnakeP sp; sp.a = up(sn_a, N); sp.invb = up(sn_invb, N);
+    const size_t na = ((size_t)B * a_rows * K + 63) / 64 * 64, no = ((size_t)B * M * N + 63) / 64 * 64;
+    float *dA = nullptr, *dY = nullptr, *dS = nullptr;
+    CK(cudaMalloc(&dA, na * 4)); E->owned.push_back(dA); E->cap[dA] = na;
+    CK(cudaMalloc(&dY, no * 4)); E->owned.push_back(dY);
+    CK(cudaMalloc(&dS, no * 4)); E->owned.push_back(dS); E->cap[dS] = no;
+    if (mode == 0) {
+        CK(cudaMemcpyAsync(dA, A, (size_t)B * a_rows * K * 4, cudaMemcpyHostToDevice, E->stream));
+    } else {
+        std::vector<__half> h(2 * na);
+        for (size_t i = 0; i < (size_t)B * a_rows * K; ++i) {
+            const float v = std::min(65504.f, std::max(-65504.f, A[i]));
+            h[i] = __float2half_rn(v);
+            h[na + i] = __float2half_rn(v - __half2float(h[i]));
+        }
+        CK(cudaMemcpyAsync(dA, h.data(), h.size() * 2, cudaMemcpyHostToDevice, E->stream));
+        CK(cudaStreamSynchronize(E->stream));
+    }
+    TapGemmParams p = gp(g, act(E, dA), (long long)a_rows * K, a_rows, a_row0, M, B);
+    p.act = act_kind; p.scale = d_scale;
+    if (d_R) setR(p, d_R);
+    if (Y) setY(p, dY);
+    if (S) setS(p, act(E, dS), sp.a ? &sp : nullptr);
+    if (mode == 2 && !voc_tc_eligible(p)) return 1;
+    if (mode == 1) p.Wtc = nullptr;                 // keeps run_gemm on the CUDA-core kernel
+    CK(run_gemm(E, p, E->stream, "test"));
+    CK(cudaStreamSynchronize(E->stream));
+    if (iters > 0 && ms) {
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        CK(cudaEventRecord(e0, E->stream));
+        for (int i = 0; i < iters; ++i) CK(run_gemm(E, p, E->stream, "test"));
+        CK(cudaEventRecord(e1, E->stream));
+        CK(cudaStreamSynchronize(E->stream));
+        float t = 0.f; CK(cudaEventElapsedTime(&t, e0, e1));
+        *ms = t / iters;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    if (Y) CK(cudaMemcpy(Y, dY, (size_t)B * M * N * 4, cudaMemcpyDeviceToHost));
+    if (S) {
+        if (mode == 0) CK(cudaMemcpy(S, dS, (size_t)B * M * N * 4, cudaMemcpyDeviceToHost));
+        else {
+            float* tmp = nullptr;
+            CK(cudaMalloc(&tmp, no * 4)); E->owned.push_back(tmp);
+            const VocAct sa = act(E, dS);
+            CK(voc_launch_unsplit(sa.hi, sa.lo, tmp, (long long)B * M * N, E->stream));
+            CK(cudaStreamSynchronize(E->stream));
+            CK(cudaMemcpy(S, tmp, (size_t)B * M * N * 4, cudaMemcpyDeviceToHost));
+        }
+    }
+    CK(cudaDeviceSynchronize());
+    return VOC_OK;
 }
 
 }  // extern "C"

@@ -1,0 +1,96 @@
+"""Kernel-level GPU parity: the tcgen05 tap-GEMM (and the CUDA-core kernel on split operands)
+against a float64 numpy restatement of the contraction, for every layer kind of the graph:
+causal dilated Conv1d (k = 7, d = 1/3/9; k = 3), phase-decomposed ConvTranspose1d (two taps, row
+offset 1 under transconv_trim = "both"), Linear / 1x1 conv, with the fused epilogues
+(bias, exact GELU, per-channel scale, residual, SnakeBeta, split-fp16 operand output).
+
+Tolerance: the tensor path multiplies split-fp16 operands (~22 mantissa bits) and accumulates in
+FP32, so a dot product of O(1) terms is good to a few 1e-6 relative to the output scale."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def ref_tapgemm(A, W, tap_off, M, a_row0, bias=None, scale=None, act=0, R=None, sn_a=None, sn_invb=None):
+    from math import erf
+    B, a_rows, K = A.shape
+    N = W.shape[1]
+    acc = np.zeros((B, M, N), dtype=np.float64)
+    A64, W64 = A.astype(np.float64), W.astype(np.float64)
+    for t, off in enumerate(tap_off):
+        rows = np.arange(M) + a_row0 + off
+        ok = (rows >= 0) & (rows < a_rows)
+        At = np.zeros((B, M, K))
+        At[:, ok, :] = A64[:, rows[ok], :]
+        acc += At @ W64[t * K:(t + 1) * K]
+    v = acc + (0 if bias is None else bias.astype(np.float64))
+    if act == 1:
+        v = 0.5 * v * (1.0 + np.vectorize(erf)(v / np.sqrt(2.0)))
+    if scale is not None:
+        v = v * scale.astype(np.float64)
+    if R is not None:
+        v = v + R.astype(np.float64)
+    s = v if sn_a is None else v + sn_invb.astype(np.float64) * np.sin(v * sn_a.astype(np.float64)) ** 2
+    return v, s
+
+
+CASES = [
+    # name,              B, a_rows, K,   N,   M,  row0, tap_off
+    ("linear",           1, 300,  128, 256, 300, 0, [0]),
+    ("linear_k96",       2, 200,   96,  96, 200, 0, [0]),
+    ("conv7_d1",         2, 333,   96,  96, 333, 0, [-6, -5, -4, -3, -2, -1, 0]),
+    ("conv7_d3",         2, 333,  192, 192, 333, 0, [-18, -15, -12, -9, -6, -3, 0]),
+    ("conv7_d9",         1, 400,  128, 384, 400, 0, [-54, -45, -36, -27, -18, -9, 0]),
+    ("conv3",            3,  64,   64, 128,  64, 0, [-2, -1, 0]),
+    ("convt_trim_both",  2, 100,  192, 288,  99, 1, [0, -1]),
+    ("convt_trim_right", 2, 100,   64, 320, 100, 0, [0, -1]),
+    ("tiny_k16",         1, 150,   16,  32, 150, 0, [-2, -1, 0]),
+]
+
+
+@pytest.mark.parametrize("flags", [0, 1], ids=["tap_reuse", "no_reuse"])
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_tc_tapgemm_matches_float64(backend, case, flags):
+    name, B, a_rows, K, N, M, row0, taps = case
+    rng = np.random.default_rng(sum(map(ord, name)))
+    A = rng.standard_normal((B, a_rows, K)).astype(np.float32)
+    W = (rng.standard_normal((len(taps) * K, N)) / np.sqrt(len(taps) * K)).astype(np.float32)
+    bias = (0.1 * rng.standard_normal(N)).astype(np.float32)
+    scale = (1.0 + 0.1 * rng.standard_normal(N)).astype(np.float32)
+    R = rng.standard_normal((B, M, N)).astype(np.float32)
+    sn_a = np.exp(0.1 * rng.standard_normal(N)).astype(np.float32)
+    sn_invb = (1.0 / (np.exp(0.1 * rng.standard_normal(N)) + 1e-9)).astype(np.float32)
+    v_ref, s_ref = ref_tapgemm(A, W, taps, M, row0, bias, scale, 0, R, sn_a, sn_invb)
+    for mode in (2, 1):
+        rc, Y, S, _ = backend.test_tapgemm(mode, A, W, taps, M, row0, bias=bias, scale=scale, R=R, sn_a=sn_a,
+                                           sn_invb=sn_invb, want_y=True, want_s=True, tc_flags=flags)
+        assert rc == 0, (name, mode, rc)
+        ey = float(np.abs(Y - v_ref).max())
+        es = float(np.abs(S - s_ref).max())
+        print(f"{name} mode {mode} flags {flags}: max|dY| {ey:.2e}  max|dS| {es:.2e}")
+        assert ey < 2e-5 and es < 2e-5, (name, mode, ey, es)
+
+
+def test_tc_gelu_and_plain_operand_output(backend):
+    """ConvNeXt pw1 form: GELU epilogue, operand output without Snake, no float32 output."""
+    rng = np.random.default_rng(7)
+    A = rng.standard_normal((1, 256, 128)).astype(np.float32)
+    W = (rng.standard_normal((128, 512)) / np.sqrt(128)).astype(np.float32)
+    bias = (0.1 * rng.standard_normal(512)).astype(np.float32)
+    v_ref, s_ref = ref_tapgemm(A, W, [0], 256, 0, bias, None, 1)
+    rc, Y, S, _ = backend.test_tapgemm(2, A, W, [0], 256, 0, bias=bias, act=1, want_y=False, want_s=True)
+    assert rc == 0
+    assert float(np.abs(S - s_ref).max()) < 2e-5
+
+
+def test_ineligible_shape_is_reported(backend):
+    rng = np.random.default_rng(3)
+    A = rng.standard_normal((1, 40, 12)).astype(np.float32)
+    W = rng.standard_normal((12, 8)).astype(np.float32)
+    rc, *_ = backend.test_tapgemm(2, A, W, [0], 40)
+    assert rc == 1
+    rc, Y, _, _ = backend.test_tapgemm(1, A, W, [0], 40)
+    assert rc == 0
+    v_ref, _ = ref_tapgemm(A, W, [0], 40, 0)
+    assert float(np.abs(Y - v_ref).max()) < 2e-5
