@@ -310,7 +310,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="chunks per GPU per step")
-    ap.add_argument("--wave", type=int, default=8, help="chunks resident in HBM at once")
+    ap.add_argument("--wave", type=int, default=32, help="chunks resident in HBM at once")
     ap.add_argument("--gemm", default="auto", choices=["auto", "simt", "tc"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
