@@ -36,7 +36,8 @@
 namespace {
 
 constexpr int BM = 128;
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 8;                       // 4 TMEM lane quadrants x COL_PARTS column parts
+constexpr int COL_PARTS = EPI_WARPS / 4;
 constexpr int TC_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int MAX_STAGES = 8;
 
@@ -142,11 +143,10 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
         : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() {
@@ -164,16 +164,16 @@ __device__ __forceinline__ constexpr uint32_t smem_desc_hi() {
     return ((8u * BK * 2u) >> 4) | (1u << 14) | ((BK == 64 ? 2u : 4u) << 29);
 }
 
-__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 // ---------------------------------------------------------------------------------------------
 template <int BN, int BK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ TcArgs a) {
-    static_assert(BN % 32 == 0 && BN >= 32 && BN <= 192, "UMMA N; BN/2 columns per epilogue thread");
+    static_assert(BN % 32 == 0 && BN >= 32 && BN <= 192, "UMMA N; BN/COL_PARTS columns per epilogue thread");
     static_assert(BK == 64 || BK == 32, "one swizzle atom per K-chunk");
-    constexpr int HN = BN / 2;                                // columns per epilogue thread
+    constexpr int HN = BN / COL_PARTS;                        // columns per epilogue thread
+    constexpr int PB = HN <= 64 ? HN : 16;                    // residual prefetch window (columns)
     constexpr uint32_t ROWB = BK * 2;                         // bytes of one shared-memory row
     constexpr uint32_t B_PLANE = BN * ROWB, B_STAGE = 2 * B_PLANE;
     constexpr uint32_t TMEM_COLS = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
@@ -185,6 +185,8 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __shared__ __align__(8) uint64_t bar_b_full[MAX_STAGES], bar_b_empty[MAX_STAGES];
     __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2];
     __shared__ uint32_t tmem_slot;
+    // per-channel epilogue parameters of the current n-tile: bias, scale, snake a, snake 1/b
+    __shared__ __align__(16) float epi_par[4][BN];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -298,14 +300,40 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
     } else {
         // ================================ epilogue ====================================
+        // (16 epilogue warps and a shared-memory transpose for fully coalesced global traffic were both
+        // measured and are not faster: profiles/r1_epilogue_experiments.txt)
         const int q = warp & 3;                       // the TMEM lane quadrant this warp can read
-        const int h = (warp - 2) >> 2;                // which half of the tile's columns
+        const int h = (warp - 2) >> 2;                // which part of the tile's columns
         const int nseg = (iters_per_tile + a.seg_iters - 1) / a.seg_iters;
-        int as = 0, pas = 0;
+        const int etid = threadIdx.x - 64;
+        int as = 0, pas = 0, par_tile = -1;
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
             const int n_tile = tile % a.n_tiles, ml = tile / a.n_tiles;
             const int m_tile = ml % a.m_tiles, b = ml / a.m_tiles;
             const int m = m_tile * BM + q * 32 + lane, n0 = n_tile * BN + h * HN;
+            const bool valid = m < a.M;
+            if (n_tile != par_tile) {
+                // (re)load the parameters of this column tile; loads of the per-column vectors at the
+                // point of use would sit, at L2 latency, in every column group's dependent chain
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+                for (int i = etid; i < BN; i += 32 * EPI_WARPS) {
+                    const int n = n_tile * BN + i;
+                    epi_par[0][i] = a.bias ? __ldg(a.bias + n) : 0.f;
+                    epi_par[1][i] = a.scale ? __ldg(a.scale + n) : 1.f;
+                    epi_par[2][i] = a.sn_a ? __ldg(a.sn_a + n) : 1.f;
+                    epi_par[3][i] = a.sn_a ? __ldg(a.sn_invb + n) : 0.f;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+                par_tile = n_tile;
+            }
+            // The residual is independent of the MMAs: its loads are issued before the accumulator
+            // wait (whole row when it fits the register budget, else a rolling 16-column window).
+            const float* Rrow = (a.R && valid) ? a.R + (long long)b * a.r_bstride + (long long)m * a.ldr + n0 : nullptr;
+            float4 rpf[2][PB / 4];
+            if (Rrow) {
+#pragma unroll
+                for (int i = 0; i < PB / 4; ++i) rpf[0][i] = *reinterpret_cast<const float4*>(Rrow + 4 * i);
+            }
             float acc[HN];
 #pragma unroll
             for (int j = 0; j < HN; ++j) acc[j] = 0.f;
@@ -313,36 +341,37 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 mbar_wait(&bar_acc_full[as], pas);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + h * HN);
+                uint32_t tr[HN / 8][8];
 #pragma unroll
-                for (int c = 0; c < HN; c += 32) {
-                    uint32_t r0[16], r1[16];
-                    tmem_ld16(taddr + c, r0);
-                    if (c + 16 < HN) tmem_ld16(taddr + c + 16, r1);
-                    tmem_ld_wait();
+                for (int c = 0; c < HN / 8; ++c) tmem_ld8(taddr + c * 8, tr[c]);
+                tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[c + j] += __uint_as_float(r0[j]);
-                    if (c + 16 < HN) {
+                for (int c = 0; c < HN / 8; ++c)
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) acc[c + 16 + j] += __uint_as_float(r1[j]);
-                    }
-                }
+                    for (int j = 0; j < 8; ++j) acc[c * 8 + j] += __uint_as_float(tr[c][j]);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_acc_empty[as]);
                 as ^= 1; if (as == 0) pas ^= 1;
             }
-            if (m >= a.M) continue;
-            const float* Rrow = a.R ? a.R + (long long)b * a.r_bstride + (long long)m * a.ldr + n0 : nullptr;
+            if (!valid) continue;
             float* Yrow = a.Y ? a.Y + (long long)b * a.y_bstride + (long long)m * a.ldy + n0 : nullptr;
             const long long soff = (long long)b * a.s_bstride + (long long)m * a.lds + n0;
 #pragma unroll
             for (int g = 0; g < HN; g += 8) {
-                const int n = n0 + g;
+                const int pc = h * HN + g;             // column within the tile
+                const int pcur = (g / PB) & 1;
+                if (Rrow && (g % PB) == 0 && g + PB < HN) {
+#pragma unroll
+                    for (int i = 0; i < PB / 4; ++i)
+                        rpf[pcur ^ 1][i] = *reinterpret_cast<const float4*>(Rrow + g + PB + 4 * i);
+                }
                 float v[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = acc[g + j] * a.wscale;
                 if (a.bias) {
-                    const float4 b0 = ldg4(a.bias + n), b1 = ldg4(a.bias + n + 4);
+                    const float4 b0 = *reinterpret_cast<const float4*>(&epi_par[0][pc]);
+                    const float4 b1 = *reinterpret_cast<const float4*>(&epi_par[0][pc + 4]);
                     v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
                     v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
                 }
@@ -351,13 +380,13 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     for (int j = 0; j < 8; ++j) v[j] = voc_gelu(v[j]);
                 }
                 if (a.scale) {
-                    const float4 s0 = ldg4(a.scale + n), s1 = ldg4(a.scale + n + 4);
+                    const float4 s0 = *reinterpret_cast<const float4*>(&epi_par[1][pc]);
+                    const float4 s1 = *reinterpret_cast<const float4*>(&epi_par[1][pc + 4]);
                     v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w;
                     v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
                 }
                 if (Rrow) {
-                    const float4 r0 = *reinterpret_cast<const float4*>(Rrow + g);
-                    const float4 r1 = *reinterpret_cast<const float4*>(Rrow + g + 4);
+                    const float4 r0 = rpf[pcur][(g % PB) / 4], r1 = rpf[pcur][(g % PB) / 4 + 1];
                     v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
                     v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
                 }
@@ -367,8 +396,10 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
                 if (a.S_hi) {
                     if (a.sn_a) {
-                        const float4 a0 = ldg4(a.sn_a + n), a1 = ldg4(a.sn_a + n + 4);
-                        const float4 i0 = ldg4(a.sn_invb + n), i1 = ldg4(a.sn_invb + n + 4);
+                        const float4 a0 = *reinterpret_cast<const float4*>(&epi_par[2][pc]);
+                        const float4 a1 = *reinterpret_cast<const float4*>(&epi_par[2][pc + 4]);
+                        const float4 i0 = *reinterpret_cast<const float4*>(&epi_par[3][pc]);
+                        const float4 i1 = *reinterpret_cast<const float4*>(&epi_par[3][pc + 4]);
                         v[0] = voc_snake(v[0], a0.x, i0.x); v[1] = voc_snake(v[1], a0.y, i0.y);
                         v[2] = voc_snake(v[2], a0.z, i0.z); v[3] = voc_snake(v[3], a0.w, i0.w);
                         v[4] = voc_snake(v[4], a1.x, i1.x); v[5] = voc_snake(v[5], a1.y, i1.y);
@@ -447,7 +478,7 @@ int pick_bn(int N) {
     return 0;
 }
 
-constexpr int SMEM_BUDGET = 232448 - 1024 - 1024;   // opt-in maximum minus alignment slack and static smem
+constexpr int SMEM_BUDGET = 232448 - 1024 - 5120;   // opt-in maximum minus alignment slack and static smem
 
 template <int BN, int BK>
 cudaError_t launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, int grid, size_t smem,
@@ -455,7 +486,7 @@ cudaError_t launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const Tc
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             232448 - 1024);
+                                             SMEM_BUDGET + 1024);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
@@ -505,6 +536,7 @@ cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int n
     const int BN = pick_bn(p.N);
     int BK = (p.K % 64 == 0 || p.K % 64 > 32) ? 64 : 32;
     if (flags & VOC_TC_BK32) BK = 32;
+    if (flags & VOC_TC_BK64) BK = 64;
 
     TcArgs a;
     memset(&a, 0, sizeof(a));
