@@ -32,6 +32,7 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <type_traits>
 
 namespace {
 
@@ -45,6 +46,8 @@ struct TcArgs {
     int M, N, K, B, ntaps, a_row0;
     int tap_off[VOC_MAX_TAPS];
     int a_reuse, a_min_off, a_box_rows, seg_iters;
+    int alt_acc;          // experiment (timing only, results wrong): alternate k-steps between both TMEM buffers
+    int split;            // 0: one TMA per stage operand (2-plane box), 1: one per plane, 2: per plane x row half
     int m_tiles, n_tiles, k_chunks, total_tiles;
     int SA, SB;
     float wscale;
@@ -131,6 +134,17 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint32_t desc_a_lo, 
         "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
         ::"r"(tmem_d), "r"(desc_a_lo), "r"(desc_b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same, accumulate always on (no runtime predicate: keeps the issue loop free of vector->uniform moves)
+__device__ __forceinline__ void mma_f16_ss_acc(uint32_t tmem_d, uint32_t desc_a_lo, uint32_t desc_b_lo, uint32_t desc_hi,
+                                               uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.eq.u32 p, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(desc_a_lo), "r"(desc_b_lo), "r"(desc_hi), "r"(idesc) : "memory");
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(
@@ -176,9 +190,18 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     constexpr int PB = HN <= 64 ? HN : 16;                    // residual prefetch window (columns)
     constexpr uint32_t ROWB = BK * 2;                         // bytes of one shared-memory row
     constexpr uint32_t B_PLANE = BN * ROWB, B_STAGE = 2 * B_PLANE;
-    constexpr uint32_t TMEM_COLS = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    // CAT (BN <= 128): the two weight planes of a stage are contiguous rows, so A_hi x [B_hi; B_lo] is ONE
+    // MMA of N = 2*BN whose right half lands in a separate "correction" block of the accumulator buffer;
+    // A_lo x B_hi then accumulates into that block.  2 MMAs per k-step instead of 3 (an MMA costs
+    // ~64 + N/2 cycles, so fewer and wider is cheaper), and the 2^-11-times-smaller cross terms no longer
+    // share the main accumulator's truncation.  The epilogue adds the two blocks in FP32.
+    constexpr bool CAT = BN <= 128;
+    constexpr uint32_t ACC_COLS = CAT ? 2 * BN : BN;          // TMEM columns of one accumulator buffer
+    constexpr uint32_t TMEM_COLS = (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128
+                                   : (2 * ACC_COLS <= 256) ? 256 : 512;
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = F16, both K-major
     constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_a_full[MAX_STAGES], bar_a_empty[MAX_STAGES];
@@ -225,15 +248,31 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             mbar_wait(&bar_a_empty[sa], pa ^ 1);
                             if (elect_one()) {
                                 mbar_expect_tx(&bar_a_full[sa], a_stage);
-                                tma_load_4d(smA + sa * a_stage, &tmA, &bar_a_full[sa], kc * BK,
-                                            row0 + (a.a_reuse ? a.a_min_off : a.tap_off[tap]), b, 0);
+                                const int arow = row0 + (a.a_reuse ? a.a_min_off : a.tap_off[tap]);
+                                if (a.split == 0) {
+                                    tma_load_4d(smA + sa * a_stage, &tmA, &bar_a_full[sa], kc * BK, arow, b, 0);
+                                } else {
+                                    const int nr = a.split == 2 ? 2 : 1, hr = a.a_box_rows / nr;
+                                    for (int pl = 0; pl < 2; ++pl)
+                                        for (int rh = 0; rh < nr; ++rh)
+                                            tma_load_4d(smA + sa * a_stage + pl * a_plane + rh * hr * ROWB, &tmA,
+                                                        &bar_a_full[sa], kc * BK, arow + rh * hr, b, pl);
+                                }
                             }
                             if (++sa == a.SA) { sa = 0; pa ^= 1; }
                         }
                         mbar_wait(&bar_b_empty[sb], pb ^ 1);
                         if (elect_one()) {
                             mbar_expect_tx(&bar_b_full[sb], B_STAGE);
-                            tma_load_4d(smB + sb * B_STAGE, &tmB, &bar_b_full[sb], kc * BK, n0, tap, 0);
+                            if (a.split == 0) {
+                                tma_load_4d(smB + sb * B_STAGE, &tmB, &bar_b_full[sb], kc * BK, n0, tap, 0);
+                            } else {
+                                const int nr = a.split == 2 ? 2 : 1, hr = BN / nr;
+                                for (int pl = 0; pl < 2; ++pl)
+                                    for (int rh = 0; rh < nr; ++rh)
+                                        tma_load_4d(smB + sb * B_STAGE + pl * B_PLANE + rh * hr * ROWB, &tmB,
+                                                    &bar_b_full[sb], kc * BK, n0 + rh * hr, tap, pl);
+                            }
                         }
                         if (++sb == a.SB) { sb = 0; pb ^= 1; }
                     }
@@ -256,7 +295,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         if (it % a.seg_iters == 0) {
                             mbar_wait(&bar_acc_empty[as], pas ^ 1);
                             tc_fence_after();
-                            tmem_acc = tmem_base + (uint32_t)(as * BN);
+                            tmem_acc = tmem_base + (uint32_t)as * ACC_COLS;
                             accum = 0;
                         }
                         if (tap == 0 || !a.a_reuse) {
@@ -271,20 +310,47 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         const uint32_t row_off = a.a_reuse ? (uint32_t)(a.tap_off[tap] - a.a_min_off) : 0u;
                         const uint32_t a_lo = smem_desc_lo(smA + cur_a * a_stage + row_off * ROWB);
                         const uint32_t b_lo = smem_desc_lo(smB + sb * B_STAGE);
+                        // a K tail shorter than the chunk is zero-filled by TMA; its all-zero k-steps are skipped
+                        const int ksteps = min(BK / 16, (a.K - kc * BK + 15) >> 4);
                         const bool last_of_a = (tap == a.ntaps - 1 || !a.a_reuse);
                         const bool last_of_seg = ((it + 1) % a.seg_iters == 0 || it + 1 == iters_per_tile);
                         if (elect_one()) {
+                            // The issuing warp is the bottleneck of the main loop when it spends more than a
+                            // few instructions per MMA (ncu: 13 per UTCHMMA held the tensor pipe at 58 %), so
+                            // the full-chunk path is branch-free, fully unrolled, and only the first MMA of a
+                            // stage takes a run-time accumulate flag.
+                            auto issue = [&](auto full) {
+                                constexpr bool FULL = decltype(full)::value;
+                                if constexpr (CAT) {
 #pragma unroll
-                            for (int pass = 0; pass < 3; ++pass) {
-                                // (A plane, B plane): (hi,lo), (lo,hi), (hi,hi); offsets in 16-byte units
-                                const uint32_t ap = a_lo + (pass == 1 ? (a_plane >> 4) : 0u);
-                                const uint32_t bp = b_lo + (pass == 0 ? (B_PLANE >> 4) : 0u);
+                                    for (int ks = 0; ks < BK / 16; ++ks) {
+                                        if (FULL || ks < ksteps) {
+                                            // [main | corr] = A_hi x [B_hi; B_lo];  corr += A_lo x B_hi
+                                            if (ks == 0) mma_f16_ss(tmem_acc, a_lo, b_lo, smem_desc_hi<BK>(), IDESC2, accum);
+                                            else mma_f16_ss_acc(tmem_acc, a_lo + ks * 2, b_lo + ks * 2, smem_desc_hi<BK>(), IDESC2);
+                                            mma_f16_ss_acc(tmem_acc + BN, a_lo + (a_plane >> 4) + ks * 2, b_lo + ks * 2,
+                                                           smem_desc_hi<BK>(), IDESC);
+                                        }
+                                    }
+                                } else {
 #pragma unroll
-                                for (int ks = 0; ks < BK / 16; ++ks) {
-                                    mma_f16_ss(tmem_acc, ap + ks * 2, bp + ks * 2, smem_desc_hi<BK>(), IDESC, accum);
-                                    accum = 1;
+                                    for (int pass = 0; pass < 3; ++pass) {
+                                        // (A plane, B plane): (hi,lo), (lo,hi), (hi,hi); offsets in 16-byte units
+                                        const uint32_t ap = a_lo + (pass == 1 ? (a_plane >> 4) : 0u);
+                                        const uint32_t bp = b_lo + (pass == 0 ? (B_PLANE >> 4) : 0u);
+#pragma unroll
+                                        for (int ks = 0; ks < BK / 16; ++ks) {
+                                            if (FULL || ks < ksteps) {
+                                                const uint32_t td = (a.alt_acc && (ks & 1)) ? (tmem_acc ^ ACC_COLS) : tmem_acc;
+                                                if (pass == 0 && ks == 0) mma_f16_ss(td, ap, bp, smem_desc_hi<BK>(), IDESC, accum);
+                                                else mma_f16_ss_acc(td, ap + ks * 2, bp + ks * 2, smem_desc_hi<BK>(), IDESC);
+                                            }
+                                        }
+                                    }
                                 }
-                            }
+                            };
+                            if (ksteps == BK / 16) issue(std::true_type{});
+                            else issue(std::false_type{});
                             mma_commit(&bar_b_empty[sb]);
                             if (last_of_a) mma_commit(&bar_a_empty[cur_a]);
                             if (last_of_seg) mma_commit(&bar_acc_full[as]);
@@ -340,15 +406,34 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int seg = 0; seg < nseg; ++seg) {
                 mbar_wait(&bar_acc_full[as], pas);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + h * HN);
-                uint32_t tr[HN / 8][8];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * ACC_COLS + (uint32_t)(h * HN);
+                if constexpr (CAT) {
+                    // main and correction blocks, at most 24 columns of each in flight
 #pragma unroll
-                for (int c = 0; c < HN / 8; ++c) tmem_ld8(taddr + c * 8, tr[c]);
-                tmem_ld_wait();
+                    for (int c0 = 0; c0 < HN / 8; c0 += 3) {
+                        uint32_t tm[3][8], tc[3][8];
 #pragma unroll
-                for (int c = 0; c < HN / 8; ++c)
+                        for (int c = 0; c < 3; ++c)
+                            if (c0 + c < HN / 8) { tmem_ld8(taddr + (c0 + c) * 8, tm[c]); tmem_ld8(taddr + BN + (c0 + c) * 8, tc[c]); }
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[c * 8 + j] += __uint_as_float(tr[c][j]);
+                        for (int c = 0; c < 3; ++c)
+                            if (c0 + c < HN / 8) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j)
+                                    acc[(c0 + c) * 8 + j] += __uint_as_float(tm[c][j]) + __uint_as_float(tc[c][j]);
+                            }
+                    }
+                } else {
+                    uint32_t tr[HN / 8][8];
+#pragma unroll
+                    for (int c = 0; c < HN / 8; ++c) tmem_ld8(taddr + c * 8, tr[c]);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < HN / 8; ++c)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[c * 8 + j] += __uint_as_float(tr[c][j]);
+                }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_acc_empty[as]);
@@ -446,8 +531,8 @@ std::map<MapKey, CUtensorMap> g_maps;
 
 // 4-D fp16 tensor {d0 (contiguous), d1, d2, 2 planes}, box {bk, box_rows, 1, 2}
 bool get_map(const void* base, long long d0, long long d1, long long d2, long long s1, long long s2, long long s3,
-             int bk, int box_rows, CUtensorMap* out) {
-    const MapKey key{base, d0, d1, d2, s1, s2, s3, bk, box_rows, 0};
+             int bk, int box_rows, int box_planes, CUtensorMap* out) {
+    const MapKey key{base, d0, d1, d2, s1, s2, s3, bk, box_rows, box_planes};
     std::lock_guard<std::mutex> lk(g_map_mu);
     auto it = g_maps.find(key);
     if (it != g_maps.end()) { *out = it->second; return true; }
@@ -455,7 +540,7 @@ bool get_map(const void* base, long long d0, long long d1, long long d2, long lo
     if (!fn) return false;
     const cuuint64_t dims[4] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2, 2};
     const cuuint64_t strides[3] = {(cuuint64_t)s1, (cuuint64_t)s2, (cuuint64_t)s3};   // bytes, dims 1..3
-    const cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)box_rows, 1, 2};
+    const cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)box_rows, 1, (cuuint32_t)box_planes};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     CUtensorMap m;
     const CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
@@ -534,7 +619,9 @@ cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int n
     if (!voc_tc_eligible(p)) return cudaErrorNotSupported;
     if (p.M <= 0 || p.B <= 0) return cudaSuccess;
     const int BN = pick_bn(p.N);
-    int BK = (p.K % 64 == 0 || p.K % 64 > 32) ? 64 : 32;
+    // One SS-mode MMA (M 128, K 16) costs ~64 + N/2 cycles from SWIZZLE_128B operands and ~100 + N/2
+    // from SWIZZLE_64B ones (tools/mma_rate.py), so 64-wide K chunks are used whenever K > 32.
+    int BK = p.K > 32 ? 64 : 32;
     if (flags & VOC_TC_BK32) BK = 32;
     if (flags & VOC_TC_BK64) BK = 64;
 
@@ -550,6 +637,8 @@ cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int n
     // on the full 64-frame window: 12 -> 98.8 dB / 1.2e-5, 24 -> 94.6 dB / 2.0e-5, 48 -> 88.6 dB / 3.9e-5,
     // 96 -> 82.6 dB / 6.9e-5, never -> 68.1 dB / 3.7e-4 (fails the 1e-4 gate).
     const int seg_mmas = (flags >> 8) > 0 ? (flags >> 8) : 24;
+    // seg_mmas counts MMAs into the main accumulator per segment as in the 3-pass form (3 per k-step);
+    // the concatenated form (BN <= 128) keeps the same number of k-steps per segment
     a.seg_iters = std::max(1, seg_mmas / (3 * BK / 16));
     a.m_tiles = (p.M + BM - 1) / BM; a.n_tiles = p.N / BN; a.k_chunks = (p.K + BK - 1) / BK;
     a.total_tiles = a.m_tiles * a.n_tiles * p.B;
@@ -576,12 +665,16 @@ cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int n
     const long long a_bs = p.B > 1 ? p.a_bstride : (long long)p.a_rows * p.lda;
     const long long a_plane = (long long)(p.A_lo - p.A_hi);
     if (a_plane % 8 || a_plane <= 0) return cudaErrorInvalidValue;
-    if (!get_map(p.A_hi, p.K, p.a_rows, p.B, (long long)p.lda * 2, a_bs * 2, a_plane * 2, BK, a.a_box_rows, &tmA))
+    a.split = (flags >> 4) & 3;
+    a.alt_acc = (flags >> 6) & 1;
+    const int nr = a.split == 2 ? 2 : 1, npl = a.split ? 1 : 2;
+    if (!get_map(p.A_hi, p.K, p.a_rows, p.B, (long long)p.lda * 2, a_bs * 2, a_plane * 2, BK, a.a_box_rows / nr, npl, &tmA))
         return cudaErrorInvalidValue;
-    if (!get_map(p.Wtc, p.K, p.N, p.ntaps, (long long)p.K * 2, (long long)p.N * p.K * 2, p.wtc_plane * 2, BK, BN, &tmB))
+    if (!get_map(p.Wtc, p.K, p.N, p.ntaps, (long long)p.K * 2, (long long)p.N * p.K * 2, p.wtc_plane * 2, BK, BN / nr, npl, &tmB))
         return cudaErrorInvalidValue;
 
-    const int grid = std::min(a.total_tiles, num_sms > 0 ? num_sms : 148);
+    int grid = std::min(a.total_tiles, num_sms > 0 ? num_sms : 148);
+    if (flags & VOC_TC_HALF_GRID) grid = std::max(1, grid / 2);      // experiment: contention vs work
     if (BK == 64) return launch_bn<64>(BN, tmA, tmB, a, grid, smem, st);
     return launch_bn<32>(BN, tmA, tmB, a, grid, smem, st);
 }
