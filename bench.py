@@ -247,21 +247,39 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     g_flops = sum(p["flops"] for p in gemm)
     g_calls = sum(p["calls"] for p in gemm)
     all_ms = sum(p["ms"] for p in prof)
-    achieved = g_flops / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
+    family = g_flops / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
     peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    passes = 1 if args.gemm == "simt" else 3
+    # the dominant kernel = the layer (one launch per wave of windows) with the largest share of the step
+    top = max(gemm, key=lambda q: q["ms"]) if gemm else None
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if top and args.wave == tr.get("wave") and B % args.wave == 0 and top["tag"] in tr and args.gemm != "simt":
+            traffic = tr[top["tag"]]["dram_bytes_per_launch"]
+    except Exception:
+        traffic = None
+    achieved = top["flops"] / (top["ms"] / 1e3) / 1e12 if top and top["ms"] > 0 else 0.0
     roofline = {
-        "kernel": "tap-GEMM family (all conv / transposed-conv / linear layers)",
+        "kernel": (f"tapgemm_tc_kernel (tcgen05 tap-GEMM), layer {top['tag']}" if args.gemm != "simt"
+                   else f"tapgemm_simt_kernel, layer {top['tag']}") if top else None,
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-        "frac": achieved / peak, "traffic": None,
+        "frac": achieved / peak, "traffic": traffic,
+        "traffic_note": "DRAM bytes of one launch of that layer (ncu --set full, profiles/r1_traffic.json); "
+                        "equals its algorithmic bytes (operand in, operand out)" if traffic else None,
         "peak_source": f"{peak_src} bf16 dense sustained (MEASURED_PEAKS.json)",
-        "tensor_passes_per_flop": 1 if args.gemm == "simt" else 3,
-        "mma_issue_tflops": achieved * (1 if args.gemm == "simt" else 3),
+        "launches_per_step": top["calls"] / args.steps if top else None,
+        "avg_launch_ms": top["ms"] / max(top["calls"], 1) if top else None,
+        "share_of_step": top["ms"] / all_ms if top and all_ms else None,
+        "tensor_passes_per_flop": passes,
+        "mma_issue_tflops": achieved * passes,
+        "family": {"what": "all tap-GEMM launches (every conv / transposed-conv / linear layer)",
+                   "achieved": family, "frac": family / peak, "mma_issue_tflops": family * passes,
+                   "launches_per_step": g_calls / args.steps, "share_of_step": g_ms / all_ms if all_ms else None},
         "note": ("FP32 CUDA-core path" if args.gemm == "simt" else
-                 "`achieved` counts algorithmic FLOPs; every product is three fp16 tcgen05 passes "
+                 "`achieved` counts algorithmic FLOPs (2*M*N*K*taps); every product is three fp16 tcgen05 passes "
                  "(hi*hi + hi*lo + lo*hi, FP32 accumulate) because one bf16/tf32 pass fails the 60 dB / 1e-4 gate, "
                  "so the tensor pipe runs at 3x `achieved` (mma_issue_tflops)"),
-        "launches_per_step": g_calls / args.steps, "avg_launch_ms": g_ms / max(g_calls, 1),
-        "share_of_step": g_ms / all_ms if all_ms else None,
     }
     breakdown = {p["tag"]: {"ms_per_step": p["ms"] / args.steps,
                             "tflops": (p["flops"] / (p["ms"] / 1e3) / 1e12) if p["ms"] > 0 and p["flops"] else None,
