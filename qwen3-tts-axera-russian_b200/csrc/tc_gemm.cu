@@ -145,6 +145,65 @@ __device__ __forceinline__ void mma_f16_ss_acc(uint32_t tmem_d, uint32_t desc_a_
         "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
         ::"r"(tmem_d), "r"(desc_a_lo), "r"(desc_b_lo), "r"(desc_hi), "r"(idesc) : "memory");
 }
+// ---- cta_group::2 (a pair of CTAs on one TPC computes a 256-row tile; B is split between them) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose bytes are credited to a barrier of the pair's leader CTA (cluster address)
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
+                                                int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t addr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void mma2_f16_ss(uint32_t tmem_d, uint32_t desc_a_lo, uint32_t desc_b_lo, uint32_t desc_hi,
+                                            uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(desc_a_lo), "r"(desc_b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma2_f16_ss_acc(uint32_t tmem_d, uint32_t desc_a_lo, uint32_t desc_b_lo, uint32_t desc_hi,
+                                                uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.eq.u32 p, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(desc_a_lo), "r"(desc_b_lo), "r"(desc_hi), "r"(idesc) : "memory");
+}
+// completion of the pair's MMAs arrives on the barrier at the same offset in both CTAs
+__device__ __forceinline__ void mma2_commit_both(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(
@@ -180,7 +239,10 @@ __device__ __forceinline__ constexpr uint32_t smem_desc_hi() {
 
 
 // ---------------------------------------------------------------------------------------------
-template <int BN, int BK>
+// TWO: cta_group::2.  A cluster of two CTAs computes two consecutive 128-row M tiles of the same column
+// tile with M = 256 MMAs issued by the leader (rank 0): each CTA stages its own A tile and HALF of the
+// weight rows, so the per-MMA shared-memory operand fetch drops from (128 + N)/2 to (128 + N/2)/2 cycles.
+template <int BN, int BK, bool TWO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ TcArgs a) {
@@ -189,18 +251,19 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     constexpr int HN = BN / COL_PARTS;                        // columns per epilogue thread
     constexpr int PB = HN <= 64 ? HN : 16;                    // residual prefetch window (columns)
     constexpr uint32_t ROWB = BK * 2;                         // bytes of one shared-memory row
-    constexpr uint32_t B_PLANE = BN * ROWB, B_STAGE = 2 * B_PLANE;
+    constexpr int BROWS = TWO ? BN / 2 : BN;                  // weight rows staged by this CTA
+    constexpr uint32_t B_PLANE = BROWS * ROWB, B_STAGE = 2 * B_PLANE;
     // CAT (BN <= 128): the two weight planes of a stage are contiguous rows, so A_hi x [B_hi; B_lo] is ONE
     // MMA of N = 2*BN whose right half lands in a separate "correction" block of the accumulator buffer;
     // A_lo x B_hi then accumulates into that block.  2 MMAs per k-step instead of 3 (an MMA costs
     // ~64 + N/2 cycles, so fewer and wider is cheaper), and the 2^-11-times-smaller cross terms no longer
     // share the main accumulator's truncation.  The epilogue adds the two blocks in FP32.
-    constexpr bool CAT = BN <= 128;
+    constexpr bool CAT = !TWO && BN <= 128;
     constexpr uint32_t ACC_COLS = CAT ? 2 * BN : BN;          // TMEM columns of one accumulator buffer
     constexpr uint32_t TMEM_COLS = (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128
                                    : (2 * ACC_COLS <= 256) ? 256 : 512;
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = F16, both K-major
-    constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((TWO ? 2 * BM : BM) >> 4) << 24);
     constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
     extern __shared__ uint8_t smem_raw[];
@@ -216,19 +279,24 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t a_plane = (uint32_t)a.a_box_rows * ROWB, a_stage = 2 * a_plane;
     const uint32_t smA = smem_base, smB = smem_base + (uint32_t)a.SA * a_stage;
     const int iters_per_tile = a.k_chunks * a.ntaps;
+    const uint32_t rank = TWO ? cluster_ctarank() : 0u;
+    // tile walk: CTA pairs (TWO) or single CTAs stride over (n tile, M tile [pair], window)
+    const int walker = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int walkers = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int i = 0; i < a.SA; ++i) { mbar_init(&bar_a_full[i], 1); mbar_init(&bar_a_empty[i], 1); }
         for (int i = 0; i < a.SB; ++i) { mbar_init(&bar_b_full[i], 1); mbar_init(&bar_b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], EPI_WARPS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], TWO ? 2 * EPI_WARPS : EPI_WARPS); }
         fence_barrier_init();
         fence_proxy_async();
     }
-    if (warp == 1) tmem_alloc(&tmem_slot, TMEM_COLS);
+    if (warp == 1) { if constexpr (TWO) tmem_alloc2(&tmem_slot, TMEM_COLS); else tmem_alloc(&tmem_slot, TMEM_COLS); }
     tc_fence_before();
     __syncthreads();
+    if constexpr (TWO) cluster_sync_all();       // the peer's barriers are initialised before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
 
@@ -238,20 +306,25 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // elected lane issues)
         {
             int sa = 0, pa = 0, sb = 0, pb = 0;
-            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+            for (int tile = walker; tile < a.total_tiles; tile += walkers) {
                 const int n_tile = tile % a.n_tiles, ml = tile / a.n_tiles;
-                const int m_tile = ml % a.m_tiles, b = ml / a.m_tiles;
-                const int row0 = m_tile * BM + a.a_row0, n0 = n_tile * BN;
+                const int m_tile = TWO ? 2 * (ml % a.m_tiles) + (int)rank : ml % a.m_tiles, b = ml / a.m_tiles;
+                const int row0 = m_tile * BM + a.a_row0, n0 = n_tile * BN + (TWO ? (int)rank * BROWS : 0);
                 for (int kc = 0; kc < a.k_chunks; ++kc) {
                     for (int tap = 0; tap < a.ntaps; ++tap) {
                         if (tap == 0 || !a.a_reuse) {
                             mbar_wait(&bar_a_empty[sa], pa ^ 1);
                             if (elect_one()) {
-                                mbar_expect_tx(&bar_a_full[sa], a_stage);
                                 const int arow = row0 + (a.a_reuse ? a.a_min_off : a.tap_off[tap]);
-                                if (a.split == 0) {
+                                if constexpr (TWO) {
+                                    // both CTAs' bytes are credited to the leader's barrier
+                                    if (rank == 0) mbar_expect_tx(&bar_a_full[sa], 2 * a_stage);
+                                    tma_load_4d_2sm(smA + sa * a_stage, &tmA, mapa_u32(&bar_a_full[sa], 0), kc * BK, arow, b, 0);
+                                } else if (a.split == 0) {
+                                    mbar_expect_tx(&bar_a_full[sa], a_stage);
                                     tma_load_4d(smA + sa * a_stage, &tmA, &bar_a_full[sa], kc * BK, arow, b, 0);
                                 } else {
+                                    mbar_expect_tx(&bar_a_full[sa], a_stage);
                                     const int nr = a.split == 2 ? 2 : 1, hr = a.a_box_rows / nr;
                                     for (int pl = 0; pl < 2; ++pl)
                                         for (int rh = 0; rh < nr; ++rh)
@@ -263,10 +336,14 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         }
                         mbar_wait(&bar_b_empty[sb], pb ^ 1);
                         if (elect_one()) {
-                            mbar_expect_tx(&bar_b_full[sb], B_STAGE);
-                            if (a.split == 0) {
+                            if constexpr (TWO) {
+                                if (rank == 0) mbar_expect_tx(&bar_b_full[sb], 2 * B_STAGE);
+                                tma_load_4d_2sm(smB + sb * B_STAGE, &tmB, mapa_u32(&bar_b_full[sb], 0), kc * BK, n0, tap, 0);
+                            } else if (a.split == 0) {
+                                mbar_expect_tx(&bar_b_full[sb], B_STAGE);
                                 tma_load_4d(smB + sb * B_STAGE, &tmB, &bar_b_full[sb], kc * BK, n0, tap, 0);
                             } else {
+                                mbar_expect_tx(&bar_b_full[sb], B_STAGE);
                                 const int nr = a.split == 2 ? 2 : 1, hr = BN / nr;
                                 for (int pl = 0; pl < 2; ++pl)
                                     for (int rh = 0; rh < nr; ++rh)
@@ -285,9 +362,9 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // accumulation, i.e. -23 dB end to end over chains of up to 1008 MMAs), so a TMEM buffer
         // only ever holds a *segment* of seg_iters stages; the epilogue warps add the segments in
         // registers with round-to-nearest.  Within a stage the two small cross terms go first.
-        {
+        if (!TWO || rank == 0) {
             int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pas = 0, cur_a = 0;
-            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+            for (int tile = walker; tile < a.total_tiles; tile += walkers) {
                 uint32_t tmem_acc = 0, accum = 0;
                 int it = 0;
                 for (int kc = 0; kc < a.k_chunks; ++kc) {
@@ -341,9 +418,13 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
                                         for (int ks = 0; ks < BK / 16; ++ks) {
                                             if (FULL || ks < ksteps) {
-                                                const uint32_t td = (a.alt_acc && (ks & 1)) ? (tmem_acc ^ ACC_COLS) : tmem_acc;
-                                                if (pass == 0 && ks == 0) mma_f16_ss(td, ap, bp, smem_desc_hi<BK>(), IDESC, accum);
-                                                else mma_f16_ss_acc(td, ap + ks * 2, bp + ks * 2, smem_desc_hi<BK>(), IDESC);
+                                                if constexpr (TWO) {
+                                                    if (pass == 0 && ks == 0) mma2_f16_ss(tmem_acc, ap, bp, smem_desc_hi<BK>(), IDESC, accum);
+                                                    else mma2_f16_ss_acc(tmem_acc, ap + ks * 2, bp + ks * 2, smem_desc_hi<BK>(), IDESC);
+                                                } else {
+                                                    if (pass == 0 && ks == 0) mma_f16_ss(tmem_acc, ap, bp, smem_desc_hi<BK>(), IDESC, accum);
+                                                    else mma_f16_ss_acc(tmem_acc, ap + ks * 2, bp + ks * 2, smem_desc_hi<BK>(), IDESC);
+                                                }
                                             }
                                         }
                                     }
@@ -351,9 +432,15 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             };
                             if (ksteps == BK / 16) issue(std::true_type{});
                             else issue(std::false_type{});
-                            mma_commit(&bar_b_empty[sb]);
-                            if (last_of_a) mma_commit(&bar_a_empty[cur_a]);
-                            if (last_of_seg) mma_commit(&bar_acc_full[as]);
+                            if constexpr (TWO) {
+                                mma2_commit_both(&bar_b_empty[sb]);
+                                if (last_of_a) mma2_commit_both(&bar_a_empty[cur_a]);
+                                if (last_of_seg) mma2_commit_both(&bar_acc_full[as]);
+                            } else {
+                                mma_commit(&bar_b_empty[sb]);
+                                if (last_of_a) mma_commit(&bar_a_empty[cur_a]);
+                                if (last_of_seg) mma_commit(&bar_acc_full[as]);
+                            }
                         }
                         __syncwarp();
                         accum = 1;
@@ -373,9 +460,10 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int nseg = (iters_per_tile + a.seg_iters - 1) / a.seg_iters;
         const int etid = threadIdx.x - 64;
         int as = 0, pas = 0, par_tile = -1;
-        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const uint32_t acc_empty_leader[2] = {TWO ? mapa_u32(&bar_acc_empty[0], 0) : 0u, TWO ? mapa_u32(&bar_acc_empty[1], 0) : 0u};
+        for (int tile = walker; tile < a.total_tiles; tile += walkers) {
             const int n_tile = tile % a.n_tiles, ml = tile / a.n_tiles;
-            const int m_tile = ml % a.m_tiles, b = ml / a.m_tiles;
+            const int m_tile = TWO ? 2 * (ml % a.m_tiles) + (int)rank : ml % a.m_tiles, b = ml / a.m_tiles;
             const int m = m_tile * BM + q * 32 + lane, n0 = n_tile * BN + h * HN;
             const bool valid = m < a.M;
             if (n_tile != par_tile) {
@@ -436,7 +524,10 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_acc_empty[as]);
+                if (lane == 0) {
+                    if constexpr (TWO) mbar_arrive_cluster(acc_empty_leader[as]);   // the leader's MMA warp owns the buffer hand-back
+                    else mbar_arrive(&bar_acc_empty[as]);
+                }
                 as ^= 1; if (as == 0) pas ^= 1;
             }
             if (!valid) continue;
@@ -502,7 +593,8 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __syncwarp();
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (TWO) cluster_sync_all();       // neither CTA leaves while its pair may still read its memory
+    if (warp == 1) { if constexpr (TWO) tmem_dealloc2(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -570,13 +662,34 @@ cudaError_t launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const Tc
                         cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, BK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              SMEM_BUDGET + 1024);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    tapgemm_tc_kernel<BN, BK><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, a);
+    tapgemm_tc_kernel<BN, BK, false><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, a);
     return cudaGetLastError();
+}
+
+// cta_group::2 launch: clusters of two CTAs
+template <int BN, int BK>
+cudaError_t launch_inst2(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, int grid, size_t smem,
+                         cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, BK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             SMEM_BUDGET + 1024);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, tapgemm_tc_kernel<BN, BK, true>, tmA, tmB, a);
 }
 
 template <int BK>
@@ -640,7 +753,16 @@ cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int n
     // seg_mmas counts MMAs into the main accumulator per segment as in the 3-pass form (3 per k-step);
     // the concatenated form (BN <= 128) keeps the same number of k-steps per segment
     a.seg_iters = std::max(1, seg_mmas / (3 * BK / 16));
+    // cta_group::2 pairs: for the wide layers (column tile 192 or 128, several M tiles per window)
+    // Measured (tools/probe_pair.py, 4 windows): conv7 C = 768 / 384 / 192: 0.202 -> 0.152, 0.260 -> 0.209,
+    // 0.257 -> 0.225 ms; conv-in 0.131 -> 0.097; but the thin layers (1x1 convs, 2-tap transposed convs with
+    // K <= 384) lose a few per cent to the pair's coupling, hence the taps * K threshold.
+    // Only for BN = 192, where the single-CTA kernel runs the same three passes: results are then bit-identical
+    // whichever mode a batch size selects (the BN <= 128 single-CTA form concatenates two passes).
+    const bool two = !(flags & VOC_TC_NO_PAIR) && BK == 64 && BN == 192 && p.M > BM &&
+                     (long long)p.ntaps * p.K >= 1024;
     a.m_tiles = (p.M + BM - 1) / BM; a.n_tiles = p.N / BN; a.k_chunks = (p.K + BK - 1) / BK;
+    if (two) a.m_tiles = (a.m_tiles + 1) / 2;             // M-tile pairs
     a.total_tiles = a.m_tiles * a.n_tiles * p.B;
     a.wscale = p.wscale;
     a.bias = p.bias; a.act = p.act; a.scale = p.scale;
@@ -650,7 +772,7 @@ cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int n
     a.sn_a = p.sn_a; a.sn_invb = p.sn_invb;
 
     // stage plan
-    const int a_stage = 2 * a.a_box_rows * BK * 2, b_stage = 2 * BN * BK * 2;
+    const int a_stage = 2 * a.a_box_rows * BK * 2, b_stage = 2 * (two ? BN / 2 : BN) * BK * 2;
     if (a.a_reuse) {
         a.SA = 2;
         a.SB = std::min(MAX_STAGES, (SMEM_BUDGET - a.SA * a_stage) / b_stage);
@@ -665,13 +787,19 @@ cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int n
     const long long a_bs = p.B > 1 ? p.a_bstride : (long long)p.a_rows * p.lda;
     const long long a_plane = (long long)(p.A_lo - p.A_hi);
     if (a_plane % 8 || a_plane <= 0) return cudaErrorInvalidValue;
-    a.split = (flags >> 4) & 3;
-    a.alt_acc = (flags >> 6) & 1;
-    const int nr = a.split == 2 ? 2 : 1, npl = a.split ? 1 : 2;
+    a.split = two ? 0 : (flags >> 4) & 3;
+    a.alt_acc = 0;
+    const int nr = two ? 1 : (a.split == 2 ? 2 : 1), npl = a.split ? 1 : 2;
     if (!get_map(p.A_hi, p.K, p.a_rows, p.B, (long long)p.lda * 2, a_bs * 2, a_plane * 2, BK, a.a_box_rows / nr, npl, &tmA))
         return cudaErrorInvalidValue;
-    if (!get_map(p.Wtc, p.K, p.N, p.ntaps, (long long)p.K * 2, (long long)p.N * p.K * 2, p.wtc_plane * 2, BK, BN / nr, npl, &tmB))
+    if (!get_map(p.Wtc, p.K, p.N, p.ntaps, (long long)p.K * 2, (long long)p.N * p.K * 2, p.wtc_plane * 2, BK,
+                 two ? BN / 2 : BN / nr, npl, &tmB))
         return cudaErrorInvalidValue;
+    if (two) {
+        const int sms = num_sms > 0 ? num_sms : 148;
+        const int grid2 = 2 * std::min(a.total_tiles, sms / 2);
+        return launch_inst2<192, 64>(tmA, tmB, a, grid2, smem, st);
+    }
 
     int grid = std::min(a.total_tiles, num_sms > 0 ? num_sms : 148);
     if (flags & VOC_TC_HALF_GRID) grid = std::max(1, grid / 2);      // experiment: contention vs work
