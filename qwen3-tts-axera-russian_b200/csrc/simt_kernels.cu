@@ -484,13 +484,71 @@ cudaError_t voc_launch_swiglu(const float* gu, VocAct out, long long rows, int i
 // =====================================================================================
 // K7: output head -- causal Conv1d(C -> 1, k) on the Snake-activated signal + clamp(-1, 1)
 // (sibling :3757-3761,3778).  HBM-bound: C*4 bytes read per output sample.
-// A (64 + k - 1) x C tile is staged in shared memory with coalesced loads, then four threads
-// share one output sample (C/4 channels each) and reduce by shuffle.
+// One lane per time step: the lane streams its own row (C channels, 16-byte loads; a warp covers
+// 32 consecutive rows = one contiguous span) and forms the k per-tap dot products
+// p_j[t] = sum_c w[j][c] * s[t][c] against weights broadcast from shared memory; the output is
+// out[t] = b + sum_j p_j[t - (k-1-j)], i.e. k warp shuffles.  Consecutive warps overlap by k-1 rows.
 // =====================================================================================
+template <int KS>
 __global__ void __launch_bounds__(256)
-head_kernel(VocAct S, long long s_bstride, int L, int C, int ksz,
-            const float* __restrict__ w /*[k][C]*/, float bias, float* __restrict__ out,
-            long long o_bstride) {
+head_kernel(VocAct S, long long s_bstride, int L, int C, const float* __restrict__ w /*[k][C]*/, float bias,
+            float* __restrict__ out, long long o_bstride) {
+    extern __shared__ float ws[];           // KS x C
+    for (int idx = threadIdx.x; idx < KS * C; idx += blockDim.x) ws[idx] = w[idx];
+    __syncthreads();
+    constexpr int OUT_PER_WARP = 32 - (KS - 1);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    const int t0 = (blockIdx.x * (blockDim.x >> 5) + warp) * OUT_PER_WARP;   // first output of this warp
+    if (t0 >= L) return;
+    const int t = t0 - (KS - 1) + lane;                                      // the row this lane reads
+    const bool have = t >= 0 && t < L;
+    float p[KS];
+#pragma unroll
+    for (int j = 0; j < KS; ++j) p[j] = 0.f;
+    const long long base = (long long)b * s_bstride + (long long)t * C;
+    for (int c = 0; c < C; c += 8) {
+        float x[8];
+        if (!have) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = 0.f;
+        } else if (S.f) {
+            const float4 u = *reinterpret_cast<const float4*>(S.f + base + c);
+            const float4 v = *reinterpret_cast<const float4*>(S.f + base + c + 4);
+            x[0] = u.x; x[1] = u.y; x[2] = u.z; x[3] = u.w; x[4] = v.x; x[5] = v.y; x[6] = v.z; x[7] = v.w;
+        } else {
+            const uint4 h = *reinterpret_cast<const uint4*>(S.hi + base + c);
+            const uint4 l = *reinterpret_cast<const uint4*>(S.lo + base + c);
+            const __half2* hh = reinterpret_cast<const __half2*>(&h);
+            const __half2* ll = reinterpret_cast<const __half2*>(&l);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 a = __half22float2(hh[i]), d = __half22float2(ll[i]);
+                x[2 * i] = a.x + d.x; x[2 * i + 1] = a.y + d.y;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < KS; ++j) {
+            const float4 w0 = *reinterpret_cast<const float4*>(ws + j * C + c);
+            const float4 w1 = *reinterpret_cast<const float4*>(ws + j * C + c + 4);
+            p[j] = fmaf(w0.x, x[0], p[j]); p[j] = fmaf(w0.y, x[1], p[j]);
+            p[j] = fmaf(w0.z, x[2], p[j]); p[j] = fmaf(w0.w, x[3], p[j]);
+            p[j] = fmaf(w1.x, x[4], p[j]); p[j] = fmaf(w1.y, x[5], p[j]);
+            p[j] = fmaf(w1.z, x[6], p[j]); p[j] = fmaf(w1.w, x[7], p[j]);
+        }
+    }
+    // out[t] = bias + sum_j p_j[t - (KS-1-j)]: tap j comes from the lane (KS-1-j) below
+    float acc = p[KS - 1];
+#pragma unroll
+    for (int j = 0; j < KS - 1; ++j) acc += __shfl_up_sync(0xffffffffu, p[j], KS - 1 - j);
+    if (lane >= KS - 1 && t < L) out[(long long)b * o_bstride + t] = fminf(1.f, fmaxf(-1.f, acc + bias));
+}
+
+// generic tap count (any k <= VOC_MAX_TAPS that has no specialisation): staged tile, 4 threads per sample
+__global__ void __launch_bounds__(256)
+head_kernel_generic(VocAct S, long long s_bstride, int L, int C, int ksz,
+                    const float* __restrict__ w /*[k][C]*/, float bias, float* __restrict__ out,
+                    long long o_bstride) {
     extern __shared__ float sh[];
     const int TT = 64;
     const int CP = C + 1;
@@ -524,13 +582,19 @@ cudaError_t voc_launch_head(VocAct S, long long s_bstride, int L, int C, int ksz
                             float bias, float* out, long long o_bstride, int B, cudaStream_t st) {
     if (C % 4) return cudaErrorInvalidValue;
     if (B <= 0 || L <= 0) return cudaSuccess;
+    if (ksz == 7 && C % 8 == 0 && s_bstride % 8 == 0) {
+        const int out_per_block = 8 * (32 - 6);
+        dim3 grid((L + out_per_block - 1) / out_per_block, B);
+        head_kernel<7><<<grid, 256, (size_t)7 * C * sizeof(float), st>>>(S, s_bstride, L, C, w, bias, out, o_bstride);
+        return cudaGetLastError();
+    }
     const size_t smem = ((size_t)(64 + ksz - 1) * (C + 1) + (size_t)ksz * C) * sizeof(float);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(head_kernel_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     dim3 grid((L + 63) / 64, B);
-    head_kernel<<<grid, 256, smem, st>>>(S, s_bstride, L, C, ksz, w, bias, out, o_bstride);
+    head_kernel_generic<<<grid, 256, smem, st>>>(S, s_bstride, L, C, ksz, w, bias, out, o_bstride);
     return cudaGetLastError();
 }
 

@@ -752,7 +752,8 @@ cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int n
     const int seg_mmas = (flags >> 8) > 0 ? (flags >> 8) : 24;
     // seg_mmas counts MMAs into the main accumulator per segment as in the 3-pass form (3 per k-step);
     // the concatenated form (BN <= 128) keeps the same number of k-steps per segment
-    a.seg_iters = std::max(1, seg_mmas / (3 * BK / 16));
+    // (one MMA per k-step reaches its main accumulator, so a segment may span three times the k-steps)
+    a.seg_iters = std::max(1, seg_mmas / ((BN <= 128 ? 1 : 3) * BK / 16));
     // cta_group::2 pairs: for the wide layers (column tile 192 or 128, several M tiles per window)
     // Measured (tools/probe_pair.py, 4 windows): conv7 C = 768 / 384 / 192: 0.202 -> 0.152, 0.260 -> 0.209,
     // 0.257 -> 0.225 ms; conv-in 0.131 -> 0.097; but the thin layers (1x1 convs, 2-tap transposed convs with
