@@ -204,6 +204,20 @@ __device__ __forceinline__ void mma2_commit_both(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
+// 256-bit global accesses (sm_100): one full 32-byte sector per lane per instruction
+__device__ __forceinline__ void ldg256(const void* p, float (&r)[8]) {
+    asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+                 : "l"(p) : "memory");
+}
+__device__ __forceinline__ void stg256(void* p, const float (&r)[8]) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]) : "memory");
+}
+__device__ __forceinline__ void stg256u(void* p, const uint32_t (&r)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(
@@ -247,6 +261,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ TcArgs a) {
     static_assert(BN % 32 == 0 && BN >= 32 && BN <= 192, "UMMA N; BN/COL_PARTS columns per epilogue thread");
+    static_assert((BN / COL_PARTS) % 16 == 0, "the epilogue stores 16 operand columns (one sector) at a time");
     static_assert(BK == 64 || BK == 32, "one swizzle atom per K-chunk");
     constexpr int HN = BN / COL_PARTS;                        // columns per epilogue thread
     constexpr int PB = HN <= 64 ? HN : 16;                    // residual prefetch window (columns)
@@ -483,10 +498,10 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             // The residual is independent of the MMAs: its loads are issued before the accumulator
             // wait (whole row when it fits the register budget, else a rolling 16-column window).
             const float* Rrow = (a.R && valid) ? a.R + (long long)b * a.r_bstride + (long long)m * a.ldr + n0 : nullptr;
-            float4 rpf[2][PB / 4];
+            float rpf[2][PB / 8][8];
             if (Rrow) {
 #pragma unroll
-                for (int i = 0; i < PB / 4; ++i) rpf[0][i] = *reinterpret_cast<const float4*>(Rrow + 4 * i);
+                for (int i = 0; i < PB / 8; ++i) ldg256(Rrow + 8 * i, rpf[0][i]);
             }
             float acc[HN];
 #pragma unroll
@@ -534,58 +549,63 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             float* Yrow = a.Y ? a.Y + (long long)b * a.y_bstride + (long long)m * a.ldy + n0 : nullptr;
             const long long soff = (long long)b * a.s_bstride + (long long)m * a.lds + n0;
 #pragma unroll
-            for (int g = 0; g < HN; g += 8) {
-                const int pc = h * HN + g;             // column within the tile
-                const int pcur = (g / PB) & 1;
-                if (Rrow && (g % PB) == 0 && g + PB < HN) {
+            for (int g16 = 0; g16 < HN; g16 += 16) {
+                uint32_t hi16[8], lo16[8];             // 16 columns of the operand planes = one 32-byte sector each
 #pragma unroll
-                    for (int i = 0; i < PB / 4; ++i)
-                        rpf[pcur ^ 1][i] = *reinterpret_cast<const float4*>(Rrow + g + PB + 4 * i);
-                }
-                float v[8];
+                for (int g = g16; g < g16 + 16; g += 8) {
+                    const int pc = h * HN + g;         // column within the tile
+                    const int pcur = (g / PB) & 1;
+                    if (Rrow && (g % PB) == 0 && g + PB < HN) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = acc[g + j] * a.wscale;
-                if (a.bias) {
-                    const float4 b0 = *reinterpret_cast<const float4*>(&epi_par[0][pc]);
-                    const float4 b1 = *reinterpret_cast<const float4*>(&epi_par[0][pc + 4]);
-                    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                }
-                if (a.act == VOC_ACT_GELU) {
+                        for (int i = 0; i < PB / 8; ++i) ldg256(Rrow + g + PB + 8 * i, rpf[pcur ^ 1][i]);
+                    }
+                    float v[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = voc_gelu(v[j]);
-                }
-                if (a.scale) {
-                    const float4 s0 = *reinterpret_cast<const float4*>(&epi_par[1][pc]);
-                    const float4 s1 = *reinterpret_cast<const float4*>(&epi_par[1][pc + 4]);
-                    v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w;
-                    v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
-                }
-                if (Rrow) {
-                    const float4 r0 = rpf[pcur][(g % PB) / 4], r1 = rpf[pcur][(g % PB) / 4 + 1];
-                    v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-                    v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
-                }
-                if (Yrow) {
-                    *reinterpret_cast<float4*>(Yrow + g) = make_float4(v[0], v[1], v[2], v[3]);
-                    *reinterpret_cast<float4*>(Yrow + g + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                    for (int j = 0; j < 8; ++j) v[j] = acc[g + j] * a.wscale;
+                    if (a.bias) {
+                        const float4 b0 = *reinterpret_cast<const float4*>(&epi_par[0][pc]);
+                        const float4 b1 = *reinterpret_cast<const float4*>(&epi_par[0][pc + 4]);
+                        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                    }
+                    if (a.act == VOC_ACT_GELU) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = voc_gelu(v[j]);
+                    }
+                    if (a.scale) {
+                        const float4 s0 = *reinterpret_cast<const float4*>(&epi_par[1][pc]);
+                        const float4 s1 = *reinterpret_cast<const float4*>(&epi_par[1][pc + 4]);
+                        v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w;
+                        v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
+                    }
+                    if (Rrow) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] += rpf[pcur][(g % PB) / 8][j];
+                    }
+                    if (Yrow) stg256(Yrow + g, v);
+                    if (a.S_hi) {
+                        if (a.sn_a) {
+                            const float4 a0 = *reinterpret_cast<const float4*>(&epi_par[2][pc]);
+                            const float4 a1 = *reinterpret_cast<const float4*>(&epi_par[2][pc + 4]);
+                            const float4 i0 = *reinterpret_cast<const float4*>(&epi_par[3][pc]);
+                            const float4 i1 = *reinterpret_cast<const float4*>(&epi_par[3][pc + 4]);
+                            v[0] = voc_snake(v[0], a0.x, i0.x); v[1] = voc_snake(v[1], a0.y, i0.y);
+                            v[2] = voc_snake(v[2], a0.z, i0.z); v[3] = voc_snake(v[3], a0.w, i0.w);
+                            v[4] = voc_snake(v[4], a1.x, i1.x); v[5] = voc_snake(v[5], a1.y, i1.y);
+                            v[6] = voc_snake(v[6], a1.z, i1.z); v[7] = voc_snake(v[7], a1.w, i1.w);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            __half2 hh, ll;
+                            voc_split2(v[2 * j], v[2 * j + 1], hh, ll);
+                            hi16[(g - g16) / 2 + j] = *reinterpret_cast<uint32_t*>(&hh);
+                            lo16[(g - g16) / 2 + j] = *reinterpret_cast<uint32_t*>(&ll);
+                        }
+                    }
                 }
                 if (a.S_hi) {
-                    if (a.sn_a) {
-                        const float4 a0 = *reinterpret_cast<const float4*>(&epi_par[2][pc]);
-                        const float4 a1 = *reinterpret_cast<const float4*>(&epi_par[2][pc + 4]);
-                        const float4 i0 = *reinterpret_cast<const float4*>(&epi_par[3][pc]);
-                        const float4 i1 = *reinterpret_cast<const float4*>(&epi_par[3][pc + 4]);
-                        v[0] = voc_snake(v[0], a0.x, i0.x); v[1] = voc_snake(v[1], a0.y, i0.y);
-                        v[2] = voc_snake(v[2], a0.z, i0.z); v[3] = voc_snake(v[3], a0.w, i0.w);
-                        v[4] = voc_snake(v[4], a1.x, i1.x); v[5] = voc_snake(v[5], a1.y, i1.y);
-                        v[6] = voc_snake(v[6], a1.z, i1.z); v[7] = voc_snake(v[7], a1.w, i1.w);
-                    }
-                    __half2 hh[4], ll[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) voc_split2(v[2 * j], v[2 * j + 1], hh[j], ll[j]);
-                    *reinterpret_cast<uint4*>(a.S_hi + soff + g) = *reinterpret_cast<const uint4*>(hh);
-                    *reinterpret_cast<uint4*>(a.S_lo + soff + g) = *reinterpret_cast<const uint4*>(ll);
+                    stg256u(a.S_hi + soff + g16, hi16);
+                    stg256u(a.S_lo + soff + g16, lo16);
                 }
             }
         }
@@ -711,9 +731,11 @@ bool voc_tc_eligible(const TapGemmParams& p) {
     if (!p.A_hi || !p.A_lo || !p.Wtc || p.S) return false;
     if (p.K % 8 || p.lda % 8 || p.N % 32 || p.K < 16) return false;
     if (p.ntaps < 1 || p.ntaps > VOC_MAX_TAPS) return false;
-    if (p.Y && (p.ldy % 4)) return false;
-    if (p.R && (p.ldr % 4)) return false;
-    if (p.S_hi && (p.lds % 8 || p.s_bstride % 8)) return false;
+    // the epilogue moves 32-byte sectors: 8 floats of Y / R, 16 halves of each operand plane
+    auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
+    if (p.Y && (p.ldy % 8 || p.y_bstride % 8 || !al32(p.Y))) return false;
+    if (p.R && (p.ldr % 8 || p.r_bstride % 8 || !al32(p.R))) return false;
+    if (p.S_hi && (p.lds % 16 || p.s_bstride % 16 || !al32(p.S_hi) || !al32(p.S_lo))) return false;
     if (p.B > 1 && (p.a_bstride % 8)) return false;
     if ((p.A_lo - p.A_hi) % 8 || p.A_lo <= p.A_hi || p.wtc_plane % 8) return false;
     if ((reinterpret_cast<uintptr_t>(p.A_hi) | reinterpret_cast<uintptr_t>(p.Wtc)) & 15) return false;
