@@ -782,8 +782,12 @@ cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int n
     // K <= 384) lose a few per cent to the pair's coupling, hence the taps * K threshold.
     // Only for BN = 192, where the single-CTA kernel runs the same three passes: results are then bit-identical
     // whichever mode a batch size selects (the BN <= 128 single-CTA form concatenates two passes).
-    const bool two = !(flags & VOC_TC_NO_PAIR) && BK == 64 && BN == 192 && p.M > BM &&
-                     (long long)p.ntaps * p.K >= 1024;
+    // BN = 96 (C = 96, the 7-tap convs): the pair halves the weight bytes each CTA re-streams per tile, which is
+    // what bounds that layer (258 KB per 128 rows).  Its single-CTA form is the concatenated one, so the choice
+    // must not depend on the batch: M here is the per-window length, the same for any number of windows.
+    const bool two = !(flags & VOC_TC_NO_PAIR) && BK == 64 && p.M > BM &&
+                     ((BN == 192 && (long long)p.ntaps * p.K >= 1024) ||
+                      (BN == 96 && (long long)p.ntaps * p.K >= 512));
     a.m_tiles = (p.M + BM - 1) / BM; a.n_tiles = p.N / BN; a.k_chunks = (p.K + BK - 1) / BK;
     if (two) a.m_tiles = (a.m_tiles + 1) / 2;             // M-tile pairs
     a.total_tiles = a.m_tiles * a.n_tiles * p.B;
@@ -821,7 +825,8 @@ cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int n
     if (two) {
         const int sms = num_sms > 0 ? num_sms : 148;
         const int grid2 = 2 * std::min(a.total_tiles, sms / 2);
-        return launch_inst2<192, 64>(tmA, tmB, a, grid2, smem, st);
+        return BN == 192 ? launch_inst2<192, 64>(tmA, tmB, a, grid2, smem, st)
+                         : launch_inst2<96, 64>(tmA, tmB, a, grid2, smem, st);
     }
 
     int grid = std::min(a.total_tiles, num_sms > 0 ? num_sms : 148);
