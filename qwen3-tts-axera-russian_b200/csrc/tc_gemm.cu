@@ -46,7 +46,6 @@ struct TcArgs {
     int M, N, K, B, ntaps, a_row0;
     int tap_off[VOC_MAX_TAPS];
     int a_reuse, a_min_off, a_box_rows, seg_iters;
-    int alt_acc;          // experiment (timing only, results wrong): alternate k-steps between both TMEM buffers
     int split;            // 0: one TMA per stage operand (2-plane box), 1: one per plane, 2: per plane x row half
     int m_tiles, n_tiles, k_chunks, total_tiles;
     int SA, SB;
@@ -815,7 +814,6 @@ cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int n
     const long long a_plane = (long long)(p.A_lo - p.A_hi);
     if (a_plane % 8 || a_plane <= 0) return cudaErrorInvalidValue;
     a.split = two ? 0 : (flags >> 4) & 3;
-    a.alt_acc = 0;
     const int nr = two ? 1 : (a.split == 2 ? 2 : 1), npl = a.split ? 1 : 2;
     if (!get_map(p.A_hi, p.K, p.a_rows, p.B, (long long)p.lda * 2, a_bs * 2, a_plane * 2, BK, a.a_box_rows / nr, npl, &tmA))
         return cudaErrorInvalidValue;

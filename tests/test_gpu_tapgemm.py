@@ -5,7 +5,10 @@ offset 1 under transconv_trim = "both"), Linear / 1x1 conv, with the fused epilo
 (bias, exact GELU, per-channel scale, residual, SnakeBeta, split-fp16 operand output).
 
 Tolerance: the tensor path multiplies split-fp16 operands (~22 mantissa bits) and accumulates in
-FP32, so a dot product of O(1) terms is good to a few 1e-6 relative to the output scale."""
+FP32, so a dot product of O(1) terms is good to a few 1e-6 relative to the output scale.
+
+tc_flags: 0 = default (tap reuse through row-shifted descriptors, cta_group::2 pairs where the launcher
+selects them), 1 = per-tap aligned loads, 128 = single-CTA kernel only."""
 import numpy as np
 import pytest
 
@@ -46,10 +49,16 @@ CASES = [
     ("convt_trim_both",  2, 100,  192, 288,  99, 1, [0, -1]),
     ("convt_trim_right", 2, 100,   64, 320, 100, 0, [0, -1]),
     ("tiny_k16",         1, 150,   16,  32, 150, 0, [-2, -1, 0]),
+    # cta_group::2 pair mode (BN = 192 with taps*K >= 1024; BN = 96 with taps*K >= 512): odd numbers of M tiles
+    # (the pair's second CTA gets an all-padding tile), several windows, K tail (K = 96 in 64-wide chunks)
+    ("pair_conv7_c192",  3, 650,  192, 192, 650, 0, [-54, -45, -36, -27, -18, -9, 0]),
+    ("pair_conv7_c96",   2, 900,   96,  96, 900, 0, [-6, -5, -4, -3, -2, -1, 0]),
+    ("pair_convt_k768",  2, 300,  768, 384, 299, 1, [0, -1]),
+    ("pair_linear_2ntile", 1, 1000, 1024, 384, 1000, 0, [0]),
 ]
 
 
-@pytest.mark.parametrize("flags", [0, 1], ids=["tap_reuse", "no_reuse"])
+@pytest.mark.parametrize("flags", [0, 1, 128], ids=["default", "no_tap_reuse", "no_pairs"])
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_tc_tapgemm_matches_float64(backend, case, flags):
     name, B, a_rows, K, N, M, row0, taps = case
