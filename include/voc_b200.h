@@ -81,6 +81,15 @@ int voc_synthesize_pcm16(void* h, const long long* codes, int n_tokens, short* o
 int voc_synthesize_dev(void* h, const long long* d_codes, int n_tokens, float* d_out_f32,
                        short* d_out_i16, long long cap, long long* n_out, void* stream);
 
+/* ---- level 2, batched: many requests in one call -------------------------
+ * What a server does with the streaming client's concurrent 64-token requests
+ * (dual_npu/tts_client.py:188-197) or a corpus of utterances: the windows of all requests share
+ * batched launches and one stitch.  codes = the requests' [n_tokens[u]][16] arrays concatenated;
+ * request u's PCM is out[out_offsets[u] .. out_offsets[u+1]) (out_offsets has n_requests + 1
+ * entries), each bit-identical to voc_synthesize_pcm16 on that request alone.                */
+int voc_synthesize_batch_pcm16(void* h, const long long* codes, const int* n_tokens, int n_requests,
+                               short* out, long long cap, long long* out_offsets);
+
 /* The _dev twins do not synchronise, so an out-of-range code cannot be reported by their
  * return value.  voc_check_dev synchronises `stream` and returns VOC_E_INVALID if any launch
  * since the last check met a code outside [0, codebook_size) (and clears the flag).        */

@@ -45,6 +45,8 @@ SIGNATURES = {
                                            C.c_void_p, C.c_void_p, C.c_longlong,
                                            C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
                                            C.c_void_p]),
+    "voc_synthesize_batch_pcm16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong,
+                                             C.c_void_p]),
     "voc_check_dev": (C.c_int, [C.c_void_p, C.c_void_p]),
     "voc_plan": (C.c_int, [C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_void_p,
                            C.POINTER(C.c_longlong), C.POINTER(C.c_int)]),
@@ -241,6 +243,21 @@ class Vocoder:
         self._ck(self.lib.voc_synthesize_pcm16(self._h, codes.ctypes.data, len(codes), out.ctypes.data,
                                                out.size, C.byref(n)))
         return out[: n.value]
+
+    def synthesize_batch_pcm16(self, requests):
+        """Many requests ([n_i, 16] int64 arrays) in one call; returns the list of their int16 PCM arrays,
+        each bit-identical to ``synthesize_pcm16`` on that request alone."""
+        reqs = [self._codes2d(r) for r in requests]
+        if not reqs:
+            return []
+        lens = np.asarray([len(r) for r in reqs], dtype=np.int32)
+        codes = np.ascontiguousarray(np.concatenate(reqs, axis=0))
+        cap = int(sum(self.out_samples(int(n)) for n in lens))
+        out = np.empty(cap, dtype=np.int16)
+        offs = np.zeros(len(reqs) + 1, dtype=np.int64)
+        self._ck(self.lib.voc_synthesize_batch_pcm16(self._h, codes.ctypes.data, lens.ctypes.data, len(reqs),
+                                                     out.ctypes.data, cap, offs.ctypes.data))
+        return [out[offs[i]:offs[i + 1]] for i in range(len(reqs))]
 
     def synthesize_dev(self, d_codes, n_tokens: int, d_out_f32=None, d_out_i16=None, cap: int = 0,
                        stream: int = 0) -> int:

@@ -243,13 +243,15 @@ __device__ __forceinline__ float act_load1(const VocAct& o, long long idx) {
 // reference pads with *code index 0*, not silence (dual_npu/vocoder_server.py:78,93).
 // An out-of-range code raises err_flag (ONNX Runtime's Gather would throw).
 // =====================================================================================
+// win_meta (optional, batched requests): window w reads frames [win_meta[2w], win_meta[2w] + win_meta[2w+1]) of
+// the concatenated code array instead of the single-request rule above.
 __global__ void rvq_gather_kernel(const long long* __restrict__ codes, int n_frames, int frames_per_win,
                                   int win_step, int n_q, int codebook_size,
                                   const float* __restrict__ tables, int dim, VocAct out,
-                                  int* err_flag) {
+                                  int* err_flag, const int* __restrict__ win_meta) {
     const int w = blockIdx.y, t = blockIdx.x;
-    const long long src = (long long)w * win_step + t;
-    const bool have = src < n_frames;
+    const long long src = win_meta ? (long long)win_meta[2 * w] + t : (long long)w * win_step + t;
+    const bool have = win_meta ? t < win_meta[2 * w + 1] : src < n_frames;
     const long long row_out = (long long)w * frames_per_win + t;
     for (int d = threadIdx.x * 4; d < dim; d += blockDim.x * 4) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -266,12 +268,12 @@ __global__ void rvq_gather_kernel(const long long* __restrict__ codes, int n_fra
 
 cudaError_t voc_launch_rvq_gather(const long long* codes, int n_frames, int frames_per_win, int win_step,
                                   int n_windows, int n_q, int codebook_size, const float* tables,
-                                  int dim, VocAct out, int* err_flag, cudaStream_t st) {
+                                  int dim, VocAct out, int* err_flag, cudaStream_t st, const int* win_meta) {
     if (dim % 4) return cudaErrorInvalidValue;
     int threads = dim / 4; if (threads > 256) threads = 256; if (threads < 32) threads = 32;
     dim3 grid(frames_per_win, n_windows);
     rvq_gather_kernel<<<grid, threads, 0, st>>>(codes, n_frames, frames_per_win, win_step, n_q,
-                                                codebook_size, tables, dim, out, err_flag);
+                                                codebook_size, tables, dim, out, err_flag, win_meta);
     return cudaGetLastError();
 }
 

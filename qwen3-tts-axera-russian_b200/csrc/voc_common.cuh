@@ -118,7 +118,8 @@ enum { VOC_TC_NO_REUSE = 1, VOC_TC_BK64 = 2, VOC_TC_BK32 = 4, VOC_TC_HALF_GRID =
 cudaError_t voc_launch_tapgemm_simt(const TapGemmParams& p, cudaStream_t st);
 cudaError_t voc_launch_rvq_gather(const long long* codes, int n_frames, int frames_per_win, int win_step,
                                   int n_windows, int n_q, int codebook_size, const float* tables,
-                                  int dim, VocAct out, int* err_flag, cudaStream_t st);
+                                  int dim, VocAct out, int* err_flag, cudaStream_t st,
+                                  const int* win_meta = nullptr);
 cudaError_t voc_launch_rmsnorm(const float* x, const float* w, VocAct y, int rows, int C, float eps,
                                cudaStream_t st);
 cudaError_t voc_launch_dwconv_ln(const float* x, const float* dw_w, const float* dw_b, const float* ln_w,

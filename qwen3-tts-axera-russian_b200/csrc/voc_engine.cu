@@ -573,7 +573,7 @@ static int engine_finalize(Engine* E) {
 // one wave: windows [w_begin, w_begin + nw) of a request -> chunk_out[nw][Lc]
 // --------------------------------------------------------------------------------------
 static int run_wave(Engine* E, const long long* d_codes, int n_frames, int win_step, int w_begin, int nw,
-                    float* chunk_out, cudaStream_t st) {
+                    float* chunk_out, cudaStream_t st, const int* d_wmeta = nullptr) {
     const Cfg& c = E->cfg;
     const int T = c.chunk_frames;
 #define KLAUNCH(tag, flops, bytes, call) do { ProfScope _ps(E, st, tag, flops, bytes); CK(call); } while (0)
@@ -583,9 +583,10 @@ static int run_wave(Engine* E, const long long* d_codes, int n_frames, int win_s
     // non-GEMM kernels read (f_qkv, f_gu) stay float32.
     // K1: RVQ gather-sum
     KLAUNCH("rvq_gather", 0.0, 4.0 * nw * T * c.rvq_dim * (c.num_quantizers + 1.0),
-            voc_launch_rvq_gather(d_codes + (long long)w_begin * win_step * c.num_quantizers,
-                                  n_frames - w_begin * win_step, T, win_step, nw, c.num_quantizers,
-                                  c.codebook_size, E->rvq_tables, c.rvq_dim, act(E, E->f_rvq), E->d_err, st));
+            voc_launch_rvq_gather(d_wmeta ? d_codes : d_codes + (long long)w_begin * win_step * c.num_quantizers,
+                                  n_frames - (d_wmeta ? 0 : w_begin * win_step), T, win_step, nw, c.num_quantizers,
+                                  c.codebook_size, E->rvq_tables, c.rvq_dim, act(E, E->f_rvq), E->d_err, st,
+                                  d_wmeta ? d_wmeta + 2 * (size_t)w_begin : nullptr));
     if (int r = dbg_capture(E, "rvq", act(E, E->f_rvq), (size_t)nw * T * c.rvq_dim, st)) return r;
     // K2: pre-conv
     {
@@ -852,6 +853,63 @@ static int synth_range(Engine* E, const long long* d_codes, int n, int w0, int w
     return VOC_OK;
 }
 
+// Many requests in one go (what a server does with concurrent connections): the windows of
+// all requests share waves, and one stitch launch -- driven by the same per-window metadata as a single
+// request, with output offsets running on across requests -- writes every request's samples.
+// lens[u] frames per request; out_off[u] = first output sample of request u (out_off[n_utt] = total).
+static int synth_batch(Engine* E, const long long* d_codes, const int* lens, int n_utt, float* d_f32, short* d_i16,
+                       long long cap, long long* out_off, cudaStream_t st) {
+    if (!E->finalized) return fail(E, VOC_E_STATE, "voc_finalize has not been called");
+    CK(cudaSetDevice(E->device));
+    const long long Lc = E->cfg.chunk_samples();
+    std::vector<int> wmeta, smeta;                    // {first frame, frames} and the 6-int stitch records
+    long long total = 0, frame0 = 0;
+    int max_a = 0;
+    for (int u = 0; u < n_utt; ++u) {
+        const int n = lens[u];
+        if (n <= 0 || n > 10000) return fail(E, VOC_E_INVALID, "n_tokens must be in 1..10000 (vocoder_server.py:149)");
+        const Plan P = make_plan(E->cfg, n);
+        if (!P.pairwise) return fail(E, VOC_E_INVALID, "batched synthesis needs the pairwise-overlap regime");
+        out_off[u] = total;
+        for (int w = 0; w < P.n_windows; ++w) {
+            wmeta.push_back((int)(frame0 + P.start[w])); wmeta.push_back(P.len[w]);
+            const long long dst = total + P.dst[w];
+            if (dst + P.a_len[w] > 0x7fffffffLL) return fail(E, VOC_E_INVALID, "batch output exceeds 2^31 samples");
+            smeta.push_back((int)dst); smeta.push_back(P.a_len[w]); smeta.push_back(P.blended[w]);
+            smeta.push_back(w + 1 < P.n_windows ? P.blended[w + 1] : 0);
+            smeta.push_back(w > 0 ? P.a_len[w - 1] : 0); smeta.push_back(0);
+            max_a = std::max(max_a, P.a_len[w]);
+        }
+        total += P.total; frame0 += n;
+    }
+    out_off[n_utt] = total;
+    if (total > cap) return fail(E, VOC_E_INVALID, "output buffer too small");
+    const int nwin = (int)(wmeta.size() / 2);
+    if (int r = ensure_i(E, wmeta.size() + smeta.size())) return r;
+    int* d_wmeta = E->d_meta; int* d_smeta = E->d_meta + wmeta.size();
+    CK(cudaMemcpyAsync(d_wmeta, wmeta.data(), wmeta.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_smeta, smeta.data(), smeta.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));                     // the host vectors go out of scope
+    // windows in groups that bound the chunk buffer (a blend reads the previous window, so a group
+    // never starts on a blended window)
+    const int group_max = std::max(E->wave * 8, 64);
+    for (int g0 = 0; g0 < nwin;) {
+        int g1 = std::min(nwin, g0 + group_max);
+        while (g1 < nwin && smeta[(size_t)g1 * 6 + 2]) ++g1;
+        const int ng = g1 - g0;
+        if (int r = ensure_buf(E, E->chunks, (size_t)ng * Lc)) return r;
+        for (int w = g0; w < g1; w += E->wave) {
+            const int nw = std::min(E->wave, g1 - w);
+            if (int r = run_wave(E, d_codes, (int)frame0, 0, w, nw, E->chunks.p + (long long)(w - g0) * Lc, st, d_wmeta)) return r;
+        }
+        ProfScope ps(E, st, "stitch", 0.0, 0.0);
+        CK(voc_launch_stitch(E->chunks.p, Lc, d_smeta + (size_t)g0 * 6, ng, 16 * 1920, E->d_fade_out, E->d_fade_in, d_f32,
+                             d_i16, max_a, st));
+        g0 = g1;
+    }
+    return VOC_OK;
+}
+
 static int ensure_codes(Engine* E, size_t n) {
     if (E->codes_cap >= n) return VOC_OK;
     if (E->d_codes) cudaFree(E->d_codes);
@@ -1014,6 +1072,35 @@ int voc_synthesize_f32(void* h, const long long* codes, int n_tokens, float* out
 }
 int voc_synthesize_pcm16(void* h, const long long* codes, int n_tokens, short* out, long long cap, long long* n_out) {
     return synth_host(h, codes, n_tokens, nullptr, out, cap, n_out);
+}
+
+int voc_synthesize_batch_pcm16(void* h, const long long* codes, const int* n_tokens, int n_requests, short* out,
+                               long long cap, long long* out_offsets) {
+    Engine* E = (Engine*)h;
+    if (!E) return VOC_E_INVALID;
+    if (!E->finalized) return fail(E, VOC_E_STATE, "voc_finalize has not been called");
+    if (!codes || !n_tokens || !out || !out_offsets || n_requests <= 0) return fail(E, VOC_E_INVALID, "bad argument");
+    CK(cudaSetDevice(E->device));
+    long long frames = 0, total = 0;
+    for (int u = 0; u < n_requests; ++u) {
+        if (n_tokens[u] <= 0 || n_tokens[u] > 10000) return fail(E, VOC_E_INVALID, "n_tokens must be in 1..10000 (vocoder_server.py:149)");
+        frames += n_tokens[u];
+        total += make_plan(E->cfg, n_tokens[u]).total;
+    }
+    if (total > cap) return fail(E, VOC_E_INVALID, "output buffer too small");
+    if (frames > 0x7fffffffLL / 16) return fail(E, VOC_E_INVALID, "too many frames in one batch");
+    if (int r = ensure_codes(E, (size_t)frames * 16)) return r;
+    CK(cudaMemcpyAsync(E->d_codes, codes, (size_t)frames * 16 * sizeof(long long), cudaMemcpyHostToDevice, E->stream));
+    if (E->pcm_cap < (size_t)total) {
+        if (E->d_pcm) cudaFree(E->d_pcm);
+        E->d_pcm = nullptr; E->pcm_cap = 0;
+        CK(cudaMalloc(&E->d_pcm, (size_t)total * sizeof(short))); E->pcm_cap = (size_t)total;
+    }
+    if (int r = synth_batch(E, E->d_codes, n_tokens, n_requests, nullptr, E->d_pcm, total, out_offsets, E->stream)) return r;
+    if (int r = check_codes_flag(E, E->stream)) return r;
+    CK(cudaMemcpyAsync(out, E->d_pcm, (size_t)total * sizeof(short), cudaMemcpyDeviceToHost, E->stream));
+    CK(cudaStreamSynchronize(E->stream));
+    return VOC_OK;
 }
 
 int voc_check_dev(void* h, void* stream) {

@@ -154,3 +154,24 @@ def test_window_ranges_tile_the_output(full_model):
         covered += cnt
     assert covered == len(full)
     assert np.array_equal(out, full)
+
+
+def test_batched_requests_equal_single_requests(full_model):
+    """voc_synthesize_batch_pcm16: many requests share waves and one stitch; every request's PCM is
+    bit-identical to synthesising it alone (single-window, multi-window, the short-last-window quirk)."""
+    cfg, w, voc = full_model
+    lens = [1, 64, 65, 97, 112, 200, 30, 48, 150]
+    reqs = [_codes(cfg, (n, 16), seed=100 + n) for n in lens]
+    got = voc.synthesize_batch_pcm16(reqs)
+    assert len(got) == len(reqs)
+    for r, g in zip(reqs, got):
+        assert np.array_equal(g, voc.synthesize_pcm16(r)), len(r)
+
+
+def test_batched_requests_reject_bad_input(full_model, backend):
+    cfg, w, voc = full_model
+    bad = _codes(cfg, (10, 16))
+    bad[3, 2] = cfg.codebook_size
+    with pytest.raises(backend.VocoderError):
+        voc.synthesize_batch_pcm16([_codes(cfg, (5, 16)), bad])
+    voc.synthesize_batch_pcm16([_codes(cfg, (5, 16))])
