@@ -42,6 +42,11 @@ int voc_abi_version(void);
 void* voc_create(const char* cfg_json, int device, int wave);
 void  voc_destroy(void* h);
 
+/* voc_create + voc_set_tensor for every tensor + voc_finalize from a .b200voc model file
+ * (weights.py:save_model; safetensors byte layout with the architecture JSON in the metadata).
+ * Replaces: ort.InferenceSession(model_path) for a native caller      vocoder_server.py:39-44 */
+void* voc_create_from_file(const char* path, int device, int wave);
+
 /* Upload one FP32 tensor in torch layout (names and shapes: weights.py:weight_shapes).
  * Replaces the weights baked into vocoder_traced_64.onnx
  * (scripts/export_vocoder_traced.py:74-99).                                               */

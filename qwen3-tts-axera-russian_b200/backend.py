@@ -26,6 +26,7 @@ VOC_OK, VOC_E_INVALID, VOC_E_CUDA, VOC_E_STATE, VOC_E_NOMEM = 0, -1, -2, -3, -4
 SIGNATURES = {
     "voc_abi_version": (C.c_int, []),
     "voc_create": (C.c_void_p, [C.c_char_p, C.c_int, C.c_int]),
+    "voc_create_from_file": (C.c_void_p, [C.c_char_p, C.c_int, C.c_int]),
     "voc_destroy": (None, [C.c_void_p]),
     "voc_set_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_longlong]),
     "voc_finalize": (C.c_int, [C.c_void_p]),

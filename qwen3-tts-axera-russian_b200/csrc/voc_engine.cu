@@ -980,6 +980,134 @@ int voc_finalize(void* h) {
     return engine_finalize(E);
 }
 
+// ---- model container (.b200voc = safetensors byte layout, written by weights.py:save_model) -----------
+// u64 LE header length, JSON header {"__metadata__": {"voc_config": "<config JSON>", ...},
+// "<tensor>": {"dtype": "F32", "shape": [...], "data_offsets": [a, b]}, ...}, then the tensor bytes.
+namespace {
+struct JsonCursor {
+    const char* p; const char* end; bool ok = true;
+    void ws() { while (p < end && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) ++p; }
+    bool eat(char c) { ws(); if (p < end && *p == c) { ++p; return true; } return false; }
+    std::string str() {
+        std::string o; ws();
+        if (p >= end || *p != '"') { ok = false; return o; }
+        ++p;
+        while (p < end && *p != '"') {
+            if (*p == '\\' && p + 1 < end) {
+                ++p;
+                switch (*p) { case 'n': o.push_back('\n'); break; case 't': o.push_back('\t'); break;
+                              case 'r': o.push_back('\r'); break; case 'b': o.push_back('\b'); break;
+                              case 'f': o.push_back('\f'); break;
+                              case 'u': { unsigned v = 0; for (int i = 0; i < 4 && p + 1 < end; ++i) { ++p; v = v * 16 + (unsigned)(isdigit(*p) ? *p - '0' : (tolower(*p) - 'a' + 10)); }
+                                          o.push_back((char)(v < 128 ? v : '?')); break; }
+                              default: o.push_back(*p); }
+                ++p;
+            } else o.push_back(*p++);
+        }
+        if (p >= end) { ok = false; return o; }
+        ++p; return o;
+    }
+    // skips any value; for numbers / arrays of numbers collects them
+    void value(std::vector<double>* nums, std::string* sval, std::map<std::string, std::string>* obj_strings,
+               std::map<std::string, std::vector<double>>* obj_nums) {
+        ws();
+        if (p >= end) { ok = false; return; }
+        if (*p == '"') { std::string v = str(); if (sval) *sval = v; return; }
+        if (*p == '{') {
+            ++p;
+            if (eat('}')) return;
+            for (;;) {
+                std::string k = str(); if (!ok || !eat(':')) { ok = false; return; }
+                std::vector<double> n; std::string sv;
+                value(&n, &sv, nullptr, nullptr);
+                if (!ok) return;
+                if (obj_strings && !sv.empty()) (*obj_strings)[k] = sv;
+                if (obj_nums && !n.empty()) (*obj_nums)[k] = n;
+                if (eat(',')) continue;
+                if (eat('}')) return;
+                ok = false; return;
+            }
+        }
+        if (*p == '[') {
+            ++p;
+            if (eat(']')) return;
+            for (;;) {
+                value(nums, nullptr, nullptr, nullptr);
+                if (!ok) return;
+                if (eat(',')) continue;
+                if (eat(']')) return;
+                ok = false; return;
+            }
+        }
+        if (!strncmp(p, "true", 4)) { p += 4; if (nums) nums->push_back(1); return; }
+        if (!strncmp(p, "false", 5)) { p += 5; if (nums) nums->push_back(0); return; }
+        if (!strncmp(p, "null", 4)) { p += 4; return; }
+        char* e = nullptr; const double d = strtod(p, &e);
+        if (e == p) { ok = false; return; }
+        p = e; if (nums) nums->push_back(d);
+    }
+};
+}  // namespace
+
+void* voc_create_from_file(const char* path, int device, int wave) {
+    auto bad = [&](const std::string& m) -> void* {
+        g_create_error = std::string(path ? path : "(null)") + ": " + m;
+        fprintf(stderr, "voc_create_from_file: %s\n", g_create_error.c_str());
+        return nullptr;
+    };
+    if (!path) return bad("no path");
+    FILE* f = fopen(path, "rb");
+    if (!f) return bad("cannot open");
+    unsigned long long hl = 0;
+    if (fread(&hl, 8, 1, f) != 1 || hl == 0 || hl > (64ull << 20)) { fclose(f); return bad("not a .b200voc container"); }
+    std::string hdr((size_t)hl, '\0');
+    if (fread(&hdr[0], 1, (size_t)hl, f) != (size_t)hl) { fclose(f); return bad("truncated header"); }
+    // top-level object: "__metadata__" -> strings, every other key -> {"data_offsets": [a, b], ...}
+    JsonCursor c{hdr.data(), hdr.data() + hdr.size()};
+    std::string cfg_json;
+    std::vector<std::pair<std::string, std::pair<long long, long long>>> tensors;
+    if (!c.eat('{')) { fclose(f); return bad("header is not a JSON object"); }
+    if (!c.eat('}')) for (;;) {
+        const std::string key = c.str();
+        if (!c.ok || !c.eat(':')) { c.ok = false; break; }
+        std::map<std::string, std::string> strs; std::map<std::string, std::vector<double>> nums;
+        c.value(nullptr, nullptr, &strs, &nums);
+        if (!c.ok) break;
+        if (key == "__metadata__") cfg_json = strs["voc_config"];
+        else {
+            auto it = nums.find("data_offsets");
+            if (it == nums.end() || it->second.size() != 2) { c.ok = false; break; }
+            if (strs["dtype"] != "F32") { fclose(f); return bad("tensor " + key + " is not F32"); }
+            tensors.push_back({key, {(long long)it->second[0], (long long)it->second[1]}});
+        }
+        if (c.eat(',')) continue;
+        if (c.eat('}')) break;
+        c.ok = false; break;
+    }
+    if (!c.ok) { fclose(f); return bad("malformed header"); }
+    if (cfg_json.empty()) { fclose(f); return bad("no voc_config in metadata"); }
+    void* h = voc_create(cfg_json.c_str(), device, wave);
+    if (!h) { fclose(f); return nullptr; }
+    const long long base = 8 + (long long)hl;
+    std::vector<float> buf;
+    for (auto& t : tensors) {
+        const long long n = (t.second.second - t.second.first) / 4;
+        if (n <= 0) { fclose(f); voc_destroy(h); return bad("empty tensor " + t.first); }
+        buf.resize((size_t)n);
+        if (fseek(f, (long)(base + t.second.first), SEEK_SET) != 0 || fread(buf.data(), 4, (size_t)n, f) != (size_t)n) {
+            fclose(f); voc_destroy(h); return bad("truncated tensor " + t.first);
+        }
+        if (voc_set_tensor(h, t.first.c_str(), buf.data(), n) != VOC_OK) { fclose(f); voc_destroy(h); return bad("voc_set_tensor failed"); }
+    }
+    fclose(f);
+    if (voc_finalize(h) != VOC_OK) {
+        g_create_error = ((Engine*)h)->err;
+        voc_destroy(h);
+        return nullptr;
+    }
+    return h;
+}
+
 int voc_max_tokens(void* h) { return h ? ((Engine*)h)->cfg.chunk_frames : VOC_E_INVALID; }
 long long voc_chunk_samples(void* h) { return h ? ((Engine*)h)->cfg.chunk_samples() : VOC_E_INVALID; }
 long long voc_out_samples(void* h, int n) {
