@@ -126,8 +126,9 @@ long long   voc_kernel_launches(void* h);  /* kernels launched by this handle so
 /* Options: "gemm" = "auto" | "simt" | "tc": kernel family of the dense layers.  "tc" (= "auto")
  *            runs them as tcgen05 tensor-core tiles on split-fp16 operands with FP32 accumulation;
  *            "simt" is the all-float32 CUDA-core path (the on-device cross-check).
- *          "tc_flags" = experiment switches (bit 0 no tap reuse, bit 2 force 32-wide K chunks,
- *            bits 8.. = MMAs accumulated in the tensor core per round-to-nearest flush)
+ *          "tc_flags" = experiment switches (bit 0 no tap reuse, bit 1 / 2 force 64- / 32-wide K
+ *            chunks, bit 7 no cta_group::2 pairs, bits 8.. = MMAs accumulated in the tensor core per
+ *            round-to-nearest flush, default 24)
  *          "profile" = "0" | "1", "debug" = "0" | "1"                                      */
 int         voc_set_option(void* h, const char* key, const char* value);
 /* The handle's own stream (cudaStream_t as void*), so a caller can bracket the host entry

@@ -46,7 +46,6 @@ struct TcArgs {
     int M, N, K, B, ntaps, a_row0;
     int tap_off[VOC_MAX_TAPS];
     int a_reuse, a_min_off, a_box_rows, seg_iters;
-    int split;            // 0: one TMA per stage operand (2-plane box), 1: one per plane, 2: per plane x row half
     int m_tiles, n_tiles, k_chunks, total_tiles;
     int SA, SB;
     float wscale;
@@ -274,8 +273,12 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // share the main accumulator's truncation.  The epilogue adds the two blocks in FP32.
     constexpr bool CAT = !TWO && BN <= 128;
     constexpr uint32_t ACC_COLS = CAT ? 2 * BN : BN;          // TMEM columns of one accumulator buffer
-    constexpr uint32_t TMEM_COLS = (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128
-                                   : (2 * ACC_COLS <= 256) ? 256 : 512;
+    // accumulator buffers in flight: two, or four where 4 x ACC_COLS fit the 512 columns and the layer is
+    // bound by the segment hand-off (the pair-mode C = 96 convs): the MMA warp then runs up to four
+    // segments ahead of the drains
+    constexpr int NBUF = (TWO && ACC_COLS <= 128) ? 4 : 2;
+    constexpr uint32_t TMEM_COLS = (NBUF * ACC_COLS <= 64) ? 64 : (NBUF * ACC_COLS <= 128) ? 128
+                                   : (NBUF * ACC_COLS <= 256) ? 256 : 512;
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = F16, both K-major
     constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((TWO ? 2 * BM : BM) >> 4) << 24);
     constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -283,7 +286,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_a_full[MAX_STAGES], bar_a_empty[MAX_STAGES];
     __shared__ __align__(8) uint64_t bar_b_full[MAX_STAGES], bar_b_empty[MAX_STAGES];
-    __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2];
+    __shared__ __align__(8) uint64_t bar_acc_full[4], bar_acc_empty[4];
     __shared__ uint32_t tmem_slot;
     // per-channel epilogue parameters of the current n-tile: bias, scale, snake a, snake 1/b
     __shared__ __align__(16) float epi_par[4][BN];
@@ -303,7 +306,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tma_prefetch_desc(&tmB);
         for (int i = 0; i < a.SA; ++i) { mbar_init(&bar_a_full[i], 1); mbar_init(&bar_a_empty[i], 1); }
         for (int i = 0; i < a.SB; ++i) { mbar_init(&bar_b_full[i], 1); mbar_init(&bar_b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], TWO ? 2 * EPI_WARPS : EPI_WARPS); }
+        for (int i = 0; i < NBUF; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], TWO ? 2 * EPI_WARPS : EPI_WARPS); }
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -334,16 +337,9 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                     // both CTAs' bytes are credited to the leader's barrier
                                     if (rank == 0) mbar_expect_tx(&bar_a_full[sa], 2 * a_stage);
                                     tma_load_4d_2sm(smA + sa * a_stage, &tmA, mapa_u32(&bar_a_full[sa], 0), kc * BK, arow, b, 0);
-                                } else if (a.split == 0) {
-                                    mbar_expect_tx(&bar_a_full[sa], a_stage);
-                                    tma_load_4d(smA + sa * a_stage, &tmA, &bar_a_full[sa], kc * BK, arow, b, 0);
                                 } else {
                                     mbar_expect_tx(&bar_a_full[sa], a_stage);
-                                    const int nr = a.split == 2 ? 2 : 1, hr = a.a_box_rows / nr;
-                                    for (int pl = 0; pl < 2; ++pl)
-                                        for (int rh = 0; rh < nr; ++rh)
-                                            tma_load_4d(smA + sa * a_stage + pl * a_plane + rh * hr * ROWB, &tmA,
-                                                        &bar_a_full[sa], kc * BK, arow + rh * hr, b, pl);
+                                    tma_load_4d(smA + sa * a_stage, &tmA, &bar_a_full[sa], kc * BK, arow, b, 0);
                                 }
                             }
                             if (++sa == a.SA) { sa = 0; pa ^= 1; }
@@ -353,16 +349,9 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             if constexpr (TWO) {
                                 if (rank == 0) mbar_expect_tx(&bar_b_full[sb], 2 * B_STAGE);
                                 tma_load_4d_2sm(smB + sb * B_STAGE, &tmB, mapa_u32(&bar_b_full[sb], 0), kc * BK, n0, tap, 0);
-                            } else if (a.split == 0) {
-                                mbar_expect_tx(&bar_b_full[sb], B_STAGE);
-                                tma_load_4d(smB + sb * B_STAGE, &tmB, &bar_b_full[sb], kc * BK, n0, tap, 0);
                             } else {
                                 mbar_expect_tx(&bar_b_full[sb], B_STAGE);
-                                const int nr = a.split == 2 ? 2 : 1, hr = BN / nr;
-                                for (int pl = 0; pl < 2; ++pl)
-                                    for (int rh = 0; rh < nr; ++rh)
-                                        tma_load_4d(smB + sb * B_STAGE + pl * B_PLANE + rh * hr * ROWB, &tmB,
-                                                    &bar_b_full[sb], kc * BK, n0 + rh * hr, tap, pl);
+                                tma_load_4d(smB + sb * B_STAGE, &tmB, &bar_b_full[sb], kc * BK, n0, tap, 0);
                             }
                         }
                         if (++sb == a.SB) { sb = 0; pb ^= 1; }
@@ -460,7 +449,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         accum = 1;
                         if (++sb == a.SB) { sb = 0; pb ^= 1; }
                         if (last_of_a) { if (++sa == a.SA) { sa = 0; pa ^= 1; } }
-                        if (last_of_seg) { as ^= 1; if (as == 0) pas ^= 1; }
+                        if (last_of_seg) { if (++as == NBUF) { as = 0; pas ^= 1; } }
                     }
                 }
             }
@@ -474,7 +463,9 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int nseg = (iters_per_tile + a.seg_iters - 1) / a.seg_iters;
         const int etid = threadIdx.x - 64;
         int as = 0, pas = 0, par_tile = -1;
-        const uint32_t acc_empty_leader[2] = {TWO ? mapa_u32(&bar_acc_empty[0], 0) : 0u, TWO ? mapa_u32(&bar_acc_empty[1], 0) : 0u};
+        uint32_t acc_empty_leader[NBUF];
+#pragma unroll
+        for (int i = 0; i < NBUF; ++i) acc_empty_leader[i] = TWO ? mapa_u32(&bar_acc_empty[i], 0) : 0u;
         for (int tile = walker; tile < a.total_tiles; tile += walkers) {
             const int n_tile = tile % a.n_tiles, ml = tile / a.n_tiles;
             const int m_tile = TWO ? 2 * (ml % a.m_tiles) + (int)rank : ml % a.m_tiles, b = ml / a.m_tiles;
@@ -542,7 +533,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     if constexpr (TWO) mbar_arrive_cluster(acc_empty_leader[as]);   // the leader's MMA warp owns the buffer hand-back
                     else mbar_arrive(&bar_acc_empty[as]);
                 }
-                as ^= 1; if (as == 0) pas ^= 1;
+                if (++as == NBUF) { as = 0; pas ^= 1; }
             }
             if (!valid) continue;
             float* Yrow = a.Y ? a.Y + (long long)b * a.y_bstride + (long long)m * a.ldy + n0 : nullptr;
@@ -813,12 +804,10 @@ cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int n
     const long long a_bs = p.B > 1 ? p.a_bstride : (long long)p.a_rows * p.lda;
     const long long a_plane = (long long)(p.A_lo - p.A_hi);
     if (a_plane % 8 || a_plane <= 0) return cudaErrorInvalidValue;
-    a.split = two ? 0 : (flags >> 4) & 3;
-    const int nr = two ? 1 : (a.split == 2 ? 2 : 1), npl = a.split ? 1 : 2;
-    if (!get_map(p.A_hi, p.K, p.a_rows, p.B, (long long)p.lda * 2, a_bs * 2, a_plane * 2, BK, a.a_box_rows / nr, npl, &tmA))
+    if (!get_map(p.A_hi, p.K, p.a_rows, p.B, (long long)p.lda * 2, a_bs * 2, a_plane * 2, BK, a.a_box_rows, 2, &tmA))
         return cudaErrorInvalidValue;
     if (!get_map(p.Wtc, p.K, p.N, p.ntaps, (long long)p.K * 2, (long long)p.N * p.K * 2, p.wtc_plane * 2, BK,
-                 two ? BN / 2 : BN / nr, npl, &tmB))
+                 two ? BN / 2 : BN, 2, &tmB))
         return cudaErrorInvalidValue;
     if (two) {
         const int sms = num_sms > 0 ? num_sms : 148;
@@ -827,8 +816,7 @@ cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int n
                          : launch_inst2<96, 64>(tmA, tmB, a, grid2, smem, st);
     }
 
-    int grid = std::min(a.total_tiles, num_sms > 0 ? num_sms : 148);
-    if (flags & VOC_TC_HALF_GRID) grid = std::max(1, grid / 2);      // experiment: contention vs work
+    const int grid = std::min(a.total_tiles, num_sms > 0 ? num_sms : 148);
     if (BK == 64) return launch_bn<64>(BN, tmA, tmB, a, grid, smem, st);
     return launch_bn<32>(BN, tmA, tmB, a, grid, smem, st);
 }

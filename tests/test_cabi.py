@@ -66,3 +66,41 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f
                 assert "stitch_oracle" not in txt and "vocoder_oracle" not in txt, f
+
+
+def test_create_from_file_fails_loudly(backend, pkg, tmp_path):
+    """voc_create_from_file: a missing / malformed container is an error with a message, and a valid one
+    still needs a GPU (no CPU fallback)."""
+    lib = backend.load_library()
+    assert not lib.voc_create_from_file(str(tmp_path / "nope.b200voc").encode(), 0, 1)
+    assert b"cannot open" in lib.voc_last_error(None)
+    junk = tmp_path / "junk.b200voc"
+    junk.write_bytes(b"\x10\x00\x00\x00\x00\x00\x00\x00{not json at all")
+    assert not lib.voc_create_from_file(str(junk).encode(), 0, 1)
+    import importlib
+    W = importlib.import_module("qwen3-tts-axera-russian_b200.weights")
+    cfg = pkg.VocoderConfig.tiny()
+    good = tmp_path / "tiny.b200voc"
+    W.save_model(str(good), cfg, pkg.init_weights(cfg, 0))
+    import torch
+    if not torch.cuda.is_available():
+        assert not lib.voc_create_from_file(str(good).encode(), 0, 1)
+        assert b"no usable CUDA device" in lib.voc_last_error(None)
+
+
+def test_native_server_is_built_and_needs_a_gpu(tmp_path, pkg):
+    """csrc/voc_server.cpp is compiled by build(); without a B200 it refuses to start (no CPU fallback)."""
+    import importlib, os, subprocess, torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "qwen3-tts-axera-russian_b200", "voc_server")
+    assert os.path.exists(exe), "run build()"
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=30)
+    assert r.returncode == 2 and "--model is required" in r.stderr
+    if not torch.cuda.is_available():
+        W = importlib.import_module("qwen3-tts-axera-russian_b200.weights")
+        cfg = pkg.VocoderConfig.tiny()
+        m = tmp_path / "tiny.b200voc"
+        W.save_model(str(m), cfg, pkg.init_weights(cfg, 0))
+        r = subprocess.run([exe, "--model", str(m), "--socket", str(tmp_path / "s.sock")], capture_output=True, text=True,
+                           timeout=60)
+        assert r.returncode == 1 and "no usable CUDA device" in (r.stderr + r.stdout)
