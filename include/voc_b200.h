@@ -129,6 +129,8 @@ long long   voc_kernel_launches(void* h);  /* kernels launched by this handle so
  *          "tc_flags" = experiment switches (bit 0 no tap reuse, bit 1 / 2 force 64- / 32-wide K
  *            chunks, bit 7 no cta_group::2 pairs, bits 8.. = MMAs accumulated in the tensor core per
  *            round-to-nearest flush, default 24)
+ *          "graphs" = "1" | "0": replay recurring waves of <= 4 windows as CUDA graphs (batch-1
+ *            streaming latency is launch-bound)
  *          "profile" = "0" | "1", "debug" = "0" | "1"                                      */
 int         voc_set_option(void* h, const char* key, const char* value);
 /* The handle's own stream (cudaStream_t as void*), so a caller can bracket the host entry

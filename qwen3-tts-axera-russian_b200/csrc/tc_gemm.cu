@@ -159,8 +159,11 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
     return r;
 }
+// Relaxed: the hand-back of a TMEM buffer orders TMEM reads (tcgen05.wait::ld + tcgen05.fence), not memory.
+// A release at cluster scope compiles to MEMBAR + ERRBAR and waits for the warp's outstanding global stores
+// (ncu: 21 % of the epilogue warps' samples in pair mode).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load whose bytes are credited to a barrier of the pair's leader CTA (cluster address)
 __device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
@@ -257,31 +260,35 @@ __device__ __forceinline__ constexpr uint32_t smem_desc_hi() {
 template <int BN, int BK, bool TWO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ TcArgs a) {
+                  const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ TcArgs a) {
     static_assert(BN % 32 == 0 && BN >= 32 && BN <= 192, "UMMA N; BN/COL_PARTS columns per epilogue thread");
     static_assert((BN / COL_PARTS) % 16 == 0, "the epilogue stores 16 operand columns (one sector) at a time");
     static_assert(BK == 64 || BK == 32, "one swizzle atom per K-chunk");
     constexpr int HN = BN / COL_PARTS;                        // columns per epilogue thread
     constexpr int PB = HN <= 64 ? HN : 16;                    // residual prefetch window (columns)
     constexpr uint32_t ROWB = BK * 2;                         // bytes of one shared-memory row
-    constexpr int BROWS = TWO ? BN / 2 : BN;                  // weight rows staged by this CTA
-    constexpr uint32_t B_PLANE = BROWS * ROWB, B_STAGE = 2 * B_PLANE;
+    // CAT (BN <= 128): see below.  In pair mode the concatenated form stages, per CTA, one whole weight plane
+    // (rank 0: B_hi, rank 1: B_lo -- so that the N = 2*BN MMA, which takes BN rows from each CTA, produces
+    // [A_hi*B_hi | A_hi*B_lo]) followed by this CTA's half of B_hi for the second MMA (N = BN, BN/2 rows each).
+    constexpr bool CAT = BN <= 128;
+    constexpr int BROWS = TWO ? BN / 2 : BN;                  // weight rows per plane staged by this CTA (3-pass form)
+    constexpr uint32_t B_PLANE = (TWO && CAT) ? BN * ROWB : BROWS * ROWB;
+    constexpr uint32_t B_STAGE = (TWO && CAT) ? (BN + BN / 2) * ROWB : 2 * B_PLANE;
     // CAT (BN <= 128): the two weight planes of a stage are contiguous rows, so A_hi x [B_hi; B_lo] is ONE
     // MMA of N = 2*BN whose right half lands in a separate "correction" block of the accumulator buffer;
     // A_lo x B_hi then accumulates into that block.  2 MMAs per k-step instead of 3 (an MMA costs
     // ~64 + N/2 cycles, so fewer and wider is cheaper), and the 2^-11-times-smaller cross terms no longer
     // share the main accumulator's truncation.  The epilogue adds the two blocks in FP32.
-    constexpr bool CAT = !TWO && BN <= 128;
     constexpr uint32_t ACC_COLS = CAT ? 2 * BN : BN;          // TMEM columns of one accumulator buffer
     // accumulator buffers in flight: two, or four where 4 x ACC_COLS fit the 512 columns and the layer is
     // bound by the segment hand-off (the pair-mode C = 96 convs): the MMA warp then runs up to four
     // segments ahead of the drains
-    constexpr int NBUF = (TWO && ACC_COLS <= 128) ? 4 : 2;
+    constexpr int NBUF = (ACC_COLS <= 128) ? 4 : 2;
     constexpr uint32_t TMEM_COLS = (NBUF * ACC_COLS <= 64) ? 64 : (NBUF * ACC_COLS <= 128) ? 128
                                    : (NBUF * ACC_COLS <= 256) ? 256 : 512;
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = F16, both K-major
     constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((TWO ? 2 * BM : BM) >> 4) << 24);
-    constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)((TWO ? 2 * BM : BM) >> 4) << 24);
 
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_a_full[MAX_STAGES], bar_a_empty[MAX_STAGES];
@@ -304,6 +311,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmB2);
         for (int i = 0; i < a.SA; ++i) { mbar_init(&bar_a_full[i], 1); mbar_init(&bar_a_empty[i], 1); }
         for (int i = 0; i < a.SB; ++i) { mbar_init(&bar_b_full[i], 1); mbar_init(&bar_b_empty[i], 1); }
         for (int i = 0; i < NBUF; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], TWO ? 2 * EPI_WARPS : EPI_WARPS); }
@@ -326,7 +334,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int tile = walker; tile < a.total_tiles; tile += walkers) {
                 const int n_tile = tile % a.n_tiles, ml = tile / a.n_tiles;
                 const int m_tile = TWO ? 2 * (ml % a.m_tiles) + (int)rank : ml % a.m_tiles, b = ml / a.m_tiles;
-                const int row0 = m_tile * BM + a.a_row0, n0 = n_tile * BN + (TWO ? (int)rank * BROWS : 0);
+                const int row0 = m_tile * BM + a.a_row0, n0 = n_tile * BN + ((TWO && !CAT) ? (int)rank * BROWS : 0);
                 for (int kc = 0; kc < a.k_chunks; ++kc) {
                     for (int tap = 0; tap < a.ntaps; ++tap) {
                         if (tap == 0 || !a.a_reuse) {
@@ -346,7 +354,12 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         }
                         mbar_wait(&bar_b_empty[sb], pb ^ 1);
                         if (elect_one()) {
-                            if constexpr (TWO) {
+                            if constexpr (TWO && CAT) {
+                                if (rank == 0) mbar_expect_tx(&bar_b_full[sb], 2 * B_STAGE);
+                                const uint32_t lb = mapa_u32(&bar_b_full[sb], 0);
+                                tma_load_4d_2sm(smB + sb * B_STAGE, &tmB, lb, kc * BK, n0, tap, (int)rank);            // a whole plane
+                                tma_load_4d_2sm(smB + sb * B_STAGE + B_PLANE, &tmB2, lb, kc * BK, n0 + (int)rank * (BN / 2), tap, 0);
+                            } else if constexpr (TWO) {
                                 if (rank == 0) mbar_expect_tx(&bar_b_full[sb], 2 * B_STAGE);
                                 tma_load_4d_2sm(smB + sb * B_STAGE, &tmB, mapa_u32(&bar_b_full[sb], 0), kc * BK, n0, tap, 0);
                             } else {
@@ -401,7 +414,19 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             // stage takes a run-time accumulate flag.
                             auto issue = [&](auto full) {
                                 constexpr bool FULL = decltype(full)::value;
-                                if constexpr (CAT) {
+                                if constexpr (CAT && TWO) {
+#pragma unroll
+                                    for (int ks = 0; ks < BK / 16; ++ks) {
+                                        if (FULL || ks < ksteps) {
+                                            // [main | corr] = A_hi x [B_hi (rank 0's rows) ; B_lo (rank 1's rows)];
+                                            // corr += A_lo x B_hi, whose halves sit after the plane in each CTA
+                                            if (ks == 0) mma2_f16_ss(tmem_acc, a_lo, b_lo, smem_desc_hi<BK>(), IDESC2, accum);
+                                            else mma2_f16_ss_acc(tmem_acc, a_lo + ks * 2, b_lo + ks * 2, smem_desc_hi<BK>(), IDESC2);
+                                            mma2_f16_ss_acc(tmem_acc + BN, a_lo + (a_plane >> 4) + ks * 2,
+                                                            b_lo + (B_PLANE >> 4) + ks * 2, smem_desc_hi<BK>(), IDESC);
+                                        }
+                                    }
+                                } else if constexpr (CAT) {
 #pragma unroll
                                     for (int ks = 0; ks < BK / 16; ++ks) {
                                         if (FULL || ks < ksteps) {
@@ -677,14 +702,14 @@ cudaError_t launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const Tc
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    tapgemm_tc_kernel<BN, BK, false><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, a);
+    tapgemm_tc_kernel<BN, BK, false><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmB, a);
     return cudaGetLastError();
 }
 
 // cta_group::2 launch: clusters of two CTAs
 template <int BN, int BK>
-cudaError_t launch_inst2(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, int grid, size_t smem,
-                         cudaStream_t st) {
+cudaError_t launch_inst2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB2, const TcArgs& a,
+                         int grid, size_t smem, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, BK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -699,7 +724,7 @@ cudaError_t launch_inst2(const CUtensorMap& tmA, const CUtensorMap& tmB, const T
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, tapgemm_tc_kernel<BN, BK, true>, tmA, tmB, a);
+    return cudaLaunchKernelEx(&cfg, tapgemm_tc_kernel<BN, BK, true>, tmA, tmB, tmB2, a);
 }
 
 template <int BK>
@@ -789,7 +814,9 @@ cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int n
     a.sn_a = p.sn_a; a.sn_invb = p.sn_invb;
 
     // stage plan
-    const int a_stage = 2 * a.a_box_rows * BK * 2, b_stage = 2 * (two ? BN / 2 : BN) * BK * 2;
+    const bool two_cat = two && BN <= 128;            // pair mode, concatenated form: a plane + a half of B_hi per CTA
+    const int a_stage = 2 * a.a_box_rows * BK * 2;
+    const int b_stage = two_cat ? (BN + BN / 2) * BK * 2 : 2 * (two ? BN / 2 : BN) * BK * 2;
     if (a.a_reuse) {
         a.SA = 2;
         a.SB = std::min(MAX_STAGES, (SMEM_BUDGET - a.SA * a_stage) / b_stage);
@@ -806,14 +833,19 @@ cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int n
     if (a_plane % 8 || a_plane <= 0) return cudaErrorInvalidValue;
     if (!get_map(p.A_hi, p.K, p.a_rows, p.B, (long long)p.lda * 2, a_bs * 2, a_plane * 2, BK, a.a_box_rows, 2, &tmA))
         return cudaErrorInvalidValue;
+    CUtensorMap tmB2;
     if (!get_map(p.Wtc, p.K, p.N, p.ntaps, (long long)p.K * 2, (long long)p.N * p.K * 2, p.wtc_plane * 2, BK,
-                 two ? BN / 2 : BN, 2, &tmB))
+                 two_cat ? BN : (two ? BN / 2 : BN), two_cat ? 1 : 2, &tmB))
+        return cudaErrorInvalidValue;
+    tmB2 = tmB;
+    if (two_cat && !get_map(p.Wtc, p.K, p.N, p.ntaps, (long long)p.K * 2, (long long)p.N * p.K * 2, p.wtc_plane * 2, BK,
+                            BN / 2, 1, &tmB2))
         return cudaErrorInvalidValue;
     if (two) {
         const int sms = num_sms > 0 ? num_sms : 148;
         const int grid2 = 2 * std::min(a.total_tiles, sms / 2);
-        return BN == 192 ? launch_inst2<192, 64>(tmA, tmB, a, grid2, smem, st)
-                         : launch_inst2<96, 64>(tmA, tmB, a, grid2, smem, st);
+        return BN == 192 ? launch_inst2<192, 64>(tmA, tmB, tmB2, a, grid2, smem, st)
+                         : launch_inst2<96, 64>(tmA, tmB, tmB2, a, grid2, smem, st);
     }
 
     const int grid = std::min(a.total_tiles, num_sms > 0 ? num_sms : 148);

@@ -17,6 +17,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <tuple>
 #include <vector>
 
 namespace {
@@ -157,6 +158,10 @@ struct Engine {
     cudaStream_t stream = nullptr;
     std::string err;
     long long launches = 0;
+    // CUDA graphs of small waves (the batch-1 streaming case is launch-bound: ~120 tiny kernels per window)
+    struct WaveGraph { cudaGraphExec_t exec = nullptr; long long launches = 0; int seen = 0; };
+    std::map<std::tuple<const void*, const void*, int, int, int, int, int, int>, WaveGraph> graphs;
+    bool use_graphs = true;
     bool finalized = false;
     int gemm_mode = 0;          // 0 auto (= tc), 1 simt (FP32 CUDA cores), 2 tc (tcgen05, split fp16)
     int tc_flags = 0;           // VOC_TC_* experiment switches
@@ -204,6 +209,7 @@ struct Engine {
     }
 
     ~Engine() {
+        for (auto& g : graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
         for (void* p : owned) cudaFree(p);
         if (d_err) cudaFree(d_err);
         if (d_meta) cudaFree(d_meta);
@@ -715,8 +721,45 @@ static int run_windows(Engine* E, const long long* d_codes, int n_frames, int wi
     const long long Lc = E->cfg.chunk_samples();
     for (int w = w0; w < w1; w += E->wave) {
         const int nw = std::min(E->wave, w1 - w);
-        int r = run_wave(E, d_codes, n_frames, win_step, w, nw, chunk_out + (long long)(w - w0) * Lc, st);
-        if (r) return r;
+        float* out = chunk_out + (long long)(w - w0) * Lc;
+        // Small waves are launch-bound, so a wave that recurs with the same buffers (the streaming client's
+        // one-window requests through the host entry points) is replayed as a CUDA graph: first sight runs
+        // eagerly (lazy set-up: kernel attributes, tensor maps), second sight is captured, later ones replay.
+        const bool graphable = E->use_graphs && nw <= 4 && !E->profile && !E->debug;
+        if (!graphable) {
+            if (int r = run_wave(E, d_codes, n_frames, win_step, w, nw, out, st)) return r;
+            continue;
+        }
+        const auto key = std::make_tuple((const void*)d_codes, (const void*)out, n_frames, win_step, w, nw,
+                                         E->gemm_mode, E->tc_flags);
+        Engine::WaveGraph& G = E->graphs[key];
+        if (G.exec) {
+            CK(cudaGraphLaunch(G.exec, st));
+            E->launches += G.launches;
+            continue;
+        }
+        if (G.seen++ == 0 || E->graphs.size() > 64) {
+            if (int r = run_wave(E, d_codes, n_frames, win_step, w, nw, out, st)) return r;
+            continue;
+        }
+        const long long l0 = E->launches;
+        CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+        const int r = run_wave(E, d_codes, n_frames, win_step, w, nw, out, st);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        if (r) { if (graph) cudaGraphDestroy(graph); return r; }
+        if (ce != cudaSuccess || !graph) {           // not capturable here: stay eager for this key
+            (void)cudaGetLastError();
+            G.seen = -1000000;
+            if (int r2 = run_wave(E, d_codes, n_frames, win_step, w, nw, out, st)) return r2;
+            continue;
+        }
+        G.launches = E->launches - l0;
+        E->launches = l0;
+        CK(cudaGraphInstantiate(&G.exec, graph, 0));
+        cudaGraphDestroy(graph);
+        CK(cudaGraphLaunch(G.exec, st));
+        E->launches += G.launches;
     }
     return VOC_OK;
 }
@@ -1278,6 +1321,7 @@ int voc_set_option(void* h, const char* key, const char* value) {
         return VOC_OK;
     }
     if (k == "tc_flags") { E->tc_flags = atoi(v.c_str()); return VOC_OK; }
+    if (k == "graphs") { E->use_graphs = (v == "1"); return VOC_OK; }
     if (k == "profile") { E->profile = (v == "1"); return VOC_OK; }
     if (k == "debug") { E->debug = (v == "1"); if (!E->debug) E->dbg.clear(); return VOC_OK; }
     return fail(E, VOC_E_INVALID, "unknown option " + k);
