@@ -794,15 +794,16 @@ cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int n
     // cta_group::2 pairs: for the wide layers (column tile 192 or 128, several M tiles per window)
     // Measured (tools/probe_pair.py, 4 windows): conv7 C = 768 / 384 / 192: 0.202 -> 0.152, 0.260 -> 0.209,
     // 0.257 -> 0.225 ms; conv-in 0.131 -> 0.097; but the thin layers (1x1 convs, 2-tap transposed convs with
-    // K <= 384) lose a few per cent to the pair's coupling, hence the taps * K threshold.
+    // K <= 384) lose a few per cent to the pair's coupling, hence the taps * K thresholds (re-measured with the
+    // final epilogue by forcing pairs on every layer: profiles/r1_pair_vs_single.txt).
     // Only for BN = 192, where the single-CTA kernel runs the same three passes: results are then bit-identical
     // whichever mode a batch size selects (the BN <= 128 single-CTA form concatenates two passes).
     // BN = 96 (C = 96, the 7-tap convs): the pair halves the weight bytes each CTA re-streams per tile, which is
     // what bounds that layer (258 KB per 128 rows).  Its single-CTA form is the concatenated one, so the choice
     // must not depend on the batch: M here is the per-window length, the same for any number of windows.
-    const bool two = !(flags & VOC_TC_NO_PAIR) && BK == 64 && p.M > BM &&
-                     ((BN == 192 && (long long)p.ntaps * p.K >= 1024) ||
-                      (BN == 96 && (long long)p.ntaps * p.K >= 512));
+    const bool two = !(flags & VOC_TC_NO_PAIR) && BK == 64 && p.M > BM && (BN == 192 || BN == 96) &&
+                     ((flags & VOC_TC_FORCE_PAIR) || (BN == 192 && (long long)p.ntaps * p.K >= 768) ||
+                      (BN == 96 && (long long)p.ntaps * p.K >= 384));
     a.m_tiles = (p.M + BM - 1) / BM; a.n_tiles = p.N / BN; a.k_chunks = (p.K + BK - 1) / BK;
     if (two) a.m_tiles = (a.m_tiles + 1) / 2;             // M-tile pairs
     a.total_tiles = a.m_tiles * a.n_tiles * p.B;
