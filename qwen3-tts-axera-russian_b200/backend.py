@@ -158,7 +158,7 @@ class Vocoder:
     the caller owns code and output buffers."""
 
     def __init__(self, cfg: Optional[VocoderConfig] = None, weights: Optional[Dict[str, np.ndarray]] = None,
-                 device: int = 0, wave: int = 8, seed: int = 0, lib_path: Optional[str] = None):
+                 device: int = 0, wave: int = 32, seed: int = 0, lib_path: Optional[str] = None):
         self.lib = load_library(lib_path)
         self.cfg = cfg or VocoderConfig()
         self.device = device

@@ -46,7 +46,7 @@ def _recv_exact(conn: socket.socket, n: int) -> bytes:
 
 
 class VocoderServer:
-    def __init__(self, model_path, socket_path="/tmp/qwen3_voc.sock", device=0, wave=8,
+    def __init__(self, model_path, socket_path="/tmp/qwen3_voc.sock", device=0, wave=32,
                  install_signal_handlers=True):
         from .backend import Vocoder
         from .weights import MODEL_SUFFIX
@@ -133,7 +133,7 @@ def main():
     parser.add_argument("--model", required=True, help="Vocoder model (.b200voc)")
     parser.add_argument("--socket", default="/tmp/qwen3_voc.sock")
     parser.add_argument("--device", type=int, default=0)
-    parser.add_argument("--wave", type=int, default=8, help="windows resident in HBM at once")
+    parser.add_argument("--wave", type=int, default=32, help="windows resident in HBM at once")
     args = parser.parse_args()
     server = VocoderServer(model_path=args.model, socket_path=args.socket, device=args.device,
                            wave=args.wave)
