@@ -55,6 +55,8 @@ class SplitF(types.SimpleNamespace):
         xh, xl = _split(x, self.kind)
         wh, wl = _split(w, self.kind)
         y = fn(xh, wh, None, **kw)
+        if self.passes == 2:            # activations split, weights rounded once: (xh + xl) * wh
+            y = y + fn(xl, wh, None, **kw)
         if self.passes >= 3:
             y = y + fn(xh, wl, None, **kw) + fn(xl, wh, None, **kw)
         if self.passes >= 4:
