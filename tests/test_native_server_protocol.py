@@ -125,7 +125,9 @@ def test_reference_client_is_served(server):
         pytest.skip("/root/reference not present on this box")
     codes = _codes(100, 5)
     got = ref(codes)
-    assert np.array_equal(got, fake_pcm(codes, len(got))) and len(got) == 104 * 1920
+    want_len = len(SO.synthesize(codes, lambda p: np.zeros(LC, np.float32), 64))
+    assert len(got) == want_len == 199125          # 122325 + (99840 - 30720) + 7680: the short last window is appended
+    assert np.array_equal(got, fake_pcm(codes, want_len))
 
 
 def test_concurrent_connections_each_get_their_own_audio(server):
