@@ -10,8 +10,8 @@
 //     zero-filled by the TMA unit, so there is no padding pass and no bounds code.
 //   * B: weights, two fp16 planes [plane][tap][N][K] of W * 2^wexp (the power-of-two scale keeps the
 //     lo plane out of the fp16 subnormals; the epilogue multiplies by 2^-wexp, which is exact).
-//   * D += Ahi*Bhi + Ahi*Blo + Alo*Bhi, FP32 accumulation in TMEM (north_star: "accumulation stays
-//     FP32"; measured 91 dB / 2.5e-5 end to end, oracle/precision_study.py).
+//   * D += Ahi*Bhi + Ahi*Blo + Alo*Bhi, FP32 accumulation (north_star: "accumulation stays FP32"; CPU
+//     emulation 91 dB / 2.5e-5 end to end, oracle/precision_study.py; measured on B200 94-96 dB / 2e-5).
 //
 // Tap reuse: for a k-tap causal conv the 128-row A tile *plus its halo of span = (k-1)*dilation
 // rows* is loaded once per K-chunk ("the time-axis halo staged in shared memory", north_star (3));
@@ -20,10 +20,23 @@
 // B200 the swizzle is applied to absolute shared-memory address bits, so the descriptor's base
 // offset stays 0 (tests/test_gpu_tapgemm.py).  Weights are streamed per (tap, K-chunk).
 //
-// One persistent CTA per SM, 10 warps: warp 0 = TMA producer, warp 1 = MMA issuer (one thread),
-// warps 2-9 = epilogue (TMEM -> registers -> bias / GELU / LayerScale / residual / SnakeBeta ->
-// float32 residual stream and split-fp16 operand for the next layer).  Two TMEM buffers let the
-// drain of one accumulation segment overlap the MMAs of the next.
+// One persistent CTA per SM, 10 warps: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane of a
+// warp-uniform loop), warps 2-9 = epilogue (TMEM -> registers -> bias / GELU / LayerScale / residual /
+// SnakeBeta -> float32 residual stream and split-fp16 operand for the next layer, all global accesses one
+// 32-byte sector per lane).
+//
+// Accumulation is segmented: the tensor core's FP32 accumulator truncates, so a TMEM buffer holds at most
+// ~24 MMAs into its main accumulator before the epilogue warps add it, round-to-nearest, into registers;
+// 2 (or 4) TMEM buffers let drains overlap the MMAs of the next segments.
+//
+// Two MMA forms.  3-pass (BN = 192): (hi,lo), (lo,hi), (hi,hi) into one accumulator.  Concatenated
+// (BN <= 128): A_hi x [B_hi; B_lo] as one N = 2*BN MMA plus A_lo x B_hi into a separate correction block.
+// An SS-mode MMA costs ~(128 + N)/2 cycles of operand fetch, so fewer and wider is cheaper.
+//
+// TWO (cta_group::2): a cluster of two CTAs computes two consecutive M tiles with M = 256 MMAs issued by
+// the leader; each CTA stages its own A tile and half of the weight rows (2-SM TMA credited to the leader's
+// barrier, multicast commits, remote relaxed arrives for the TMEM hand-back).  Bit-identical to the
+// single-CTA kernel; selected by layer shape only (never by batch size).
 #include "voc_common.cuh"
 
 #include <cuda.h>
