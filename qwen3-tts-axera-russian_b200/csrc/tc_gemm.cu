@@ -555,21 +555,28 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                     acc[(c0 + c) * 8 + j] += __uint_as_float(tm[c][j]) + __uint_as_float(tc[c][j]);
                             }
                     }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if constexpr (TWO) mbar_arrive_cluster(acc_empty_leader[as]);   // the leader's MMA warp owns the buffer hand-back
+                        else mbar_arrive(&bar_acc_empty[as]);
+                    }
                 } else {
                     uint32_t tr[HN / 8][8];
 #pragma unroll
                     for (int c = 0; c < HN / 8; ++c) tmem_ld8(taddr + c * 8, tr[c]);
                     tmem_ld_wait();
+                    // the buffer is free as soon as its contents are in registers: hand it back before the adds
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if constexpr (TWO) mbar_arrive_cluster(acc_empty_leader[as]);
+                        else mbar_arrive(&bar_acc_empty[as]);
+                    }
 #pragma unroll
                     for (int c = 0; c < HN / 8; ++c)
 #pragma unroll
                         for (int j = 0; j < 8; ++j) acc[c * 8 + j] += __uint_as_float(tr[c][j]);
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                    if constexpr (TWO) mbar_arrive_cluster(acc_empty_leader[as]);   // the leader's MMA warp owns the buffer hand-back
-                    else mbar_arrive(&bar_acc_empty[as]);
                 }
                 if (++as == NBUF) { as = 0; pas ^= 1; }
             }

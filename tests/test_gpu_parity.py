@@ -175,3 +175,21 @@ def test_batched_requests_reject_bad_input(full_model, backend):
     with pytest.raises(backend.VocoderError):
         voc.synthesize_batch_pcm16([_codes(cfg, (5, 16)), bad])
     voc.synthesize_batch_pcm16([_codes(cfg, (5, 16))])
+
+
+@pytest.mark.parametrize("n", [7500, 10000])
+def test_full_size_requests_equal_reference_stitching(full_model, n):
+    """BASELINE's 10-minute utterance (7 500 frames, 157 windows) and the protocol's maximum request
+    (10 000 tokens, vocoder_server.py:149): level 2 and the batched entry point equal level 1 + the
+    reference's Python loop bit for bit, and the length obeys the short-last-window rule
+    (n + n mod 48 frames when 1 <= n mod 48 <= 15)."""
+    cfg, w, voc = full_model
+    codes = _codes(cfg, (n, 16), seed=n)
+    chunk_fn = lambda padded: voc.infer_chunks(padded)[0]
+    ref = SO.to_pcm16(SO.synthesize(codes, chunk_fn, cfg.chunk_frames))
+    got = voc.synthesize_pcm16(codes)
+    assert got.shape == ref.shape
+    assert np.array_equal(got, ref)
+    (batched,) = voc.synthesize_batch_pcm16([codes])
+    assert np.array_equal(batched, ref)
+    assert voc.out_samples(n) == len(ref)
