@@ -23,8 +23,8 @@ def pkg():
 @pytest.fixture(scope="session")
 def backend():
     import __graft_entry__ as g
-    if not os.path.exists(g.LIB):
-        g.build()
+    if not os.path.exists(g.LIB) or not os.path.exists(g.SERVER):
+        g.build(force=True)
     return importlib.import_module("qwen3-tts-axera-russian_b200.backend")
 
 

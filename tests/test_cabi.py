@@ -88,7 +88,7 @@ def test_create_from_file_fails_loudly(backend, pkg, tmp_path):
         assert b"no usable CUDA device" in lib.voc_last_error(None)
 
 
-def test_native_server_is_built_and_needs_a_gpu(tmp_path, pkg):
+def test_native_server_is_built_and_needs_a_gpu(tmp_path, pkg, backend):
     """csrc/voc_server.cpp is compiled by build(); without a B200 it refuses to start (no CPU fallback)."""
     import importlib, os, subprocess, torch
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -82,7 +82,7 @@ def reference_client(sock_path):
 
 
 @pytest.fixture(scope="module")
-def server(tmp_path_factory):
+def server(tmp_path_factory, backend):
     if not os.path.exists(SERVER):
         pytest.fail("voc_server is not built: run build()")
     d = tmp_path_factory.mktemp("native_proto")
