@@ -104,6 +104,42 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
         }
     }
 }
+// The same on raw shared-memory addresses, for the MMA-issuing warp: the tensor pipe has no queue slack
+// (tools/mma_microbench.cu: every cycle the issuing thread spends elsewhere is lost), so its per-stage path
+// must be a handful of instructions -- precomputed addresses, a fast-path try_wait, slow path out of line.
+__device__ __forceinline__ uint32_t opaque_u32(uint32_t x) {
+    uint32_t y;
+    asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+}
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t addr, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __noinline__ void mbar_wait_slow(uint32_t addr, uint32_t parity) {
+    const long long t0 = clock64();
+    while (!mbar_try_wait_a(addr, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("voc_b200 tc_gemm: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity) {
+    if (!mbar_try_wait_a(addr, parity)) mbar_wait_slow(addr, parity);
+}
+__device__ __forceinline__ void mma_commit_a(uint32_t addr) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mma2_commit_both_a(uint32_t addr) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(addr), "h"((uint16_t)3) : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -392,45 +428,51 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // only ever holds a *segment* of seg_iters stages; the epilogue warps add the segments in
         // registers with round-to-nearest.  Within a stage the two small cross terms go first.
         if (!TWO || rank == 0) {
+            // raw barrier addresses (element i at base + 8 i)
+            // (opaque: otherwise the compiler rematerialises each address from SR_CgaCtaId at every use)
+            const uint32_t a_full0 = opaque_u32(smem_u32(&bar_a_full[0])), a_empty0 = opaque_u32(smem_u32(&bar_a_empty[0]));
+            const uint32_t b_full0 = opaque_u32(smem_u32(&bar_b_full[0])), b_empty0 = opaque_u32(smem_u32(&bar_b_empty[0]));
+            const uint32_t acc_full0 = opaque_u32(smem_u32(&bar_acc_full[0])), acc_empty0 = opaque_u32(smem_u32(&bar_acc_empty[0]));
+            const int last_ksteps = (a.K - (a.k_chunks - 1) * BK + 15) >> 4;       // k-steps of the (possibly short) last chunk
+            const int seg_iters = a.seg_iters, ntaps = a.ntaps, k_chunks = a.k_chunks, SA = a.SA, SB = a.SB;
+            const bool reuse = a.a_reuse != 0;
             int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pas = 0, cur_a = 0;
             for (int tile = walker; tile < a.total_tiles; tile += walkers) {
                 uint32_t tmem_acc = 0, accum = 0;
-                int it = 0;
-                for (int kc = 0; kc < a.k_chunks; ++kc) {
-                    for (int tap = 0; tap < a.ntaps; ++tap, ++it) {
-                        if (it % a.seg_iters == 0) {
-                            mbar_wait(&bar_acc_empty[as], pas ^ 1);
-                            tc_fence_after();
+                int seg_left = 0, iters_left = iters_per_tile;
+                for (int kc = 0; kc < k_chunks; ++kc) {
+                    const bool full_chunk = (kc + 1 < k_chunks) || last_ksteps == BK / 16;
+                    for (int tap = 0; tap < ntaps; ++tap) {
+                        if (seg_left == 0) {
+                            mbar_wait_a(acc_empty0 + 8 * as, pas ^ 1);
                             tmem_acc = tmem_base + (uint32_t)as * ACC_COLS;
                             accum = 0;
+                            seg_left = iters_left < seg_iters ? iters_left : seg_iters;
                         }
-                        if (tap == 0 || !a.a_reuse) {
-                            mbar_wait(&bar_a_full[sa], pa);
+                        if (tap == 0 || !reuse) {
+                            mbar_wait_a(a_full0 + 8 * sa, pa);
                             cur_a = sa;
                         }
-                        mbar_wait(&bar_b_full[sb], pb);
+                        mbar_wait_a(b_full0 + 8 * sb, pb);
                         tc_fence_after();
                         // tap reuse: the descriptor simply starts row_off rows into the halo tile.  The
                         // swizzle is a function of the absolute shared-memory address, so no base-offset
                         // correction is applied (the documented (addr >> 7) & 7 value yields garbage).
-                        const uint32_t row_off = a.a_reuse ? (uint32_t)(a.tap_off[tap] - a.a_min_off) : 0u;
+                        const uint32_t row_off = reuse ? (uint32_t)(a.tap_off[tap] - a.a_min_off) : 0u;
                         const uint32_t a_lo = smem_desc_lo(smA + cur_a * a_stage + row_off * ROWB);
                         const uint32_t b_lo = smem_desc_lo(smB + sb * B_STAGE);
-                        // a K tail shorter than the chunk is zero-filled by TMA; its all-zero k-steps are skipped
-                        const int ksteps = min(BK / 16, (a.K - kc * BK + 15) >> 4);
-                        const bool last_of_a = (tap == a.ntaps - 1 || !a.a_reuse);
-                        const bool last_of_seg = ((it + 1) % a.seg_iters == 0 || it + 1 == iters_per_tile);
+                        const bool last_of_a = (tap == ntaps - 1 || !reuse);
+                        --seg_left; --iters_left;
+                        const bool last_of_seg = seg_left == 0;
                         if (elect_one()) {
-                            // The issuing warp is the bottleneck of the main loop when it spends more than a
-                            // few instructions per MMA (ncu: 13 per UTCHMMA held the tensor pipe at 58 %), so
-                            // the full-chunk path is branch-free, fully unrolled, and only the first MMA of a
-                            // stage takes a run-time accumulate flag.
+                            // the full-chunk path is branch-free and fully unrolled; only the first MMA of a
+                            // stage takes a run-time accumulate flag
                             auto issue = [&](auto full) {
                                 constexpr bool FULL = decltype(full)::value;
                                 if constexpr (CAT && TWO) {
 #pragma unroll
                                     for (int ks = 0; ks < BK / 16; ++ks) {
-                                        if (FULL || ks < ksteps) {
+                                        if (FULL || ks < last_ksteps) {
                                             // [main | corr] = A_hi x [B_hi (rank 0's rows) ; B_lo (rank 1's rows)];
                                             // corr += A_lo x B_hi, whose halves sit after the plane in each CTA
                                             if (ks == 0) mma2_f16_ss(tmem_acc, a_lo, b_lo, smem_desc_hi<BK>(), IDESC2, accum);
@@ -442,7 +484,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                 } else if constexpr (CAT) {
 #pragma unroll
                                     for (int ks = 0; ks < BK / 16; ++ks) {
-                                        if (FULL || ks < ksteps) {
+                                        if (FULL || ks < last_ksteps) {
                                             // [main | corr] = A_hi x [B_hi; B_lo];  corr += A_lo x B_hi
                                             if (ks == 0) mma_f16_ss(tmem_acc, a_lo, b_lo, smem_desc_hi<BK>(), IDESC2, accum);
                                             else mma_f16_ss_acc(tmem_acc, a_lo + ks * 2, b_lo + ks * 2, smem_desc_hi<BK>(), IDESC2);
@@ -458,7 +500,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                         const uint32_t bp = b_lo + (pass == 0 ? (B_PLANE >> 4) : 0u);
 #pragma unroll
                                         for (int ks = 0; ks < BK / 16; ++ks) {
-                                            if (FULL || ks < ksteps) {
+                                            if (FULL || ks < last_ksteps) {
                                                 if constexpr (TWO) {
                                                     if (pass == 0 && ks == 0) mma2_f16_ss(tmem_acc, ap, bp, smem_desc_hi<BK>(), IDESC, accum);
                                                     else mma2_f16_ss_acc(tmem_acc, ap + ks * 2, bp + ks * 2, smem_desc_hi<BK>(), IDESC);
@@ -471,22 +513,22 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                     }
                                 }
                             };
-                            if (ksteps == BK / 16) issue(std::true_type{});
+                            if (full_chunk) issue(std::true_type{});
                             else issue(std::false_type{});
                             if constexpr (TWO) {
-                                mma2_commit_both(&bar_b_empty[sb]);
-                                if (last_of_a) mma2_commit_both(&bar_a_empty[cur_a]);
-                                if (last_of_seg) mma2_commit_both(&bar_acc_full[as]);
+                                mma2_commit_both_a(b_empty0 + 8 * sb);
+                                if (last_of_a) mma2_commit_both_a(a_empty0 + 8 * cur_a);
+                                if (last_of_seg) mma2_commit_both_a(acc_full0 + 8 * as);
                             } else {
-                                mma_commit(&bar_b_empty[sb]);
-                                if (last_of_a) mma_commit(&bar_a_empty[cur_a]);
-                                if (last_of_seg) mma_commit(&bar_acc_full[as]);
+                                mma_commit_a(b_empty0 + 8 * sb);
+                                if (last_of_a) mma_commit_a(a_empty0 + 8 * cur_a);
+                                if (last_of_seg) mma_commit_a(acc_full0 + 8 * as);
                             }
                         }
                         __syncwarp();
                         accum = 1;
-                        if (++sb == a.SB) { sb = 0; pb ^= 1; }
-                        if (last_of_a) { if (++sa == a.SA) { sa = 0; pa ^= 1; } }
+                        if (++sb == SB) { sb = 0; pb ^= 1; }
+                        if (last_of_a) { if (++sa == SA) { sa = 0; pa ^= 1; } }
                         if (last_of_seg) { if (++as == NBUF) { as = 0; pas ^= 1; } }
                     }
                 }
