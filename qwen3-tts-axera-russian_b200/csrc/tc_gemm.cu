@@ -59,6 +59,7 @@ struct TcArgs {
     int M, N, K, B, ntaps, a_row0;
     int tap_off[VOC_MAX_TAPS];
     int a_reuse, a_min_off, a_box_rows, seg_iters;
+    int tap_row0, tap_step;                  // a_reuse: tap t starts tap_row0 + t * tap_step rows into the halo tile
     int m_tiles, n_tiles, k_chunks, total_tiles;
     int SA, SB;
     float wscale;
@@ -433,46 +434,61 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint32_t a_full0 = opaque_u32(smem_u32(&bar_a_full[0])), a_empty0 = opaque_u32(smem_u32(&bar_a_empty[0]));
             const uint32_t b_full0 = opaque_u32(smem_u32(&bar_b_full[0])), b_empty0 = opaque_u32(smem_u32(&bar_b_empty[0]));
             const uint32_t acc_full0 = opaque_u32(smem_u32(&bar_acc_full[0])), acc_empty0 = opaque_u32(smem_u32(&bar_acc_empty[0]));
-            const int last_ksteps = (a.K - (a.k_chunks - 1) * BK + 15) >> 4;       // k-steps of the (possibly short) last chunk
-            const int seg_iters = a.seg_iters, ntaps = a.ntaps, k_chunks = a.k_chunks, SA = a.SA, SB = a.SB;
-            const bool reuse = a.a_reuse != 0;
+            // Everything the per-stage path touches lives in registers (opaque: the compiler would otherwise
+            // re-read kernel parameters from the constant bank, a dependent ~30-cycle load each, every stage).
+            // The tensor pipe queues only a few MMAs (tools/mma_issue_bench.cu: ~300-450 cycles of slack), so the
+            // scalar work of a stage has to stay well below the stage's MMA time (300-1150 cycles).
+            // rt0 is zero at run time (a TMEM address has no bits above the lane field's reach here) but not
+            // at compile time: adding it pins a kernel parameter into a register for the whole loop.
+            const uint32_t rt0 = tmem_base >> 24;     // lanes < 128 live in bits 16..22
+            auto reg = [&](uint32_t x) { return opaque_u32(x + rt0); };
+            const int last_ksteps = (int)reg((uint32_t)((a.K - (a.k_chunks - 1) * BK + 15) >> 4));  // of the last chunk
+            const int seg_iters = (int)reg((uint32_t)a.seg_iters), ntaps = (int)reg((uint32_t)a.ntaps);
+            const int k_chunks = (int)reg((uint32_t)a.k_chunks);
+            const int SA = (int)reg((uint32_t)a.SA), SB = (int)reg((uint32_t)a.SB);
+            const bool reuse = reg((uint32_t)a.a_reuse) != 0;
+            const int ipt = (int)reg((uint32_t)iters_per_tile);
+            // descriptor low words advance by these (16-byte units): per A stage, per tap (rows into the halo tile)
+            const uint32_t a_desc0 = reg(smem_desc_lo(smA) + (a.a_reuse ? (uint32_t)a.tap_row0 * (ROWB >> 4) : 0u));
+            const uint32_t a_stage16 = reg(a_stage >> 4);
+            const uint32_t tap_step16 = reg(a.a_reuse ? (uint32_t)(a.tap_step * (int)(ROWB >> 4)) : 0u);
+            const uint32_t b_desc0 = reg(smem_desc_lo(smB));
             int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pas = 0, cur_a = 0;
+            uint32_t b_lo = b_desc0;
             for (int tile = walker; tile < a.total_tiles; tile += walkers) {
-                uint32_t tmem_acc = 0, accum = 0;
-                int seg_left = 0, iters_left = iters_per_tile;
-                for (int kc = 0; kc < k_chunks; ++kc) {
-                    const bool full_chunk = (kc + 1 < k_chunks) || last_ksteps == BK / 16;
-                    for (int tap = 0; tap < ntaps; ++tap) {
+                uint32_t tmem_acc = 0, accum = 0, a_lo = 0;
+                int seg_left = 0, tap = 0, kc_left = k_chunks;
+                for (int iters_left = ipt; iters_left > 0; --iters_left) {
+                    {
                         if (seg_left == 0) {
                             mbar_wait_a(acc_empty0 + 8 * as, pas ^ 1);
                             tmem_acc = tmem_base + (uint32_t)as * ACC_COLS;
                             accum = 0;
                             seg_left = iters_left < seg_iters ? iters_left : seg_iters;
                         }
+                        // tap reuse: the descriptor simply starts some rows into the halo tile.  The swizzle is a
+                        // function of the absolute shared-memory address, so no base-offset correction is applied
+                        // (the documented (addr >> 7) & 7 value yields garbage).
                         if (tap == 0 || !reuse) {
                             mbar_wait_a(a_full0 + 8 * sa, pa);
                             cur_a = sa;
+                            a_lo = a_desc0 + (uint32_t)sa * a_stage16;
                         }
                         mbar_wait_a(b_full0 + 8 * sb, pb);
                         tc_fence_after();
-                        // tap reuse: the descriptor simply starts row_off rows into the halo tile.  The
-                        // swizzle is a function of the absolute shared-memory address, so no base-offset
-                        // correction is applied (the documented (addr >> 7) & 7 value yields garbage).
-                        const uint32_t row_off = reuse ? (uint32_t)(a.tap_off[tap] - a.a_min_off) : 0u;
-                        const uint32_t a_lo = smem_desc_lo(smA + cur_a * a_stage + row_off * ROWB);
-                        const uint32_t b_lo = smem_desc_lo(smB + sb * B_STAGE);
+                        const bool full_chunk = kc_left > 1 || last_ksteps == BK / 16;
                         const bool last_of_a = (tap == ntaps - 1 || !reuse);
-                        --seg_left; --iters_left;
+                        --seg_left;
                         const bool last_of_seg = seg_left == 0;
                         if (elect_one()) {
-                            // the full-chunk path is branch-free and fully unrolled; only the first MMA of a
-                            // stage takes a run-time accumulate flag
-                            auto issue = [&](auto full) {
-                                constexpr bool FULL = decltype(full)::value;
+                            // every path is branch-free and fully unrolled (a short last chunk picks one of the
+                            // compile-time variants); only the first MMA of a stage takes a run-time accumulate flag
+                            auto issue = [&](auto nks) {
+                                constexpr int NKS = decltype(nks)::value;        // k-steps in this stage, compile time
                                 if constexpr (CAT && TWO) {
 #pragma unroll
-                                    for (int ks = 0; ks < BK / 16; ++ks) {
-                                        if (FULL || ks < last_ksteps) {
+                                    for (int ks = 0; ks < NKS; ++ks) {
+                                        {
                                             // [main | corr] = A_hi x [B_hi (rank 0's rows) ; B_lo (rank 1's rows)];
                                             // corr += A_lo x B_hi, whose halves sit after the plane in each CTA
                                             if (ks == 0) mma2_f16_ss(tmem_acc, a_lo, b_lo, smem_desc_hi<BK>(), IDESC2, accum);
@@ -483,8 +499,8 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                     }
                                 } else if constexpr (CAT) {
 #pragma unroll
-                                    for (int ks = 0; ks < BK / 16; ++ks) {
-                                        if (FULL || ks < last_ksteps) {
+                                    for (int ks = 0; ks < NKS; ++ks) {
+                                        {
                                             // [main | corr] = A_hi x [B_hi; B_lo];  corr += A_lo x B_hi
                                             if (ks == 0) mma_f16_ss(tmem_acc, a_lo, b_lo, smem_desc_hi<BK>(), IDESC2, accum);
                                             else mma_f16_ss_acc(tmem_acc, a_lo + ks * 2, b_lo + ks * 2, smem_desc_hi<BK>(), IDESC2);
@@ -499,8 +515,8 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                         const uint32_t ap = a_lo + (pass == 1 ? (a_plane >> 4) : 0u);
                                         const uint32_t bp = b_lo + (pass == 0 ? (B_PLANE >> 4) : 0u);
 #pragma unroll
-                                        for (int ks = 0; ks < BK / 16; ++ks) {
-                                            if (FULL || ks < last_ksteps) {
+                                        for (int ks = 0; ks < NKS; ++ks) {
+                                            {
                                                 if constexpr (TWO) {
                                                     if (pass == 0 && ks == 0) mma2_f16_ss(tmem_acc, ap, bp, smem_desc_hi<BK>(), IDESC, accum);
                                                     else mma2_f16_ss_acc(tmem_acc, ap + ks * 2, bp + ks * 2, smem_desc_hi<BK>(), IDESC);
@@ -513,8 +529,10 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                     }
                                 }
                             };
-                            if (full_chunk) issue(std::true_type{});
-                            else issue(std::false_type{});
+                            if (full_chunk) issue(std::integral_constant<int, BK / 16>{});
+                            else if (BK == 64 && last_ksteps == 2) issue(std::integral_constant<int, 2>{});
+                            else if (BK == 64 && last_ksteps == 3) issue(std::integral_constant<int, 3>{});
+                            else issue(std::integral_constant<int, 1>{});
                             if constexpr (TWO) {
                                 mma2_commit_both_a(b_empty0 + 8 * sb);
                                 if (last_of_a) mma2_commit_both_a(a_empty0 + 8 * cur_a);
@@ -527,7 +545,10 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         }
                         __syncwarp();
                         accum = 1;
-                        if (++sb == SB) { sb = 0; pb ^= 1; }
+                        a_lo += tap_step16;
+                        b_lo += B_STAGE >> 4;
+                        if (++sb == SB) { sb = 0; pb ^= 1; b_lo = b_desc0; }
+                        if (++tap == ntaps) { tap = 0; --kc_left; }
                         if (last_of_a) { if (++sa == SA) { sa = 0; pa ^= 1; } }
                         if (last_of_seg) { if (++as == NBUF) { as = 0; pas ^= 1; } }
                     }
@@ -843,7 +864,13 @@ cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int n
     int mn = p.tap_off[0], mx = p.tap_off[0];
     for (int i = 0; i < p.ntaps; ++i) { a.tap_off[i] = p.tap_off[i]; mn = std::min(mn, p.tap_off[i]); mx = std::max(mx, p.tap_off[i]); }
     a.a_reuse = (p.ntaps > 1 && !(flags & VOC_TC_NO_REUSE)) ? 1 : 0;
+    // the issuing warp steps its A descriptor from tap to tap, so tap reuse wants equally spaced taps
+    // (every convolution and transposed convolution of the decoder); anything else reloads A per tap
+    for (int i = 2; i < p.ntaps; ++i)
+        if (p.tap_off[i] - p.tap_off[i - 1] != p.tap_off[1] - p.tap_off[0]) a.a_reuse = 0;
     a.a_min_off = mn;
+    a.tap_row0 = p.tap_off[0] - mn;
+    a.tap_step = p.ntaps > 1 ? p.tap_off[1] - p.tap_off[0] : 0;
     a.a_box_rows = a.a_reuse ? ((BM + (mx - mn) + 15) / 16) * 16 : BM;
     // MMAs accumulated in the tensor core before a round-to-nearest flush (bits 8.. of flags).  Measured
     // on the full 64-frame window: 12 -> 98.8 dB / 1.2e-5, 24 -> 94.6 dB / 2.0e-5, 48 -> 88.6 dB / 3.9e-5,

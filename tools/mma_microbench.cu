@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int iters, int alt, int s
                                                   int gap_cycles = 0) {
     extern __shared__ uint8_t raw[];
     __shared__ __align__(8) uint64_t bar, bar2, bar3;
-    __shared__ uint32_t slot;
+    __shared__ uint32_t slot, flag;
     const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
     const uint32_t smA = base, smB = base + 2 * 192 * 128;            // A: 2 planes x 192 rows x 128 B; B: 256 rows x 128 B x 2
     uint32_t rank = 0;
@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int iters, int alt, int s
     for (uint32_t i = threadIdx.x * 4; i < 2 * 192 * 128 + 2 * 256 * 128; i += blockDim.x * 4)
         *reinterpret_cast<uint32_t*>(raw + (base - smem_u32(raw)) + i) = 0x3c003c00u;     // fp16 1.0 pairs
     if (threadIdx.x == 0) {
+        flag = 1;
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2)) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1000000;" ::"r"(smem_u32(&bar3)) : "memory");
@@ -84,6 +85,27 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int iters, int alt, int s
                         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 1;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                                      : "=r"(okk) : "r"(smem_u32(&bar2)) : "memory");
                         lcg += okk;
+                    }
+                    if (kind & 8) {                                  // non-blocking test_wait instead of try_wait
+                        uint32_t okk;
+                        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], 1;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                                     : "=r"(okk) : "r"(smem_u32(&bar2)) : "memory");
+                        lcg += okk;
+                    }
+                    if (kind & 16) {                                 // a plain volatile shared-memory load (a relayed flag)
+                        uint32_t v;
+                        asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(&flag)) : "memory");
+                        lcg += v;
+                    }
+                    if (kind & 32) {                                 // try_wait whose result gates the next group (consumed)
+                        uint32_t okk = 0;
+                        while (!okk)
+                            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 1;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                                         : "=r"(okk) : "r"(smem_u32(&bar2)) : "memory");
+                    }
+                    if (kind & 64) {                                 // a volatile load whose result gates the next group
+                        uint32_t v = 0;
+                        while (!v) asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(&flag)) : "memory");
                     }
                     if (kind & 4) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     if (kind & 2) {
@@ -181,7 +203,7 @@ int main() {
     {
         double is;
         const double base1 = run<false>(192, iters, 0, 0, 148, d_out, &is, 3, 0), base2 = run<true>(192, iters, 0, 0, 148, d_out, &is, 3, 0);
-        for (int kind : {1, 2, 3, 4, 7}) {
+        for (int kind : {1, 2, 3, 4, 7, 8, 16, 32, 64, 66, 34}) {
             const double a = run<false>(192, iters, 0, 0, 148, d_out, &is, 3, -kind);
             const double b = run<true>(192, iters, 0, 0, 148, d_out, &is, 3, -kind);
             printf("kind %d: single +%6.1f  pair +%6.1f cycles per group of 12 MMAs\n", kind, (a - base1) * 12, (b - base2) * 12);
