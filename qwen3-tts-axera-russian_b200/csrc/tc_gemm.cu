@@ -134,6 +134,18 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t addr, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity) {
     if (!mbar_try_wait_a(addr, parity)) mbar_wait_slow(addr, parity);
 }
+// lean spin for the MMA-issuing thread: three instructions, no watchdog (a stuck pipeline still trips the
+// watchdog of the producer and epilogue warps, which wait on the same hand-offs)
+__device__ __forceinline__ void mbar_spin_a(uint32_t addr, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "SPIN_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra SPIN_DONE;\n\t"
+        "bra SPIN_WAIT;\n\t"
+        "SPIN_DONE:\n\t}"
+        :: "r"(addr), "r"(parity) : "memory");
+}
 __device__ __forceinline__ void mma_commit_a(uint32_t addr) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(addr) : "memory");
 }
@@ -428,6 +440,8 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // accumulation, i.e. -23 dB end to end over chains of up to 1008 MMAs), so a TMEM buffer
         // only ever holds a *segment* of seg_iters stages; the epilogue warps add the segments in
         // registers with round-to-nearest.  Within a stage the two small cross terms go first.
+        // The loop is warp-uniform with one elected lane issuing: inside a divergent region the compiler cannot
+        // prove the descriptors uniform and wraps every UTCHMMA in an ELECT / R2UR.BROADCAST waterfall.
         if (!TWO || rank == 0) {
             // raw barrier addresses (element i at base + 8 i)
             // (opaque: otherwise the compiler rematerialises each address from SR_CgaCtaId at every use)
@@ -443,42 +457,41 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint32_t rt0 = tmem_base >> 24;     // lanes < 128 live in bits 16..22
             auto reg = [&](uint32_t x) { return opaque_u32(x + rt0); };
             const int last_ksteps = (int)reg((uint32_t)((a.K - (a.k_chunks - 1) * BK + 15) >> 4));  // of the last chunk
-            const int seg_iters = (int)reg((uint32_t)a.seg_iters), ntaps = (int)reg((uint32_t)a.ntaps);
-            const int k_chunks = (int)reg((uint32_t)a.k_chunks);
+            const int seg_iters = (int)reg((uint32_t)a.seg_iters);
             const int SA = (int)reg((uint32_t)a.SA), SB = (int)reg((uint32_t)a.SB);
-            const bool reuse = reg((uint32_t)a.a_reuse) != 0;
             const int ipt = (int)reg((uint32_t)iters_per_tile);
+            // One "fill" of an A stage serves n_inner consecutive stages: all taps of a K chunk with tap reuse,
+            // one stage otherwise; fills from first_short on belong to the (possibly short) last K chunk.
+            const int n_fills = (int)reg((uint32_t)(a.a_reuse ? a.k_chunks : a.k_chunks * a.ntaps));
+            const int n_inner = (int)reg((uint32_t)(a.a_reuse ? a.ntaps : 1));
+            const int first_short = (int)reg((uint32_t)(a.a_reuse ? a.k_chunks - 1 : (a.k_chunks - 1) * a.ntaps));
             // descriptor low words advance by these (16-byte units): per A stage, per tap (rows into the halo tile)
             const uint32_t a_desc0 = reg(smem_desc_lo(smA) + (a.a_reuse ? (uint32_t)a.tap_row0 * (ROWB >> 4) : 0u));
             const uint32_t a_stage16 = reg(a_stage >> 4);
             const uint32_t tap_step16 = reg(a.a_reuse ? (uint32_t)(a.tap_step * (int)(ROWB >> 4)) : 0u);
             const uint32_t b_desc0 = reg(smem_desc_lo(smB));
-            int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pas = 0, cur_a = 0;
+            int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pas = 0;
             uint32_t b_lo = b_desc0;
             for (int tile = walker; tile < a.total_tiles; tile += walkers) {
-                uint32_t tmem_acc = 0, accum = 0, a_lo = 0;
-                int seg_left = 0, tap = 0, kc_left = k_chunks;
-                for (int iters_left = ipt; iters_left > 0; --iters_left) {
-                    {
+                uint32_t tmem_acc = 0, accum = 0;
+                int seg_left = 0, iters_left = ipt;
+                for (int fill = 0; fill < n_fills; ++fill) {
+                    // tap reuse: the descriptor simply starts some rows into the halo tile and steps from tap to
+                    // tap.  The swizzle is a function of the absolute shared-memory address, so no base-offset
+                    // correction is applied (the documented (addr >> 7) & 7 value yields garbage).
+                    mbar_spin_a(a_full0 + 8 * sa, pa);
+                    uint32_t a_lo = a_desc0 + (uint32_t)sa * a_stage16;
+                    const bool full_chunk = fill < first_short || last_ksteps == BK / 16;
+                    for (int t = 0; t < n_inner; ++t) {
                         if (seg_left == 0) {
-                            mbar_wait_a(acc_empty0 + 8 * as, pas ^ 1);
+                            mbar_spin_a(acc_empty0 + 8 * as, pas ^ 1);
                             tmem_acc = tmem_base + (uint32_t)as * ACC_COLS;
                             accum = 0;
                             seg_left = iters_left < seg_iters ? iters_left : seg_iters;
                         }
-                        // tap reuse: the descriptor simply starts some rows into the halo tile.  The swizzle is a
-                        // function of the absolute shared-memory address, so no base-offset correction is applied
-                        // (the documented (addr >> 7) & 7 value yields garbage).
-                        if (tap == 0 || !reuse) {
-                            mbar_wait_a(a_full0 + 8 * sa, pa);
-                            cur_a = sa;
-                            a_lo = a_desc0 + (uint32_t)sa * a_stage16;
-                        }
-                        mbar_wait_a(b_full0 + 8 * sb, pb);
+                        mbar_spin_a(b_full0 + 8 * sb, pb);
                         tc_fence_after();
-                        const bool full_chunk = kc_left > 1 || last_ksteps == BK / 16;
-                        const bool last_of_a = (tap == ntaps - 1 || !reuse);
-                        --seg_left;
+                        --seg_left; --iters_left;
                         const bool last_of_seg = seg_left == 0;
                         if (elect_one()) {
                             // every path is branch-free and fully unrolled (a short last chunk picks one of the
@@ -535,11 +548,9 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             else issue(std::integral_constant<int, 1>{});
                             if constexpr (TWO) {
                                 mma2_commit_both_a(b_empty0 + 8 * sb);
-                                if (last_of_a) mma2_commit_both_a(a_empty0 + 8 * cur_a);
                                 if (last_of_seg) mma2_commit_both_a(acc_full0 + 8 * as);
                             } else {
                                 mma_commit_a(b_empty0 + 8 * sb);
-                                if (last_of_a) mma_commit_a(a_empty0 + 8 * cur_a);
                                 if (last_of_seg) mma_commit_a(acc_full0 + 8 * as);
                             }
                         }
@@ -548,10 +559,15 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         a_lo += tap_step16;
                         b_lo += B_STAGE >> 4;
                         if (++sb == SB) { sb = 0; pb ^= 1; b_lo = b_desc0; }
-                        if (++tap == ntaps) { tap = 0; --kc_left; }
-                        if (last_of_a) { if (++sa == SA) { sa = 0; pa ^= 1; } }
                         if (last_of_seg) { if (++as == NBUF) { as = 0; pas ^= 1; } }
                     }
+                    // the A stage is free once everything issued so far has read it
+                    if (elect_one()) {
+                        if constexpr (TWO) mma2_commit_both_a(a_empty0 + 8 * sa);
+                        else mma_commit_a(a_empty0 + 8 * sa);
+                    }
+                    __syncwarp();
+                    if (++sa == SA) { sa = 0; pa ^= 1; }
                 }
             }
         }
