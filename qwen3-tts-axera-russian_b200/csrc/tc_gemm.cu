@@ -31,7 +31,8 @@
 //
 // Two MMA forms.  3-pass (BN = 192): (hi,lo), (lo,hi), (hi,hi) into one accumulator.  Concatenated
 // (BN <= 128): A_hi x [B_hi; B_lo] as one N = 2*BN MMA plus A_lo x B_hi into a separate correction block.
-// An SS-mode MMA costs ~(128 + N)/2 cycles of operand fetch, so fewer and wider is cheaper.
+// One MMA costs max(~44 + N/8, N/2) cycles (tools/mma_issue_bench.cu): N = 192 runs at the math floor, and the
+// concatenated form trades three N = 96 MMAs (56 cycles each) for one of N = 192 and one of N = 96.
 //
 // TWO (cta_group::2): a cluster of two CTAs computes two consecutive M tiles with M = 256 MMAs issued by
 // the leader; each CTA stages its own A tile and half of the weight rows (2-SM TMA credited to the leader's
@@ -71,6 +72,25 @@ struct TcArgs {
 };
 
 // ---------------------------------------------------------------------------------------------
+// Bring-up profiling (compiled in only with -DVOC_TC_PROF, see tools/ab_build.sh): where each role of the
+// kernel spends its cycles.  Counters are summed over CTAs; voc_tc_prof_read() fetches and clears them.
+// ---------------------------------------------------------------------------------------------
+#ifdef VOC_TC_PROF
+enum { PF_MMA_TOTAL, PF_MMA_W_ACC, PF_MMA_W_A, PF_MMA_W_B, PF_EPI_TOTAL, PF_EPI_W_ACC, PF_EPI_DRAIN, PF_EPI_FINAL,
+       PF_PROD_TOTAL, PF_PROD_W_A, PF_PROD_W_B, PF_CTAS, PF_TILES, PF_SEGS, PF_N };
+__device__ unsigned long long g_tc_prof[PF_N];
+#define PF_DECL(name) long long name = 0
+#define PF_T0(t) const long long t = clock64()
+#define PF_ACC(name, t) name += clock64() - (t)
+#define PF_FLUSH(idx, name) atomicAdd(&g_tc_prof[idx], (unsigned long long)(name))
+#else
+#define PF_DECL(name)
+#define PF_T0(t)
+#define PF_ACC(name, t)
+#define PF_FLUSH(idx, name)
+#endif
+
+// ---------------------------------------------------------------------------------------------
 // PTX wrappers
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -98,44 +118,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* b, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
     if (mbar_try_wait(b, parity)) return;
     const long long t0 = clock64();
+    // watchdog: a broken pipeline becomes a launch failure, not a hung GPU.  No printf here: a call in this
+    // loop makes the compiler spill whatever is live across the wait -- in the epilogue that was the residual
+    // prefetch, whose spill store then waited out the full DRAM latency of every load (54 % of all stall samples).
     while (!mbar_try_wait(b, parity)) {
-        if (clock64() - t0 > 4000000000LL) {
-            printf("voc_b200 tc_gemm: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-            __trap();
-        }
+        if (clock64() - t0 > 4000000000LL) __trap();
     }
 }
-// The same on raw shared-memory addresses, for the MMA-issuing warp: the tensor pipe has no queue slack
-// (tools/mma_microbench.cu: every cycle the issuing thread spends elsewhere is lost), so its per-stage path
-// must be a handful of instructions -- precomputed addresses, a fast-path try_wait, slow path out of line.
 __device__ __forceinline__ uint32_t opaque_u32(uint32_t x) {
     uint32_t y;
     asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x));
     return y;
 }
-__device__ __forceinline__ bool mbar_try_wait_a(uint32_t addr, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __noinline__ void mbar_wait_slow(uint32_t addr, uint32_t parity) {
-    const long long t0 = clock64();
-    while (!mbar_try_wait_a(addr, parity)) {
-        if (clock64() - t0 > 4000000000LL) {
-            printf("voc_b200 tc_gemm: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-            __trap();
-        }
-    }
-}
-__device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity) {
-    if (!mbar_try_wait_a(addr, parity)) mbar_wait_slow(addr, parity);
-}
-// lean spin for the MMA-issuing thread: three instructions, no watchdog (a stuck pipeline still trips the
-// watchdog of the producer and epilogue warps, which wait on the same hand-offs)
+// Waits of the MMA-issuing warp, on raw shared-memory addresses: a lean spin of three instructions, no watchdog
+// (a stuck pipeline still trips the watchdog of the producer and epilogue warps, which wait on the same
+// hand-offs).  The issuing thread's scalar work per stage must stay below the stage's MMA time.
 __device__ __forceinline__ void mbar_spin_a(uint32_t addr, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -318,8 +315,16 @@ __device__ __forceinline__ constexpr uint32_t smem_desc_hi() {
 // ---------------------------------------------------------------------------------------------
 // TWO: cta_group::2.  A cluster of two CTAs computes two consecutive 128-row M tiles of the same column
 // tile with M = 256 MMAs issued by the leader (rank 0): each CTA stages its own A tile and HALF of the
-// weight rows, so the per-MMA shared-memory operand fetch drops from (128 + N)/2 to (128 + N/2)/2 cycles.
-template <int BN, int BK, bool TWO>
+// weight rows: one issuing warp feeds two SMs' tensor pipes and each CTA streams half the weight bytes.
+// EPI fixes the epilogue's shape at compile time for the three hot layer kinds (their run-time tests and the
+// untaken variants' code -- erff for GELU alone is ~200 instructions per 8 columns -- otherwise sit in every
+// 16-column group of a 5000-instruction straight-line epilogue that already stalls on instruction fetch):
+enum { EPI_GENERIC = 0,      // everything decided at run time from TcArgs
+       EPI_SNAKE_S = 1,      // bias, Snake -> split operand S                     (7-tap convs of a residual unit)
+       EPI_RES_Y_S = 2,      // bias, + residual -> Y; Snake -> split operand S    (1x1 convs of a residual unit)
+       EPI_Y_S = 3 };        // bias -> Y; Snake -> split operand S                (transposed convs)
+
+template <int BN, int BK, bool TWO, int EPI = EPI_GENERIC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ TcArgs a) {
@@ -392,6 +397,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // (the whole warp runs the loop so that addresses and phases stay in uniform registers; one
         // elected lane issues)
         {
+            PF_DECL(pf_w_a); PF_DECL(pf_w_b); PF_T0(pf_t0);
             int sa = 0, pa = 0, sb = 0, pb = 0;
             for (int tile = walker; tile < a.total_tiles; tile += walkers) {
                 const int n_tile = tile % a.n_tiles, ml = tile / a.n_tiles;
@@ -400,7 +406,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 for (int kc = 0; kc < a.k_chunks; ++kc) {
                     for (int tap = 0; tap < a.ntaps; ++tap) {
                         if (tap == 0 || !a.a_reuse) {
-                            mbar_wait(&bar_a_empty[sa], pa ^ 1);
+                            { PF_T0(tw); mbar_wait(&bar_a_empty[sa], pa ^ 1); PF_ACC(pf_w_a, tw); }
                             if (elect_one()) {
                                 const int arow = row0 + (a.a_reuse ? a.a_min_off : a.tap_off[tap]);
                                 if constexpr (TWO) {
@@ -414,7 +420,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             }
                             if (++sa == a.SA) { sa = 0; pa ^= 1; }
                         }
-                        mbar_wait(&bar_b_empty[sb], pb ^ 1);
+                        { PF_T0(tw); mbar_wait(&bar_b_empty[sb], pb ^ 1); PF_ACC(pf_w_b, tw); }
                         if (elect_one()) {
                             if constexpr (TWO && CAT) {
                                 if (rank == 0) mbar_expect_tx(&bar_b_full[sb], 2 * B_STAGE);
@@ -433,6 +439,9 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     }
                 }
             }
+#ifdef VOC_TC_PROF
+            if (lane == 0) { PF_FLUSH(PF_PROD_TOTAL, clock64() - pf_t0); PF_FLUSH(PF_PROD_W_A, pf_w_a); PF_FLUSH(PF_PROD_W_B, pf_w_b); }
+#endif
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
@@ -472,6 +481,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint32_t b_desc0 = reg(smem_desc_lo(smB));
             int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pas = 0;
             uint32_t b_lo = b_desc0;
+            PF_DECL(pf_w_acc); PF_DECL(pf_w_a); PF_DECL(pf_w_b); PF_DECL(pf_tiles); PF_T0(pf_t0);
             for (int tile = walker; tile < a.total_tiles; tile += walkers) {
                 uint32_t tmem_acc = 0, accum = 0;
                 int seg_left = 0, iters_left = ipt;
@@ -479,17 +489,17 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     // tap reuse: the descriptor simply starts some rows into the halo tile and steps from tap to
                     // tap.  The swizzle is a function of the absolute shared-memory address, so no base-offset
                     // correction is applied (the documented (addr >> 7) & 7 value yields garbage).
-                    mbar_spin_a(a_full0 + 8 * sa, pa);
+                    { PF_T0(tw); mbar_spin_a(a_full0 + 8 * sa, pa); PF_ACC(pf_w_a, tw); }
                     uint32_t a_lo = a_desc0 + (uint32_t)sa * a_stage16;
                     const bool full_chunk = fill < first_short || last_ksteps == BK / 16;
                     for (int t = 0; t < n_inner; ++t) {
                         if (seg_left == 0) {
-                            mbar_spin_a(acc_empty0 + 8 * as, pas ^ 1);
+                            { PF_T0(tw); mbar_spin_a(acc_empty0 + 8 * as, pas ^ 1); PF_ACC(pf_w_acc, tw); }
                             tmem_acc = tmem_base + (uint32_t)as * ACC_COLS;
                             accum = 0;
                             seg_left = iters_left < seg_iters ? iters_left : seg_iters;
                         }
-                        mbar_spin_a(b_full0 + 8 * sb, pb);
+                        { PF_T0(tw); mbar_spin_a(b_full0 + 8 * sb, pb); PF_ACC(pf_w_b, tw); }
                         tc_fence_after();
                         --seg_left; --iters_left;
                         const bool last_of_seg = seg_left == 0;
@@ -569,7 +579,16 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     __syncwarp();
                     if (++sa == SA) { sa = 0; pa ^= 1; }
                 }
+#ifdef VOC_TC_PROF
+                ++pf_tiles;
+#endif
             }
+#ifdef VOC_TC_PROF
+            if (lane == 0) {
+                PF_FLUSH(PF_MMA_TOTAL, clock64() - pf_t0); PF_FLUSH(PF_MMA_W_ACC, pf_w_acc); PF_FLUSH(PF_MMA_W_A, pf_w_a);
+                PF_FLUSH(PF_MMA_W_B, pf_w_b); PF_FLUSH(PF_CTAS, 1); PF_FLUSH(PF_TILES, pf_tiles);
+            }
+#endif
         }
     } else {
         // ================================ epilogue ====================================
@@ -579,7 +598,15 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int h = (warp - 2) >> 2;                // which part of the tile's columns
         const int nseg = (iters_per_tile + a.seg_iters - 1) / a.seg_iters;
         const int etid = threadIdx.x - 64;
+        const bool has_bias = EPI != EPI_GENERIC || a.bias != nullptr;
+        const bool has_gelu = EPI == EPI_GENERIC && a.act == VOC_ACT_GELU;
+        const bool has_scale = EPI == EPI_GENERIC && a.scale != nullptr;
+        const bool has_r = EPI == EPI_RES_Y_S || (EPI == EPI_GENERIC && a.R != nullptr);
+        const bool has_y = EPI == EPI_RES_Y_S || EPI == EPI_Y_S || (EPI == EPI_GENERIC && a.Y != nullptr);
+        const bool has_s = EPI != EPI_GENERIC || a.S_hi != nullptr;
+        const bool has_snake = EPI != EPI_GENERIC || a.sn_a != nullptr;
         int as = 0, pas = 0, par_tile = -1;
+        PF_DECL(pf_w_acc); PF_DECL(pf_drain); PF_DECL(pf_final); PF_DECL(pf_segs); PF_T0(pf_t0);
         uint32_t acc_empty_leader[NBUF];
 #pragma unroll
         for (int i = 0; i < NBUF; ++i) acc_empty_leader[i] = TWO ? mapa_u32(&bar_acc_empty[i], 0) : 0u;
@@ -604,7 +631,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             // The residual is independent of the MMAs: its loads are issued before the accumulator
             // wait (whole row when it fits the register budget, else a rolling 16-column window).
-            const float* Rrow = (a.R && valid) ? a.R + (long long)b * a.r_bstride + (long long)m * a.ldr + n0 : nullptr;
+            const float* Rrow = (has_r && valid) ? a.R + (long long)b * a.r_bstride + (long long)m * a.ldr + n0 : nullptr;
             float rpf[2][PB / 8][8];
             if (Rrow) {
 #pragma unroll
@@ -614,7 +641,8 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int j = 0; j < HN; ++j) acc[j] = 0.f;
             for (int seg = 0; seg < nseg; ++seg) {
-                mbar_wait(&bar_acc_full[as], pas);
+                { PF_T0(tw); mbar_wait(&bar_acc_full[as], pas); PF_ACC(pf_w_acc, tw); }
+                PF_T0(pf_td);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * ACC_COLS + (uint32_t)(h * HN);
                 if constexpr (CAT) {
@@ -641,26 +669,47 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         else mbar_arrive(&bar_acc_empty[as]);
                     }
                 } else {
-                    uint32_t tr[HN / 8][8];
+                    // in chunks of 32 columns: the kernel runs at 168 registers per thread (three warps share a
+                    // 16 K-register partition), which a whole half row in flight next to the accumulators exceeds
+                    constexpr int CH = 4;                               // 8-column loads per chunk
 #pragma unroll
-                    for (int c = 0; c < HN / 8; ++c) tmem_ld8(taddr + c * 8, tr[c]);
-                    tmem_ld_wait();
-                    // the buffer is free as soon as its contents are in registers: hand it back before the adds
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) {
-                        if constexpr (TWO) mbar_arrive_cluster(acc_empty_leader[as]);
-                        else mbar_arrive(&bar_acc_empty[as]);
+                    for (int c0 = 0; c0 < HN / 8; c0 += CH) {
+                        uint32_t tr[CH][8];
+#pragma unroll
+                        for (int c = 0; c < CH; ++c)
+                            if (c0 + c < HN / 8) tmem_ld8(taddr + (c0 + c) * 8, tr[c]);
+                        tmem_ld_wait();
+                        if (c0 + CH >= HN / 8) {
+                            // the buffer is free as soon as its contents are in registers: hand it back before the adds
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) {
+                                if constexpr (TWO) mbar_arrive_cluster(acc_empty_leader[as]);
+                                else mbar_arrive(&bar_acc_empty[as]);
+                            }
+                        }
+#pragma unroll
+                        for (int c = 0; c < CH; ++c)
+                            if (c0 + c < HN / 8) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) acc[(c0 + c) * 8 + j] += __uint_as_float(tr[c][j]);
+                            }
                     }
-#pragma unroll
-                    for (int c = 0; c < HN / 8; ++c)
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) acc[c * 8 + j] += __uint_as_float(tr[c][j]);
                 }
                 if (++as == NBUF) { as = 0; pas ^= 1; }
+                PF_ACC(pf_drain, pf_td);
+#ifdef VOC_TC_PROF
+                ++pf_segs;
+#endif
             }
+            PF_T0(pf_tf);
+#ifdef VOC_TC_PROF
+            if (valid)
+#else
             if (!valid) continue;
-            float* Yrow = a.Y ? a.Y + (long long)b * a.y_bstride + (long long)m * a.ldy + n0 : nullptr;
+#endif
+            {
+            float* Yrow = has_y ? a.Y + (long long)b * a.y_bstride + (long long)m * a.ldy + n0 : nullptr;
             const long long soff = (long long)b * a.s_bstride + (long long)m * a.lds + n0;
 #pragma unroll
             for (int g16 = 0; g16 < HN; g16 += 16) {
@@ -676,17 +725,17 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     float v[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[j] = acc[g + j] * a.wscale;
-                    if (a.bias) {
+                    if (has_bias) {
                         const float4 b0 = *reinterpret_cast<const float4*>(&epi_par[0][pc]);
                         const float4 b1 = *reinterpret_cast<const float4*>(&epi_par[0][pc + 4]);
                         v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
                         v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
                     }
-                    if (a.act == VOC_ACT_GELU) {
+                    if (has_gelu) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) v[j] = voc_gelu(v[j]);
                     }
-                    if (a.scale) {
+                    if (has_scale) {
                         const float4 s0 = *reinterpret_cast<const float4*>(&epi_par[1][pc]);
                         const float4 s1 = *reinterpret_cast<const float4*>(&epi_par[1][pc + 4]);
                         v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w;
@@ -697,8 +746,8 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         for (int j = 0; j < 8; ++j) v[j] += rpf[pcur][(g % PB) / 8][j];
                     }
                     if (Yrow) stg256(Yrow + g, v);
-                    if (a.S_hi) {
-                        if (a.sn_a) {
+                    if (has_s) {
+                        if (has_snake) {
                             const float4 a0 = *reinterpret_cast<const float4*>(&epi_par[2][pc]);
                             const float4 a1 = *reinterpret_cast<const float4*>(&epi_par[2][pc + 4]);
                             const float4 i0 = *reinterpret_cast<const float4*>(&epi_par[3][pc]);
@@ -717,12 +766,20 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         }
                     }
                 }
-                if (a.S_hi) {
+                if (has_s) {
                     stg256u(a.S_hi + soff + g16, hi16);
                     stg256u(a.S_lo + soff + g16, lo16);
                 }
             }
+            }
+            PF_ACC(pf_final, pf_tf);
         }
+#ifdef VOC_TC_PROF
+        if (warp == 2 && lane == 0) {
+            PF_FLUSH(PF_EPI_TOTAL, clock64() - pf_t0); PF_FLUSH(PF_EPI_W_ACC, pf_w_acc); PF_FLUSH(PF_EPI_DRAIN, pf_drain);
+            PF_FLUSH(PF_EPI_FINAL, pf_final); PF_FLUSH(PF_SEGS, pf_segs);
+        }
+#endif
     }
     __syncwarp();
     tc_fence_before();
@@ -791,27 +848,27 @@ int pick_bn(int N) {
 
 constexpr int SMEM_BUDGET = 232448 - 1024 - 5120;   // opt-in maximum minus alignment slack and static smem
 
-template <int BN, int BK>
+template <int BN, int BK, int EPI = EPI_GENERIC>
 cudaError_t launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, int grid, size_t smem,
                         cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, BK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, BK, false, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              SMEM_BUDGET + 1024);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    tapgemm_tc_kernel<BN, BK, false><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmB, a);
+    tapgemm_tc_kernel<BN, BK, false, EPI><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmB, a);
     return cudaGetLastError();
 }
 
 // cta_group::2 launch: clusters of two CTAs
-template <int BN, int BK>
+template <int BN, int BK, int EPI = EPI_GENERIC>
 cudaError_t launch_inst2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB2, const TcArgs& a,
                          int grid, size_t smem, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, BK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, BK, true, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              SMEM_BUDGET + 1024);
         if (e != cudaSuccess) return e;
         attr_done = true;
@@ -823,7 +880,7 @@ cudaError_t launch_inst2(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, tapgemm_tc_kernel<BN, BK, true>, tmA, tmB, tmB2, a);
+    return cudaLaunchKernelEx(&cfg, tapgemm_tc_kernel<BN, BK, true, EPI>, tmA, tmB, tmB2, a);
 }
 
 template <int BK>
@@ -840,6 +897,17 @@ cudaError_t launch_bn(int BN, const CUtensorMap& tmA, const CUtensorMap& tmB, co
 }
 
 }  // namespace
+
+#ifdef VOC_TC_PROF
+extern "C" int voc_tc_prof_read(unsigned long long* out, int n, int reset) {
+    unsigned long long h[PF_N];
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(h, g_tc_prof, sizeof(h)) != cudaSuccess) return -1;
+    for (int i = 0; i < n && i < PF_N; ++i) out[i] = h[i];
+    if (reset) { memset(h, 0, sizeof(h)); cudaMemcpyToSymbol(g_tc_prof, h, sizeof(h)); }
+    return PF_N;
+}
+#endif
 
 bool voc_tc_eligible(const TapGemmParams& p) {
     if (!p.A_hi || !p.A_lo || !p.Wtc || p.S) return false;
@@ -947,14 +1015,34 @@ cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int n
     if (two_cat && !get_map(p.Wtc, p.K, p.N, p.ntaps, (long long)p.K * 2, (long long)p.N * p.K * 2, p.wtc_plane * 2, BK,
                             BN / 2, 1, &tmB2))
         return cudaErrorInvalidValue;
+    // the three hot epilogue shapes get their own instantiation on the tiles the decoder blocks use
+    int epi = EPI_GENERIC;
+    if (p.bias && p.act == VOC_ACT_NONE && !p.scale && p.S_hi && p.sn_a && !(flags & VOC_TC_GENERIC_EPI)) {
+        if (!p.R && !p.Y) epi = EPI_SNAKE_S;
+        else if (p.R && p.Y) epi = EPI_RES_Y_S;
+        else if (p.Y) epi = EPI_Y_S;
+    }
     if (two) {
         const int sms = num_sms > 0 ? num_sms : 148;
         const int grid2 = 2 * std::min(a.total_tiles, sms / 2);
-        return BN == 192 ? launch_inst2<192, 64>(tmA, tmB, tmB2, a, grid2, smem, st)
-                         : launch_inst2<96, 64>(tmA, tmB, tmB2, a, grid2, smem, st);
+#define VOC_TC_PAIR(BN_) \
+        (epi == EPI_SNAKE_S ? launch_inst2<BN_, 64, EPI_SNAKE_S>(tmA, tmB, tmB2, a, grid2, smem, st) \
+         : epi == EPI_RES_Y_S ? launch_inst2<BN_, 64, EPI_RES_Y_S>(tmA, tmB, tmB2, a, grid2, smem, st) \
+         : epi == EPI_Y_S ? launch_inst2<BN_, 64, EPI_Y_S>(tmA, tmB, tmB2, a, grid2, smem, st) \
+                          : launch_inst2<BN_, 64, EPI_GENERIC>(tmA, tmB, tmB2, a, grid2, smem, st))
+        return BN == 192 ? VOC_TC_PAIR(192) : VOC_TC_PAIR(96);
+#undef VOC_TC_PAIR
     }
 
     const int grid = std::min(a.total_tiles, num_sms > 0 ? num_sms : 148);
+    if (BK == 64 && (BN == 192 || BN == 96) && epi != EPI_GENERIC) {
+#define VOC_TC_SINGLE(BN_) \
+        (epi == EPI_SNAKE_S ? launch_inst<BN_, 64, EPI_SNAKE_S>(tmA, tmB, a, grid, smem, st) \
+         : epi == EPI_RES_Y_S ? launch_inst<BN_, 64, EPI_RES_Y_S>(tmA, tmB, a, grid, smem, st) \
+                              : launch_inst<BN_, 64, EPI_Y_S>(tmA, tmB, a, grid, smem, st))
+        return BN == 192 ? VOC_TC_SINGLE(192) : VOC_TC_SINGLE(96);
+#undef VOC_TC_SINGLE
+    }
     if (BK == 64) return launch_bn<64>(BN, tmA, tmB, a, grid, smem, st);
     return launch_bn<32>(BN, tmA, tmB, a, grid, smem, st);
 }

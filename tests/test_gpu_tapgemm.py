@@ -8,7 +8,7 @@ Tolerance: the tensor path multiplies split-fp16 operands (~22 mantissa bits) an
 FP32, so a dot product of O(1) terms is good to a few 1e-6 relative to the output scale.
 
 tc_flags: 0 = default (tap reuse through row-shifted descriptors, cta_group::2 pairs where the launcher
-selects them), 1 = per-tap aligned loads, 128 = single-CTA kernel only."""
+selects them), 1 = per-tap aligned loads, 8 = run-time epilogue only, 128 = single-CTA kernel only."""
 import numpy as np
 import pytest
 
@@ -79,6 +79,39 @@ def test_tc_tapgemm_matches_float64(backend, case, flags):
         es = float(np.abs(S - s_ref).max())
         print(f"{name} mode {mode} flags {flags}: max|dY| {ey:.2e}  max|dS| {es:.2e}")
         assert ey < 2e-5 and es < 2e-5, (name, mode, ey, es)
+
+
+EPI_CASES = [c for c in CASES if c[0] in ("linear_k96", "conv7_d1", "conv7_d3", "convt_trim_both", "pair_conv7_c192",
+                                           "pair_conv7_c96", "pair_convt_k768")]
+
+
+@pytest.mark.parametrize("kind", ["snake_s", "res_y_s", "y_s"])
+@pytest.mark.parametrize("case", EPI_CASES, ids=[c[0] for c in EPI_CASES])
+def test_tc_compile_time_epilogues(backend, case, kind):
+    """The three hot layer kinds (7-tap conv, 1x1 conv with residual, transposed conv) run an epilogue fixed at
+    compile time on the 96- and 192-column tiles; it must equal the run-time one (tc_flags bit 3) bit for bit."""
+    name, B, a_rows, K, N, M, row0, taps = case
+    rng = np.random.default_rng(sum(map(ord, name + kind)))
+    A = rng.standard_normal((B, a_rows, K)).astype(np.float32)
+    W = (rng.standard_normal((len(taps) * K, N)) / np.sqrt(len(taps) * K)).astype(np.float32)
+    bias = (0.1 * rng.standard_normal(N)).astype(np.float32)
+    R = rng.standard_normal((B, M, N)).astype(np.float32) if kind == "res_y_s" else None
+    sn_a = np.exp(0.1 * rng.standard_normal(N)).astype(np.float32)
+    sn_invb = (1.0 / (np.exp(0.1 * rng.standard_normal(N)) + 1e-9)).astype(np.float32)
+    want_y = kind != "snake_s"
+    v_ref, s_ref = ref_tapgemm(A, W, taps, M, row0, bias, None, 0, R, sn_a, sn_invb)
+    out = {}
+    for flags in (0, 8):
+        rc, Y, S, _ = backend.test_tapgemm(2, A, W, taps, M, row0, bias=bias, R=R, sn_a=sn_a, sn_invb=sn_invb,
+                                           want_y=want_y, want_s=True, tc_flags=flags)
+        assert rc == 0, (name, kind, flags, rc)
+        assert float(np.abs(S - s_ref).max()) < 2e-5, (name, kind, flags)
+        if want_y:
+            assert float(np.abs(Y - v_ref).max()) < 2e-5, (name, kind, flags)
+        out[flags] = (Y, S)
+    assert np.array_equal(out[0][1], out[8][1]), (name, kind, "S differs between compile-time and run-time epilogue")
+    if want_y:
+        assert np.array_equal(out[0][0], out[8][0]), (name, kind, "Y differs")
 
 
 def test_tc_gelu_and_plain_operand_output(backend):

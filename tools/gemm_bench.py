@@ -38,6 +38,30 @@ def layers(trim_both=True):
     return out
 
 
+PROF_NAMES = ["mma_total", "mma_w_acc", "mma_w_a", "mma_w_b", "epi_total", "epi_w_acc", "epi_drain", "epi_final",
+              "prod_total", "prod_w_a", "prod_w_b", "ctas", "tiles", "segs"]
+
+
+def read_prof(backend, iters):
+    """Cycle counters of a -DVOC_TC_PROF build (tools/ab_build.sh), per tile; None for a production build."""
+    import ctypes as C
+    lib = backend.load_library()
+    if not hasattr(lib, "voc_tc_prof_read"):
+        return None
+    buf = (C.c_ulonglong * 16)()
+    lib.voc_tc_prof_read.restype = C.c_int
+    lib.voc_tc_prof_read.argtypes = [C.POINTER(C.c_ulonglong), C.c_int, C.c_int]
+    if lib.voc_tc_prof_read(buf, 16, 1) < 0:
+        return None
+    v = dict(zip(PROF_NAMES, [int(x) for x in buf]))
+    tiles = max(v["tiles"], 1)                    # tiles walked by the issuing warps (pairs count once)
+    ctas = max(v["ctas"], 1)
+    out = {"tiles_per_walker": round(tiles / ctas, 2), "segs_per_tile": round(v["segs"] / max(tiles, 1), 2)}
+    for k in PROF_NAMES[:11]:
+        out[k] = round(v[k] / tiles)              # cycles per tile (epilogue: one warp per CTA sampled; pairs: both CTAs summed)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--windows", type=int, default=4)
@@ -72,6 +96,9 @@ def main():
                        "tflops": round(flops / ms / 1e9, 2) if ms > 0 else None}
                 if mode == 2 and ms > 0:
                     rec["mma_tflops"] = round(3 * flops / ms / 1e9, 1)
+                prof = read_prof(backend, args.iters)
+                if prof:
+                    rec["prof"] = prof
                 out = S if S is not None else Y
                 if args.check and out is not None:
                     if ref is None:
