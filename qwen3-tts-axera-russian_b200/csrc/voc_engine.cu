@@ -187,7 +187,7 @@ struct Engine {
     SnakeP head_snake; float* head_w = nullptr; float head_b = 0.f;
 
     // activations
-    DevBuf front, big[3], chunks, stitch_f32;
+    DevBuf front, big[4], chunks, stitch_f32;
     float *f_rvq, *f_pre, *f_h, *f_hn, *f_qkv, *f_att, *f_gu, *f_act, *f_x, *f_ln, *f_mid, *f_x2;
     size_t big_elems = 0;
     int* d_err = nullptr;
@@ -553,7 +553,7 @@ static int engine_finalize(Engine* E) {
         mx = std::max(mx, (size_t)L * (c.decoder_dim >> (b + 1)));
     }
     E->big_elems = mx;
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < 4; ++i) {
         CK(cudaMalloc(&E->big[i].p, mx * W * sizeof(float))); E->big[i].n = mx * W;
         E->cap[E->big[i].p] = mx * W;
     }
@@ -649,7 +649,7 @@ static int run_wave(Engine* E, const long long* d_codes, int n_frames, int win_s
         if (int r2 = dbg_capture(E, nm, act(E, x), (size_t)nw * L * C, st)) return r2;
     }
     // K4: decoder conv-in, emits only Snake_0(conv_in(x)) -- the operand of block 0
-    float* bX = E->big[0].p; float* bS = E->big[1].p; float* bT = E->big[2].p;
+    float* bX = E->big[0].p; float* bS = E->big[1].p; float* bT = E->big[2].p; float* bX2 = E->big[3].p;
     {
         TapGemmParams p = gp(E->conv_in, act(E, x), (long long)L * c.latent_dim, L, 0, L, nw);
         setS(p, act(E, bS), &E->blocks[0].s_in);
@@ -682,15 +682,19 @@ static int run_wave(Engine* E, const long long* d_codes, int n_frames, int win_s
                 setS(p, act(E, bT), &R.s2);
                 GEMM(T_C7[ti], p);
             }
-            {   // conv k1 + residual -> x (in place) and the next consumer's Snake
+            {   // conv k1 + residual -> x and the next consumer's Snake.  The residual stream ping-pongs between
+                // two buffers: updating it in place (a lane's float32 stores landing in the 128-byte lines its
+                // next residual loads are about to read) ran the fast epilogue 3.4x slower at C = 192.
                 TapGemmParams p = gp(R.c2, act(E, bT), (long long)L * C, L, 0, L, nw);
                 setR(p, bX);
                 const bool last_ru = (j + 1 == Bk.ru.size());
                 const SnakeP& nxt = !last_ru ? Bk.ru[j + 1].s1
                                   : (b + 1 < E->blocks.size() ? E->blocks[b + 1].s_in : E->head_snake);
                 setS(p, act(E, bS), &nxt);
-                if (!last_ru || E->debug) setY(p, bX);        // the residual stream ends with the block
+                const bool writes_y = !last_ru || E->debug;   // the residual stream ends with the block
+                if (writes_y) setY(p, bX2);
                 GEMM(T_C1[ti], p);
+                if (writes_y) std::swap(bX, bX2);
             }
         }
         char nm[32]; snprintf(nm, sizeof nm, "dec%d", (int)b);
@@ -1430,7 +1434,8 @@ int voc_test_tapgemm(int device, int mode, int tc_flags, int B, int a_rows, int 
     TapGemmParams p = gp(g, act(E, dA), (long long)a_rows * K, a_rows, a_row0, M, B);
     p.act = act_kind; p.scale = d_scale;
     if (d_R) setR(p, d_R);
-    if (Y) setY(p, dY);
+    // VOC_TEST_INPLACE (timing only): the float32 output overwrites the residual, as the residual units do
+    if (Y) setY(p, (d_R && getenv("VOC_TEST_INPLACE")) ? d_R : dY);
     if (S) setS(p, act(E, dS), sp.a ? &sp : nullptr);
     if (mode == 2 && !voc_tc_eligible(p)) return 1;
     if (mode == 1) p.Wtc = nullptr;                 // keeps run_gemm on the CUDA-core kernel
