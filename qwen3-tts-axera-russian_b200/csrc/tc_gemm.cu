@@ -60,6 +60,7 @@ struct TcArgs {
     int M, N, K, B, ntaps, a_row0;
     int tap_off[VOC_MAX_TAPS];
     int a_reuse, a_min_off, a_box_rows, seg_iters;
+    int seg_head;                            // the first seg_head segments of a tile are twice as long (0: none)
     int tap_row0, tap_step;                  // a_reuse: tap t starts tap_row0 + t * tap_step rows into the halo tile
     int m_tiles, n_tiles, k_chunks, total_tiles;
     int SA, SB;
@@ -466,7 +467,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint32_t rt0 = tmem_base >> 24;     // lanes < 128 live in bits 16..22
             auto reg = [&](uint32_t x) { return opaque_u32(x + rt0); };
             const int last_ksteps = (int)reg((uint32_t)((a.K - (a.k_chunks - 1) * BK + 15) >> 4));  // of the last chunk
-            const int seg_iters = (int)reg((uint32_t)a.seg_iters);
+            const int seg_iters = (int)reg((uint32_t)a.seg_iters), seg_head = (int)reg((uint32_t)a.seg_head);
             const int SA = (int)reg((uint32_t)a.SA), SB = (int)reg((uint32_t)a.SB);
             const int ipt = (int)reg((uint32_t)iters_per_tile);
             // One "fill" of an A stage serves n_inner consecutive stages: all taps of a K chunk with tap reuse,
@@ -484,7 +485,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             PF_DECL(pf_w_acc); PF_DECL(pf_w_a); PF_DECL(pf_w_b); PF_DECL(pf_tiles); PF_T0(pf_t0);
             for (int tile = walker; tile < a.total_tiles; tile += walkers) {
                 uint32_t tmem_acc = 0, accum = 0;
-                int seg_left = 0, iters_left = ipt;
+                int seg_left = 0, iters_left = ipt, seg_idx = 0;
                 for (int fill = 0; fill < n_fills; ++fill) {
                     // tap reuse: the descriptor simply starts some rows into the halo tile and steps from tap to
                     // tap.  The swizzle is a function of the absolute shared-memory address, so no base-offset
@@ -497,7 +498,11 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             { PF_T0(tw); mbar_spin_a(acc_empty0 + 8 * as, pas ^ 1); PF_ACC(pf_w_acc, tw); }
                             tmem_acc = tmem_base + (uint32_t)as * ACC_COLS;
                             accum = 0;
-                            seg_left = iters_left < seg_iters ? iters_left : seg_iters;
+                            // the segments issued while the epilogue warps are still busy with the previous
+                            // tile's final epilogue are twice as long, which doubles the issuing warp's run-ahead
+                            const int want = seg_idx < seg_head ? 2 * seg_iters : seg_iters;
+                            seg_left = iters_left < want ? iters_left : want;
+                            ++seg_idx;
                         }
                         { PF_T0(tw); mbar_spin_a(b_full0 + 8 * sb, pb); PF_ACC(pf_w_b, tw); }
                         tc_fence_after();
@@ -596,7 +601,8 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // measured and are not faster: profiles/r1_epilogue_experiments.txt)
         const int q = warp & 3;                       // the TMEM lane quadrant this warp can read
         const int h = (warp - 2) >> 2;                // which part of the tile's columns
-        const int nseg = (iters_per_tile + a.seg_iters - 1) / a.seg_iters;
+        int nseg = 0;                                 // same segment schedule as the issuing warp
+        for (int rem = iters_per_tile; rem > 0; ++nseg) rem -= (nseg < a.seg_head ? 2 : 1) * a.seg_iters;
         const int etid = threadIdx.x - 64;
         const bool has_bias = EPI != EPI_GENERIC || a.bias != nullptr;
         const bool has_gelu = EPI == EPI_GENERIC && a.act == VOC_ACT_GELU;
@@ -964,6 +970,9 @@ cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int n
     // the concatenated form (BN <= 128) keeps the same number of k-steps per segment
     // (one MMA per k-step reaches its main accumulator, so a segment may span three times the k-steps)
     a.seg_iters = std::max(1, seg_mmas / ((BN <= 128 ? 1 : 3) * BK / 16));
+    // 3-pass form (two 192-column TMEM buffers, a 13 k-cycle final epilogue per tile at C = 192): the first two
+    // segments of a tile hold twice the MMAs.  Measured end to end: see profiles/r1_segment_sweep.txt.
+    a.seg_head = (BN > 128 && !(flags & VOC_TC_NO_SEG_HEAD)) ? 2 : 0;
     // cta_group::2 pairs: for the wide layers (column tile 192 or 128, several M tiles per window)
     // Measured (tools/probe_pair.py, 4 windows): conv7 C = 768 / 384 / 192: 0.202 -> 0.152, 0.260 -> 0.209,
     // 0.257 -> 0.225 ms; conv-in 0.131 -> 0.097; but the thin layers (1x1 convs, 2-tap transposed convs with

@@ -110,10 +110,10 @@ bool voc_tc_eligible(const TapGemmParams& p);
 cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int num_sms, int flags);
 void voc_tc_clear_cache();
 // flags: bit 0 no tap reuse, bit 1 / bit 2 force 64- / 32-wide K chunks, bit 3 run-time (generic) epilogue only,
-// bit 6 / bit 7 always / never cta_group::2 pairs, bits 8.. MMAs into the main accumulator per round-to-nearest
-// flush (default 24)
-enum { VOC_TC_NO_REUSE = 1, VOC_TC_BK64 = 2, VOC_TC_BK32 = 4, VOC_TC_GENERIC_EPI = 8, VOC_TC_FORCE_PAIR = 64,
-       VOC_TC_NO_PAIR = 128 };
+// bit 4 no double-length head segments, bit 6 / bit 7 always / never cta_group::2 pairs, bits 8.. MMAs into the main
+// accumulator per round-to-nearest flush (default 24)
+enum { VOC_TC_NO_REUSE = 1, VOC_TC_BK64 = 2, VOC_TC_BK32 = 4, VOC_TC_GENERIC_EPI = 8, VOC_TC_NO_SEG_HEAD = 16,
+       VOC_TC_FORCE_PAIR = 64, VOC_TC_NO_PAIR = 128 };
 
 // host-side launch wrappers (simt_kernels.cu)
 cudaError_t voc_launch_tapgemm_simt(const TapGemmParams& p, cudaStream_t st);
