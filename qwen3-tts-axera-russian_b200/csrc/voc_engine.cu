@@ -162,6 +162,7 @@ struct Engine {
     struct WaveGraph { cudaGraphExec_t exec = nullptr; long long launches = 0; int seen = 0; };
     std::map<std::tuple<const void*, const void*, int, int, int, int, int, int>, WaveGraph> graphs;
     bool use_graphs = true;
+    int graph_max_wave = 4;                    // waves of at most this many windows are replayed as graphs
     bool finalized = false;
     int gemm_mode = 0;          // 0 auto (= tc), 1 simt (FP32 CUDA cores), 2 tc (tcgen05, split fp16)
     int tc_flags = 0;           // VOC_TC_* experiment switches
@@ -729,7 +730,7 @@ static int run_windows(Engine* E, const long long* d_codes, int n_frames, int wi
         // Small waves are launch-bound, so a wave that recurs with the same buffers (the streaming client's
         // one-window requests through the host entry points) is replayed as a CUDA graph: first sight runs
         // eagerly (lazy set-up: kernel attributes, tensor maps), second sight is captured, later ones replay.
-        const bool graphable = E->use_graphs && nw <= 4 && !E->profile && !E->debug;
+        const bool graphable = E->use_graphs && nw <= E->graph_max_wave && !E->profile && !E->debug;
         if (!graphable) {
             if (int r = run_wave(E, d_codes, n_frames, win_step, w, nw, out, st)) return r;
             continue;
@@ -996,6 +997,7 @@ void* voc_create(const char* cfg_json, int device, int wave) {
     // experiment hooks (the documented switch is voc_set_option)
     if (const char* g = getenv("VOC_GEMM")) E->gemm_mode = !strcmp(g, "simt") ? 1 : !strcmp(g, "tc") ? 2 : 0;
     if (const char* f = getenv("VOC_TC_FLAGS")) E->tc_flags = atoi(f);
+    if (const char* f = getenv("VOC_GRAPH_MAX_WAVE")) E->graph_max_wave = atoi(f);
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking) != cudaSuccess) {
         g_create_error = "cudaSetDevice / stream creation failed";
         fprintf(stderr, "voc_create: %s\n", g_create_error.c_str());
@@ -1326,6 +1328,7 @@ int voc_set_option(void* h, const char* key, const char* value) {
     }
     if (k == "tc_flags") { E->tc_flags = atoi(v.c_str()); return VOC_OK; }
     if (k == "graphs") { E->use_graphs = (v == "1"); return VOC_OK; }
+    if (k == "graph_max_wave") { E->graph_max_wave = atoi(v.c_str()); return VOC_OK; }
     if (k == "profile") { E->profile = (v == "1"); return VOC_OK; }
     if (k == "debug") { E->debug = (v == "1"); if (!E->debug) E->dbg.clear(); return VOC_OK; }
     return fail(E, VOC_E_INVALID, "unknown option " + k);
