@@ -317,13 +317,14 @@ __device__ __forceinline__ constexpr uint32_t smem_desc_hi() {
 // TWO: cta_group::2.  A cluster of two CTAs computes two consecutive 128-row M tiles of the same column
 // tile with M = 256 MMAs issued by the leader (rank 0): each CTA stages its own A tile and HALF of the
 // weight rows: one issuing warp feeds two SMs' tensor pipes and each CTA streams half the weight bytes.
-// EPI fixes the epilogue's shape at compile time for the three hot layer kinds (their run-time tests and the
+// EPI fixes the epilogue's shape at compile time for the four hot layer kinds (their run-time tests and the
 // untaken variants' code -- erff for GELU alone is ~200 instructions per 8 columns -- otherwise sit in every
 // 16-column group of a 5000-instruction straight-line epilogue that already stalls on instruction fetch):
 enum { EPI_GENERIC = 0,      // everything decided at run time from TcArgs
        EPI_SNAKE_S = 1,      // bias, Snake -> split operand S                     (7-tap convs of a residual unit)
        EPI_RES_Y_S = 2,      // bias, + residual -> Y; Snake -> split operand S    (1x1 convs of a residual unit)
-       EPI_Y_S = 3 };        // bias -> Y; Snake -> split operand S                (transposed convs)
+       EPI_Y_S = 3,          // bias -> Y; Snake -> split operand S                (transposed convs)
+       EPI_RES_S = 4 };      // bias, + residual; Snake -> split operand S         (the last 1x1 conv of a block)
 
 template <int BN, int BK, bool TWO, int EPI = EPI_GENERIC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -607,7 +608,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const bool has_bias = EPI != EPI_GENERIC || a.bias != nullptr;
         const bool has_gelu = EPI == EPI_GENERIC && a.act == VOC_ACT_GELU;
         const bool has_scale = EPI == EPI_GENERIC && a.scale != nullptr;
-        const bool has_r = EPI == EPI_RES_Y_S || (EPI == EPI_GENERIC && a.R != nullptr);
+        const bool has_r = EPI == EPI_RES_Y_S || EPI == EPI_RES_S || (EPI == EPI_GENERIC && a.R != nullptr);
         const bool has_y = EPI == EPI_RES_Y_S || EPI == EPI_Y_S || (EPI == EPI_GENERIC && a.Y != nullptr);
         const bool has_s = EPI != EPI_GENERIC || a.S_hi != nullptr;
         const bool has_snake = EPI != EPI_GENERIC || a.sn_a != nullptr;
@@ -1030,6 +1031,7 @@ cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int n
         if (!p.R && !p.Y) epi = EPI_SNAKE_S;
         else if (p.R && p.Y) epi = EPI_RES_Y_S;
         else if (p.Y) epi = EPI_Y_S;
+        else epi = EPI_RES_S;
     }
     if (two) {
         const int sms = num_sms > 0 ? num_sms : 148;
@@ -1038,6 +1040,7 @@ cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int n
         (epi == EPI_SNAKE_S ? launch_inst2<BN_, 64, EPI_SNAKE_S>(tmA, tmB, tmB2, a, grid2, smem, st) \
          : epi == EPI_RES_Y_S ? launch_inst2<BN_, 64, EPI_RES_Y_S>(tmA, tmB, tmB2, a, grid2, smem, st) \
          : epi == EPI_Y_S ? launch_inst2<BN_, 64, EPI_Y_S>(tmA, tmB, tmB2, a, grid2, smem, st) \
+         : epi == EPI_RES_S ? launch_inst2<BN_, 64, EPI_RES_S>(tmA, tmB, tmB2, a, grid2, smem, st) \
                           : launch_inst2<BN_, 64, EPI_GENERIC>(tmA, tmB, tmB2, a, grid2, smem, st))
         return BN == 192 ? VOC_TC_PAIR(192) : VOC_TC_PAIR(96);
 #undef VOC_TC_PAIR
@@ -1048,6 +1051,7 @@ cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int n
 #define VOC_TC_SINGLE(BN_) \
         (epi == EPI_SNAKE_S ? launch_inst<BN_, 64, EPI_SNAKE_S>(tmA, tmB, a, grid, smem, st) \
          : epi == EPI_RES_Y_S ? launch_inst<BN_, 64, EPI_RES_Y_S>(tmA, tmB, a, grid, smem, st) \
+         : epi == EPI_RES_S ? launch_inst<BN_, 64, EPI_RES_S>(tmA, tmB, a, grid, smem, st) \
                               : launch_inst<BN_, 64, EPI_Y_S>(tmA, tmB, a, grid, smem, st))
         return BN == 192 ? VOC_TC_SINGLE(192) : VOC_TC_SINGLE(96);
 #undef VOC_TC_SINGLE

@@ -85,20 +85,20 @@ EPI_CASES = [c for c in CASES if c[0] in ("linear_k96", "conv7_d1", "conv7_d3", 
                                            "pair_conv7_c96", "pair_convt_k768")]
 
 
-@pytest.mark.parametrize("kind", ["snake_s", "res_y_s", "y_s"])
+@pytest.mark.parametrize("kind", ["snake_s", "res_y_s", "y_s", "res_s"])
 @pytest.mark.parametrize("case", EPI_CASES, ids=[c[0] for c in EPI_CASES])
 def test_tc_compile_time_epilogues(backend, case, kind):
-    """The three hot layer kinds (7-tap conv, 1x1 conv with residual, transposed conv) run an epilogue fixed at
+    """The hot layer kinds (7-tap conv, 1x1 conv with residual with / without a float32 output, transposed conv) run an epilogue fixed at
     compile time on the 96- and 192-column tiles; it must equal the run-time one (tc_flags bit 3) bit for bit."""
     name, B, a_rows, K, N, M, row0, taps = case
     rng = np.random.default_rng(sum(map(ord, name + kind)))
     A = rng.standard_normal((B, a_rows, K)).astype(np.float32)
     W = (rng.standard_normal((len(taps) * K, N)) / np.sqrt(len(taps) * K)).astype(np.float32)
     bias = (0.1 * rng.standard_normal(N)).astype(np.float32)
-    R = rng.standard_normal((B, M, N)).astype(np.float32) if kind == "res_y_s" else None
+    R = rng.standard_normal((B, M, N)).astype(np.float32) if kind in ("res_y_s", "res_s") else None
     sn_a = np.exp(0.1 * rng.standard_normal(N)).astype(np.float32)
     sn_invb = (1.0 / (np.exp(0.1 * rng.standard_normal(N)) + 1e-9)).astype(np.float32)
-    want_y = kind != "snake_s"
+    want_y = kind in ("res_y_s", "y_s")
     v_ref, s_ref = ref_tapgemm(A, W, taps, M, row0, bias, None, 0, R, sn_a, sn_invb)
     out = {}
     for flags in (0, 8):
