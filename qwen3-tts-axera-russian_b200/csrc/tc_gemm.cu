@@ -63,6 +63,7 @@ struct TcArgs {
     int seg_head;                            // the first seg_head segments of a tile are twice as long (0: none)
     int tap_row0, tap_step;                  // a_reuse: tap t starts tap_row0 + t * tap_step rows into the halo tile
     int m_tiles, n_tiles, k_chunks, total_tiles;
+    int kc_steps, kc_last;                   // k-steps (of 16) per K chunk / in the last one; chunk c starts at c * kc_steps * 16
     int SA, SB;
     float wscale;
     const float* bias;  int act;  const float* scale;
@@ -414,10 +415,10 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                 if constexpr (TWO) {
                                     // both CTAs' bytes are credited to the leader's barrier
                                     if (rank == 0) mbar_expect_tx(&bar_a_full[sa], 2 * a_stage);
-                                    tma_load_4d_2sm(smA + sa * a_stage, &tmA, mapa_u32(&bar_a_full[sa], 0), kc * BK, arow, b, 0);
+                                    tma_load_4d_2sm(smA + sa * a_stage, &tmA, mapa_u32(&bar_a_full[sa], 0), kc * a.kc_steps * 16, arow, b, 0);
                                 } else {
                                     mbar_expect_tx(&bar_a_full[sa], a_stage);
-                                    tma_load_4d(smA + sa * a_stage, &tmA, &bar_a_full[sa], kc * BK, arow, b, 0);
+                                    tma_load_4d(smA + sa * a_stage, &tmA, &bar_a_full[sa], kc * a.kc_steps * 16, arow, b, 0);
                                 }
                             }
                             if (++sa == a.SA) { sa = 0; pa ^= 1; }
@@ -427,14 +428,14 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             if constexpr (TWO && CAT) {
                                 if (rank == 0) mbar_expect_tx(&bar_b_full[sb], 2 * B_STAGE);
                                 const uint32_t lb = mapa_u32(&bar_b_full[sb], 0);
-                                tma_load_4d_2sm(smB + sb * B_STAGE, &tmB, lb, kc * BK, n0, tap, (int)rank);            // a whole plane
-                                tma_load_4d_2sm(smB + sb * B_STAGE + B_PLANE, &tmB2, lb, kc * BK, n0 + (int)rank * (BN / 2), tap, 0);
+                                tma_load_4d_2sm(smB + sb * B_STAGE, &tmB, lb, kc * a.kc_steps * 16, n0, tap, (int)rank);            // a whole plane
+                                tma_load_4d_2sm(smB + sb * B_STAGE + B_PLANE, &tmB2, lb, kc * a.kc_steps * 16, n0 + (int)rank * (BN / 2), tap, 0);
                             } else if constexpr (TWO) {
                                 if (rank == 0) mbar_expect_tx(&bar_b_full[sb], 2 * B_STAGE);
-                                tma_load_4d_2sm(smB + sb * B_STAGE, &tmB, mapa_u32(&bar_b_full[sb], 0), kc * BK, n0, tap, 0);
+                                tma_load_4d_2sm(smB + sb * B_STAGE, &tmB, mapa_u32(&bar_b_full[sb], 0), kc * a.kc_steps * 16, n0, tap, 0);
                             } else {
                                 mbar_expect_tx(&bar_b_full[sb], B_STAGE);
-                                tma_load_4d(smB + sb * B_STAGE, &tmB, &bar_b_full[sb], kc * BK, n0, tap, 0);
+                                tma_load_4d(smB + sb * B_STAGE, &tmB, &bar_b_full[sb], kc * a.kc_steps * 16, n0, tap, 0);
                             }
                         }
                         if (++sb == a.SB) { sb = 0; pb ^= 1; }
@@ -467,7 +468,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             // at compile time: adding it pins a kernel parameter into a register for the whole loop.
             const uint32_t rt0 = tmem_base >> 24;     // lanes < 128 live in bits 16..22
             auto reg = [&](uint32_t x) { return opaque_u32(x + rt0); };
-            const int last_ksteps = (int)reg((uint32_t)((a.K - (a.k_chunks - 1) * BK + 15) >> 4));  // of the last chunk
+            const int ks_regular = (int)reg((uint32_t)a.kc_steps), ks_last = (int)reg((uint32_t)a.kc_last);
             const int seg_iters = (int)reg((uint32_t)a.seg_iters), seg_head = (int)reg((uint32_t)a.seg_head);
             const int SA = (int)reg((uint32_t)a.SA), SB = (int)reg((uint32_t)a.SB);
             const int ipt = (int)reg((uint32_t)iters_per_tile);
@@ -493,7 +494,11 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     // correction is applied (the documented (addr >> 7) & 7 value yields garbage).
                     { PF_T0(tw); mbar_spin_a(a_full0 + 8 * sa, pa); PF_ACC(pf_w_a, tw); }
                     uint32_t a_lo = a_desc0 + (uint32_t)sa * a_stage16;
-                    const bool full_chunk = fill < first_short || last_ksteps == BK / 16;
+                    const int ks_this = fill < first_short ? ks_regular : ks_last;      // k-steps of this fill's stages
+                    // the stages of one fill, with the k-step count a compile-time constant: dispatched once per
+                    // fill (a per-stage switch compiled to a constant-bank jump table: a dependent load + BRX)
+                    auto stages = [&](auto nks) {
+                    constexpr int NKS = decltype(nks)::value;
                     for (int t = 0; t < n_inner; ++t) {
                         if (seg_left == 0) {
                             { PF_T0(tw); mbar_spin_a(acc_empty0 + 8 * as, pas ^ 1); PF_ACC(pf_w_acc, tw); }
@@ -512,8 +517,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         if (elect_one()) {
                             // every path is branch-free and fully unrolled (a short last chunk picks one of the
                             // compile-time variants); only the first MMA of a stage takes a run-time accumulate flag
-                            auto issue = [&](auto nks) {
-                                constexpr int NKS = decltype(nks)::value;        // k-steps in this stage, compile time
+                            {
                                 if constexpr (CAT && TWO) {
 #pragma unroll
                                     for (int ks = 0; ks < NKS; ++ks) {
@@ -557,11 +561,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                         }
                                     }
                                 }
-                            };
-                            if (full_chunk) issue(std::integral_constant<int, BK / 16>{});
-                            else if (BK == 64 && last_ksteps == 2) issue(std::integral_constant<int, 2>{});
-                            else if (BK == 64 && last_ksteps == 3) issue(std::integral_constant<int, 3>{});
-                            else issue(std::integral_constant<int, 1>{});
+                            }
                             if constexpr (TWO) {
                                 mma2_commit_both_a(b_empty0 + 8 * sb);
                                 if (last_of_seg) mma2_commit_both_a(acc_full0 + 8 * as);
@@ -577,6 +577,11 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         if (++sb == SB) { sb = 0; pb ^= 1; b_lo = b_desc0; }
                         if (last_of_seg) { if (++as == NBUF) { as = 0; pas ^= 1; } }
                     }
+                    };
+                    if (ks_this == BK / 16) stages(std::integral_constant<int, BK / 16>{});
+                    else if (BK == 64 && ks_this == 3) stages(std::integral_constant<int, 3>{});
+                    else if (BK == 64 && ks_this == 2) stages(std::integral_constant<int, 2>{});
+                    else stages(std::integral_constant<int, 1>{});
                     // the A stage is free once everything issued so far has read it
                     if (elect_one()) {
                         if constexpr (TWO) mma2_commit_both_a(a_empty0 + 8 * sa);
@@ -970,10 +975,6 @@ cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int n
     // seg_mmas counts MMAs into the main accumulator per segment as in the 3-pass form (3 per k-step);
     // the concatenated form (BN <= 128) keeps the same number of k-steps per segment
     // (one MMA per k-step reaches its main accumulator, so a segment may span three times the k-steps)
-    a.seg_iters = std::max(1, seg_mmas / ((BN <= 128 ? 1 : 3) * BK / 16));
-    // 3-pass form (two 192-column TMEM buffers, a 13 k-cycle final epilogue per tile at C = 192): the first two
-    // segments of a tile hold twice the MMAs.  Measured end to end: see profiles/r1_segment_sweep.txt.
-    a.seg_head = (BN > 128 && !(flags & VOC_TC_NO_SEG_HEAD)) ? 2 : 0;
     // cta_group::2 pairs: for the wide layers (column tile 192 or 128, several M tiles per window)
     // Measured (tools/probe_pair.py, 4 windows): conv7 C = 768 / 384 / 192: 0.202 -> 0.152, 0.260 -> 0.209,
     // 0.257 -> 0.225 ms; conv-in 0.131 -> 0.097; but the thin layers (1x1 convs, 2-tap transposed convs with
@@ -988,6 +989,18 @@ cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int n
                      ((flags & VOC_TC_FORCE_PAIR) || (BN == 192 && (long long)p.ntaps * p.K >= 768) ||
                       (BN == 96 && (long long)p.ntaps * p.K >= 384));
     a.m_tiles = (p.M + BM - 1) / BM; a.n_tiles = p.N / BN; a.k_chunks = (p.K + BK - 1) / BK;
+    // K chunks of equal depth: K = 96 runs as 48 + 48 (two 64-wide boxes, the second starting at column 48, three
+    // k-steps used of each) instead of 64 + 32 -- a 2-k-step stage is shorter than the issuing warp's scalar path.
+    {
+        const int ksteps = (p.K + 15) / 16;
+        a.kc_steps = (ksteps + a.k_chunks - 1) / a.k_chunks;
+        a.k_chunks = (ksteps + a.kc_steps - 1) / a.kc_steps;
+        a.kc_last = ksteps - (a.k_chunks - 1) * a.kc_steps;
+    }
+    a.seg_iters = std::max(1, seg_mmas / ((BN <= 128 ? 1 : 3) * a.kc_steps));
+    // 3-pass form (two 192-column TMEM buffers, a 13 k-cycle final epilogue per tile at C = 192): the first two
+    // segments of a tile hold twice the MMAs.  Measured end to end: see profiles/r1_segment_sweep.txt.
+    a.seg_head = (BN > 128 && !(flags & VOC_TC_NO_SEG_HEAD)) ? 2 : 0;
     if (two) a.m_tiles = (a.m_tiles + 1) / 2;             // M-tile pairs
     a.total_tiles = a.m_tiles * a.n_tiles * p.B;
     a.wscale = p.wscale;

@@ -49,6 +49,13 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int iters, long long* out
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = slot;
     if (threadIdx.x == 0) {
+        // N < 0: the concatenated form's pattern -- an N = 192 MMA into columns [0, 192) followed by an N = 96 MMA into
+        // columns [96 + off, 192 + off) with off = 0 (what tc_gemm.cu does: the correction block is the upper half of
+        // the wide MMA's output) or off = 96 (disjoint columns), per k-step
+        const bool cat = N < 0;
+        const uint32_t cat_off = N == -2 ? 96u : 0u;
+        if (cat) N = 192;
+        const uint32_t idesc96 = (1u << 4) | ((uint32_t)(96 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint32_t a_lo = desc_lo(smA), b_lo = desc_lo(smB);
         const uint32_t bar2_a = smem_u32(&bar2), bar3_a = smem_u32(&bar3);
@@ -59,7 +66,10 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int iters, long long* out
             for (int grp = 0; grp < 8; ++grp) {
                 const uint32_t d = tmem + (uint32_t)((grp % NACC) * 256);
 #pragma unroll
-                for (int m = 0; m < G; ++m) mma(d, a_lo + (m & 3) * 2, b_lo + (m & 3) * 2, idesc);
+                for (int m = 0; m < G; ++m) {
+                    if (cat && (m & 1)) mma(d + 96 + cat_off, a_lo + (m & 3) * 2, b_lo + (m & 3) * 2, idesc96);
+                    else mma(d, a_lo + (m & 3) * 2, b_lo + (m & 3) * 2, idesc);
+                }
 #pragma unroll
                 for (int w = 0; w < W; ++w) {
                     uint32_t ok;
@@ -118,6 +128,8 @@ int main() {
     printf("# straight-line issue: cycles per tcgen05.mma (cta_group::1, M 128, K 16), no filler, 32 per group\n");
     for (int N : {16, 32, 64, 96, 128, 192, 256})
         printf("N %3d: %6.1f cycles per MMA (math floor %5.1f)\n", N, run<32, 0, 0, 0, 1>(N, d_out), N / 2.0);
+    printf("# concatenated-form pattern, cycles per (N 192 + N 96) pair: correction block inside the wide MMA's columns %6.1f, disjoint columns %6.1f  (96 + 56 = 152 if independent)\n",
+           2 * run<32, 0, 0, 0, 1>(-1, d_out), 2 * run<32, 0, 0, 0, 1>(-2, d_out));
     printf("# cost of instructions between groups; (+x/group) = cycles per group above G x max(64?, N/2) -- see the first table for the true floor\n");
     row<12, 0, 0, 0, 1>(d_out);
     row<12, 8, 0, 0, 1>(d_out);

@@ -68,6 +68,14 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int iters, int alt, int s
         const int nacc = alt ? (512 / N) : 1;
         int since = 0; uint32_t lcg = 1;
         const long long t0 = clock64();
+        if (!alt && !gap_every) {
+            // clean path: straight-line groups of 8, no modulo, no gap test (the general loop below is itself
+            // issue-bound at ~118 cycles per MMA -- see tools/mma_issue_bench.cu)
+            for (int it = 0; it < iters / 2; ++it) {
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) mma<TWO>(tmem, a_lo + (ks & 3) * 2, b_lo + (ks & 3) * 2, idesc);
+            }
+        } else
         for (int it = 0; it < iters; ++it) {
             const uint32_t d = tmem + (uint32_t)((it % nacc) * N);
 #pragma unroll
