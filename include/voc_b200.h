@@ -127,10 +127,13 @@ long long   voc_kernel_launches(void* h);  /* kernels launched by this handle so
  *            runs them as tcgen05 tensor-core tiles on split-fp16 operands with FP32 accumulation;
  *            "simt" is the all-float32 CUDA-core path (the on-device cross-check).
  *          "tc_flags" = experiment switches (bit 0 no tap reuse, bit 1 / 2 force 64- / 32-wide K
- *            chunks, bit 7 no cta_group::2 pairs, bits 8.. = MMAs accumulated in the tensor core per
- *            round-to-nearest flush, default 24)
- *          "graphs" = "1" | "0": replay recurring waves of <= 4 windows as CUDA graphs (batch-1
- *            streaming latency is launch-bound)
+ *            chunks, bit 3 run-time epilogue only, bit 4 no double-length head segments, bit 7 no
+ *            cta_group::2 pairs, bits 8.. = MMAs accumulated in the tensor core per round-to-nearest
+ *            flush, default 24)
+ *          "graphs" = "1" | "0": replay recurring waves of <= "graph_max_wave" (default 4) windows as
+ *            CUDA graphs (batch-1 streaming latency is launch-bound)
+ *          "front_wave" = windows per launch of the stages before the decoder blocks (codebook sum,
+ *            transformer, up-sampling); default min(256, 8 * wave); set before voc_finalize
  *          "profile" = "0" | "1", "debug" = "0" | "1"                                      */
 int         voc_set_option(void* h, const char* key, const char* value);
 /* The handle's own stream (cudaStream_t as void*), so a caller can bracket the host entry

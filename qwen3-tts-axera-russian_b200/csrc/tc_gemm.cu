@@ -262,10 +262,6 @@ __device__ __forceinline__ void mma2_f16_ss_acc(uint32_t tmem_d, uint32_t desc_a
         ::"r"(tmem_d), "r"(desc_a_lo), "r"(desc_b_lo), "r"(desc_hi), "r"(idesc) : "memory");
 }
 // completion of the pair's MMAs arrives on the barrier at the same offset in both CTAs
-__device__ __forceinline__ void mma2_commit_both(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
-}
 // 256-bit global accesses (sm_100): one full 32-byte sector per lane per instruction
 __device__ __forceinline__ void ldg256(const void* p, float (&r)[8]) {
     asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -288,9 +284,6 @@ __device__ __forceinline__ bool elect_one() {
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(pred));
     return pred != 0;
-}
-__device__ __forceinline__ void mma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile(
@@ -885,8 +878,7 @@ cudaError_t launch_inst2(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;

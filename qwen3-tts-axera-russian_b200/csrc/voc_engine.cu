@@ -162,6 +162,7 @@ struct Engine {
     struct WaveGraph { cudaGraphExec_t exec = nullptr; long long launches = 0; int seen = 0; };
     std::map<std::tuple<const void*, const void*, int, int, int, int, int, int>, WaveGraph> graphs;
     bool use_graphs = true;
+    int front_wave = 0;                        // windows per launch of the stages before the decoder blocks (>= wave)
     int graph_max_wave = 4;                    // waves of at most this many windows are replayed as graphs
     bool finalized = false;
     int gemm_mode = 0;          // 0 auto (= tc), 1 simt (FP32 CUDA cores), 2 tc (tcgen05, split fp16)
@@ -525,7 +526,11 @@ static int engine_finalize(Engine* E) {
     E->raw.clear();
 
     // ---- activation pools
-    const int W = E->wave, T = c.chunk_frames;
+    // Two wave sizes: the decoder blocks (gigabytes of activations per launch) run `wave` windows at a time, the
+    // stages before them (codebook sum, transformer, up-sampling: 10 MB per window, ~100 small launches) run
+    // `front_wave` windows at a time so that their GEMMs fill the machine.
+    if (E->front_wave < E->wave) E->front_wave = std::max(E->wave, std::min(256, 8 * E->wave));
+    const int W = E->front_wave, T = c.chunk_frames;
     int Tup = T; for (int r : c.upsampling_ratios) Tup *= r;
     size_t off = 0;
     auto carve = [&](size_t n) { size_t o = off; off += (n + 63) / 64 * 64; return o; };
@@ -555,8 +560,8 @@ static int engine_finalize(Engine* E) {
     }
     E->big_elems = mx;
     for (int i = 0; i < 4; ++i) {
-        CK(cudaMalloc(&E->big[i].p, mx * W * sizeof(float))); E->big[i].n = mx * W;
-        E->cap[E->big[i].p] = mx * W;
+        CK(cudaMalloc(&E->big[i].p, mx * E->wave * sizeof(float))); E->big[i].n = mx * E->wave;
+        E->cap[E->big[i].p] = mx * E->wave;
     }
     CK(cudaMalloc(&E->d_err, sizeof(int)));
 
@@ -577,10 +582,11 @@ static int engine_finalize(Engine* E) {
 }
 
 // --------------------------------------------------------------------------------------
-// one wave: windows [w_begin, w_begin + nw) of a request -> chunk_out[nw][Lc]
+// one front wave: windows [w_begin, w_begin + nw) of a request (nw <= front_wave) through the codebook sum,
+// pre-conv, transformer and up-sampling stages -> *x_out [nw][*L_out][latent] in operand format
 // --------------------------------------------------------------------------------------
-static int run_wave(Engine* E, const long long* d_codes, int n_frames, int win_step, int w_begin, int nw,
-                    float* chunk_out, cudaStream_t st, const int* d_wmeta = nullptr) {
+static int run_front(Engine* E, const long long* d_codes, int n_frames, int win_step, int w_begin, int nw,
+                     cudaStream_t st, const int* d_wmeta, float** x_out, int* L_out) {
     const Cfg& c = E->cfg;
     const int T = c.chunk_frames;
 #define KLAUNCH(tag, flops, bytes, call) do { ProfScope _ps(E, st, tag, flops, bytes); CK(call); } while (0)
@@ -649,10 +655,28 @@ static int run_wave(Engine* E, const long long* d_codes, int n_frames, int win_s
         char nm[32]; snprintf(nm, sizeof nm, "up%d", (int)u);
         if (int r2 = dbg_capture(E, nm, act(E, x), (size_t)nw * L * C, st)) return r2;
     }
+    *x_out = x; *L_out = L;
+    return VOC_OK;
+}
+
+// an operand tensor `elems` elements into a pool buffer (both planes move together)
+static VocAct act_at(Engine* E, float* base, size_t elems) {
+    VocAct a = act(E, base);
+    if (a.f) a.f += elems;
+    if (a.hi) { a.hi += elems; a.lo += elems; }
+    return a;
+}
+
+// --------------------------------------------------------------------------------------
+// one wave of the decoder: windows [x_win0, x_win0 + nw) of a front wave's output (nw <= wave) through conv-in,
+// the decoder blocks and the head -> chunk_out[nw][Lc]
+// --------------------------------------------------------------------------------------
+static int run_back(Engine* E, float* x, int x_win0, int L, int nw, float* chunk_out, cudaStream_t st) {
+    const Cfg& c = E->cfg;
     // K4: decoder conv-in, emits only Snake_0(conv_in(x)) -- the operand of block 0
     float* bX = E->big[0].p; float* bS = E->big[1].p; float* bT = E->big[2].p; float* bX2 = E->big[3].p;
     {
-        TapGemmParams p = gp(E->conv_in, act(E, x), (long long)L * c.latent_dim, L, 0, L, nw);
+        TapGemmParams p = gp(E->conv_in, act_at(E, x, (size_t)x_win0 * L * c.latent_dim), (long long)L * c.latent_dim, L, 0, L, nw);
         setS(p, act(E, bS), &E->blocks[0].s_in);
         if (E->debug) setY(p, bX);
         GEMM("conv_in", p);
@@ -710,6 +734,18 @@ static int run_wave(Engine* E, const long long* d_codes, int n_frames, int win_s
     return VOC_OK;
 }
 
+// windows [w_begin, w_begin + nw) of a request (nw <= front_wave) -> chunk_out[nw][Lc]
+static int run_wave(Engine* E, const long long* d_codes, int n_frames, int win_step, int w_begin, int nw,
+                    float* chunk_out, cudaStream_t st, const int* d_wmeta = nullptr) {
+    float* x = nullptr; int L = 0;
+    if (int r = run_front(E, d_codes, n_frames, win_step, w_begin, nw, st, d_wmeta, &x, &L)) return r;
+    const long long Lc = E->cfg.chunk_samples();
+    for (int s = 0; s < nw; s += E->wave) {
+        if (int r = run_back(E, x, s, L, std::min(E->wave, nw - s), chunk_out + (long long)s * Lc, st)) return r;
+    }
+    return VOC_OK;
+}
+
 static int check_codes_flag(Engine* E, cudaStream_t st) {
     int flag = 0;
     CK(cudaMemcpyAsync(&flag, E->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -724,8 +760,9 @@ static int check_codes_flag(Engine* E, cudaStream_t st) {
 static int run_windows(Engine* E, const long long* d_codes, int n_frames, int win_step, int w0, int w1,
                        float* chunk_out, cudaStream_t st) {
     const long long Lc = E->cfg.chunk_samples();
-    for (int w = w0; w < w1; w += E->wave) {
-        const int nw = std::min(E->wave, w1 - w);
+    const int fw = E->debug ? E->wave : E->front_wave;      // debug captures describe one decoder wave
+    for (int w = w0; w < w1; w += fw) {
+        const int nw = std::min(fw, w1 - w);
         float* out = chunk_out + (long long)(w - w0) * Lc;
         // Small waves are launch-bound, so a wave that recurs with the same buffers (the streaming client's
         // one-window requests through the host entry points) is replayed as a CUDA graph: first sight runs
@@ -946,8 +983,9 @@ static int synth_batch(Engine* E, const long long* d_codes, const int* lens, int
         while (g1 < nwin && smeta[(size_t)g1 * 6 + 2]) ++g1;
         const int ng = g1 - g0;
         if (int r = ensure_buf(E, E->chunks, (size_t)ng * Lc)) return r;
-        for (int w = g0; w < g1; w += E->wave) {
-            const int nw = std::min(E->wave, g1 - w);
+        const int fw = E->debug ? E->wave : E->front_wave;
+        for (int w = g0; w < g1; w += fw) {
+            const int nw = std::min(fw, g1 - w);
             if (int r = run_wave(E, d_codes, (int)frame0, 0, w, nw, E->chunks.p + (long long)(w - g0) * Lc, st, d_wmeta)) return r;
         }
         ProfScope ps(E, st, "stitch", 0.0, 0.0);
@@ -998,6 +1036,7 @@ void* voc_create(const char* cfg_json, int device, int wave) {
     if (const char* g = getenv("VOC_GEMM")) E->gemm_mode = !strcmp(g, "simt") ? 1 : !strcmp(g, "tc") ? 2 : 0;
     if (const char* f = getenv("VOC_TC_FLAGS")) E->tc_flags = atoi(f);
     if (const char* f = getenv("VOC_GRAPH_MAX_WAVE")) E->graph_max_wave = atoi(f);
+    if (const char* f = getenv("VOC_FRONT_WAVE")) E->front_wave = atoi(f);
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking) != cudaSuccess) {
         g_create_error = "cudaSetDevice / stream creation failed";
         fprintf(stderr, "voc_create: %s\n", g_create_error.c_str());
@@ -1329,6 +1368,10 @@ int voc_set_option(void* h, const char* key, const char* value) {
     if (k == "tc_flags") { E->tc_flags = atoi(v.c_str()); return VOC_OK; }
     if (k == "graphs") { E->use_graphs = (v == "1"); return VOC_OK; }
     if (k == "graph_max_wave") { E->graph_max_wave = atoi(v.c_str()); return VOC_OK; }
+    if (k == "front_wave") {
+        if (E->finalized) return fail(E, VOC_E_INVALID, "front_wave must be set before the weights are finalized");
+        E->front_wave = atoi(v.c_str()); return VOC_OK;
+    }
     if (k == "profile") { E->profile = (v == "1"); return VOC_OK; }
     if (k == "debug") { E->debug = (v == "1"); if (!E->debug) E->dbg.clear(); return VOC_OK; }
     return fail(E, VOC_E_INVALID, "unknown option " + k);
