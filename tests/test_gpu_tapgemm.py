@@ -49,6 +49,11 @@ CASES = [
     ("convt_trim_both",  2, 100,  192, 288,  99, 1, [0, -1]),
     ("convt_trim_right", 2, 100,   64, 320, 100, 0, [0, -1]),
     ("tiny_k16",         1, 150,   16,  32, 150, 0, [-2, -1, 0]),
+    # K that is not a multiple of the 64-wide chunk nor of the 16-wide k-step: chunks of equal depth (48 + 24 -> 3 + 2
+    # k-steps, the second box starting at column 48), the last k-step half zero-filled by TMA
+    ("linear_k72",       1, 130,   72,  64, 130, 0, [0]),
+    ("conv3_k40",        2, 140,   40,  96, 140, 0, [-4, -2, 0]),
+    ("conv7_k160",       1, 300,  160, 192, 300, 0, [-6, -5, -4, -3, -2, -1, 0]),
     # cta_group::2 pair mode (BN = 192 with taps*K >= 1024; BN = 96 with taps*K >= 512): odd numbers of M tiles
     # (the pair's second CTA gets an all-padding tile), several windows, K tail (K = 96 in 64-wide chunks)
     ("pair_conv7_c192",  3, 650,  192, 192, 650, 0, [-54, -45, -36, -27, -18, -9, 0]),
