@@ -372,8 +372,10 @@ __global__ void __launch_bounds__(64)
 attention_kernel(const float* __restrict__ qkv, VocAct out, int T, int heads,
                  const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, int window) {
     constexpr int H2 = HD / 2;
-    __shared__ float Ks[64][HD + 1];
-    __shared__ float Vs[64][HD + 1];
+    // every lane of a warp reads the same key row at the same time (a broadcast), so rows need no padding and
+    // are read four floats per shared-memory instruction (the loops below are otherwise one LDS per FMA)
+    __shared__ __align__(16) float Ks[64][HD];
+    __shared__ __align__(16) float Vs[64][HD];
     const int b = blockIdx.z, hh = blockIdx.y, q0 = blockIdx.x * 64;
     const int tid = threadIdx.x;
     const int A = heads * HD;
@@ -427,7 +429,11 @@ attention_kernel(const float* __restrict__ qkv, VocAct out, int T, int heads,
             if (kj > qi || kj <= qi - window) continue;
             float s = 0.f;
 #pragma unroll
-            for (int d = 0; d < HD; ++d) s = fmaf(q[d], Ks[j][d], s);
+            for (int d = 0; d < HD; d += 4) {
+                const float4 k4 = *reinterpret_cast<const float4*>(&Ks[j][d]);
+                s = fmaf(q[d], k4.x, s); s = fmaf(q[d + 1], k4.y, s);
+                s = fmaf(q[d + 2], k4.z, s); s = fmaf(q[d + 3], k4.w, s);
+            }
             s *= scaling;
             if (s > mx) {
                 const float corr = expf(mx - s);        // exp(-inf) = 0 on first key
@@ -439,7 +445,11 @@ attention_kernel(const float* __restrict__ qkv, VocAct out, int T, int heads,
             const float pexp = expf(s - mx);
             l += pexp;
 #pragma unroll
-            for (int d = 0; d < HD; ++d) o[d] = fmaf(pexp, Vs[j][d], o[d]);
+            for (int d = 0; d < HD; d += 4) {
+                const float4 v4 = *reinterpret_cast<const float4*>(&Vs[j][d]);
+                o[d] = fmaf(pexp, v4.x, o[d]); o[d + 1] = fmaf(pexp, v4.y, o[d + 1]);
+                o[d + 2] = fmaf(pexp, v4.z, o[d + 2]); o[d + 3] = fmaf(pexp, v4.w, o[d + 3]);
+            }
         }
     }
     if (qvalid) {
