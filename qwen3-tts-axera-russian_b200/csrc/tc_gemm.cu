@@ -11,7 +11,7 @@
 //   * B: weights, two fp16 planes [plane][tap][N][K] of W * 2^wexp (the power-of-two scale keeps the
 //     lo plane out of the fp16 subnormals; the epilogue multiplies by 2^-wexp, which is exact).
 //   * D += Ahi*Bhi + Ahi*Blo + Alo*Bhi, FP32 accumulation (north_star: "accumulation stays FP32"; CPU
-//     emulation 91 dB / 2.5e-5 end to end, oracle/precision_study.py; measured on B200 94-96 dB / 2e-5).
+//     emulation 91 dB / 2.5e-5 end to end, oracle/precision_study.py; measured on B200 92.6 dB / 2.5e-5).
 //
 // Tap reuse: for a k-tap causal conv the 128-row A tile *plus its halo of span = (k-1)*dilation
 // rows* is loaded once per K-chunk ("the time-axis halo staged in shared memory", north_star (3));
@@ -26,8 +26,15 @@
 // 32-byte sector per lane).
 //
 // Accumulation is segmented: the tensor core's FP32 accumulator truncates, so a TMEM buffer holds at most
-// ~24 MMAs into its main accumulator before the epilogue warps add it, round-to-nearest, into registers;
+// ~24 MMAs into its main accumulator (48 for the first two segments of a 3-pass tile, while the epilogue warps
+// are still busy with the previous tile) before the epilogue warps add it, round-to-nearest, into registers;
 // 2 (or 4) TMEM buffers let drains overlap the MMAs of the next segments.
+//
+// The issuing warp is written for throughput of ONE thread: an MMA costs it ~45 cycles, the pipe queues only
+// ~300-450 cycles of work, so everything it touches per stage sits in registers (raw barrier addresses, running
+// descriptors, counters instead of modulos) and the k-step count is a compile-time constant chosen once per A
+// fill.  The epilogue's shape is a template parameter for the layer kinds that matter (EPI_*).
+// Measurements behind these choices: profiles/r1_mma_microbench.txt.
 //
 // Two MMA forms.  3-pass (BN = 192): (hi,lo), (lo,hi), (hi,hi) into one accumulator.  Concatenated
 // (BN <= 128): A_hi x [B_hi; B_lo] as one N = 2*BN MMA plus A_lo x B_hi into a separate correction block.
