@@ -219,6 +219,20 @@ def decode(codes_bqt, W: Weights, cfg, taps: Optional[dict] = None):
     h = tap("pre_conv", causal_conv1d(h, W["pre_conv.w"], W["pre_conv.b"]))
     if cfg.pre_transformer:
         h = tap("xf", pre_transformer(h, W, cfg))
+    return decode_tail(h, W, cfg, taps)
+
+
+def decode_tail(h, W: Weights, cfg, taps: Optional[dict] = None):
+    """Latent ``[B, latent, T]`` (the pre-transformer's output) -> wav ``[B, 1, L]``: up-sampling stages,
+    conv-in, decoder blocks, head, clamp (M4-M9).  The composition the executable sibling runs after
+    its own front end (``Qwen3OmniMoeCode2Wav.forward``: ``for blocks in self.upsample ... for block in
+    self.decoder ... clamp``); pinned as a whole by tests/golden/sibling_tail.npz."""
+
+    def tap(name, v):
+        if taps is not None:
+            taps[name] = v.detach().clone()
+        return v
+
     for u, r in enumerate(cfg.upsampling_ratios):
         p = f"up.{u}."
         h = causal_transconv1d(h, W[p + "convt.w"], W[p + "convt.b"], r, cfg.transconv_trim)

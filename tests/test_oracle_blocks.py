@@ -159,3 +159,36 @@ def test_weight_container_roundtrip(pkg, tmp_path):
     assert all(np.array_equal(w[k], w2[k]) for k in w)
     w3 = pkg.init_weights(cfg, 7)
     assert all(np.array_equal(w[k], w3[k]) for k in w)           # deterministic in the seed
+
+
+def test_sibling_whole_tail_composition():
+    """Everything after the pre-transformer as ONE chain -- up-sampling stages, conv-in, the four decoder blocks
+    with the production strides, head Snake + conv, clamp -- against the executable sibling's own forward
+    (tests/golden/sibling_tail.npz; generator: make_sibling_tail_golden.py).  Pins the oracle's composition:
+    block order, Snake placement, the transposed-conv trim carried from block to block, the clamp."""
+    Gt = np.load(os.path.join(os.path.dirname(__file__), "golden", "sibling_tail.npz"))
+
+    class TailCfg(Cfg):
+        upsampling_ratios = (2, 2)
+        upsample_rates = (8, 5, 4, 3)
+        transconv_trim = "both"
+        convnext = True
+
+    names = [k for k in Gt.files if k not in ("h", "wav", "wav_unclamped")]
+    W = VO.Weights({k: Gt[k] for k in names})
+    taps = {}
+    with torch.no_grad():
+        wav = VO.decode_tail(torch.from_numpy(Gt["h"]), W, TailCfg, taps)
+    ref = Gt["wav"]
+    assert tuple(wav.shape) == ref.shape == (2, 1, 5205)            # ((((3*4 - 1)*8 - 1)*5 - 1)*4 - 1)*3
+    err = float(np.abs(wav.numpy() - ref).max())
+    assert err < 5e-5, err
+    # the clamp is exercised (about 4 % of the samples) and placed last
+    assert 0.01 < float((np.abs(Gt["wav_unclamped"]) > 1).mean()) < 0.2
+    assert float(np.abs(wav.numpy()).max()) == 1.0
+    # float64 evaluation of the same chain agrees with the sibling's float32 to its float32 round-off
+    # (intermediate activations of this random model reach rms 15)
+    W64 = VO.Weights({k: Gt[k] for k in names}, torch.float64)
+    with torch.no_grad():
+        wav64 = VO.decode_tail(torch.from_numpy(Gt["h"]).double(), W64, TailCfg)
+    assert float(np.abs(wav64.numpy() - ref).max()) < 2e-4
