@@ -47,3 +47,44 @@ def reference_server_with(mod, chunk_fn, max_tokens=64, socket_path="/tmp/unused
             return chunk_fn(padded)
 
     return Fake()
+
+
+def sibling_model_case(pkg):
+    """The small random model of tests/golden/sibling_model.npz (``transformers`` ``Qwen3OmniMoeCode2Wav`` after its
+    code embedding: pre-transformer + up-sampling + decoder + head + clamp) as a VocoderConfig + weight dict whose front
+    end is the identity: codebook 0 holds the golden latent frames, the other codebooks are zero, unit out-projections,
+    a pre-conv whose current-frame tap is the unit matrix, unit transformer in/out projections.
+    Returns (cfg, weights, codes [2, 12, 16], reference wav [2, L])."""
+    import os
+
+    import numpy as np
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "sibling_model.npz"))
+    H, T = 32, 12
+    cfg = pkg.VocoderConfig(codebook_size=32, codebook_dim=H, rvq_dim=H, latent_dim=H, num_quantizers=16, num_semantic=1,
+                            decoder_dim=64, chunk_frames=T, xf_hidden=H, xf_inter=48, xf_layers=2, xf_heads=2,
+                            xf_head_dim=16, sliding_window=5)
+    w = pkg.init_weights(cfg, 0)
+    for k in G.files:
+        if k in w:
+            assert w[k].shape == G[k].shape, (k, w[k].shape, G[k].shape)
+            w[k] = np.ascontiguousarray(G[k], dtype=np.float32)
+    hidden = G["hidden"]                                    # [2, T, H]
+    cb0 = np.zeros((32, H), np.float32)
+    codes = np.zeros((2, T, 16), np.int64)
+    for b in range(2):
+        for t in range(T):
+            cb0[T * b + t] = hidden[b, t]
+            codes[b, t, 0] = T * b + t
+    w["rvq.codebook.0"] = cb0
+    for q in range(1, 16):
+        w[f"rvq.codebook.{q}"] = np.zeros((32, H), np.float32)
+    eye = np.eye(H, dtype=np.float32)
+    w["rvq.proj_sem.w"] = eye.copy()
+    w["rvq.proj_ac.w"] = eye.copy()
+    pc = np.zeros((H, H, 3), np.float32)
+    pc[:, :, 2] = eye                                       # tap k-1 of a causal conv is the current frame
+    w["pre_conv.w"] = pc
+    w["pre_conv.b"] = np.zeros(H, np.float32)
+    w["xf.in_proj.w"] = eye.copy(); w["xf.in_proj.b"] = np.zeros(H, np.float32)
+    w["xf.out_proj.w"] = eye.copy(); w["xf.out_proj.b"] = np.zeros(H, np.float32)
+    return cfg, w, codes, G["wav"][:, 0, :], G

@@ -241,3 +241,20 @@ def test_cuda_path_matches_the_sibling_forward_after_the_front_end(pkg, backend)
         # this random model's activations reach rms 15 inside, so the absolute gate is relative to that scale
         assert snr > 60.0 and mx < 2e-4, (gemm, snr, mx)
         assert float(np.abs(got).max()) == 1.0              # the clamp
+
+
+def test_cuda_path_matches_the_sibling_model_after_the_code_embedding(pkg, backend):
+    """As above, with the pre-transformer included: the CUDA path on the small random model of
+    tests/golden/sibling_model.npz (2 transformer layers with RoPE, sliding-window causal attention, LayerScale and
+    SwiGLU, then the whole decoder) against the float32 output of ``Qwen3OmniMoeCode2Wav`` itself -- M3 to M9 in one
+    forward, 22 485 samples per window from 12 latent frames."""
+    from helpers import sibling_model_case
+    cfg, w, codes, ref, _ = sibling_model_case(pkg)
+    for gemm in ("auto", "simt"):
+        voc = backend.Vocoder(cfg, w, wave=2)
+        voc.set_option("gemm", gemm)
+        got = voc.infer_chunks(codes)
+        assert got.shape == ref.shape
+        snr, mx = _report(f"sibling-model/{gemm}", ref, got)
+        assert snr > 60.0 and mx < 3e-4, (gemm, snr, mx)
+        assert float(np.abs(got).max()) == 1.0              # the clamp

@@ -192,3 +192,22 @@ def test_sibling_whole_tail_composition():
     with torch.no_grad():
         wav64 = VO.decode_tail(torch.from_numpy(Gt["h"]).double(), W64, TailCfg)
     assert float(np.abs(wav64.numpy() - ref).max()) < 2e-4
+
+
+def test_sibling_whole_model_after_the_code_embedding():
+    """Pre-transformer + up-sampling + decoder + head + clamp as ONE forward against the executable sibling
+    (tests/golden/sibling_model.npz; generator: make_sibling_model_golden.py), through the oracle's public
+    ``forward`` with an identity front end (tests/helpers.py::sibling_model_case)."""
+    import importlib
+
+    from helpers import sibling_model_case
+    pkg = importlib.import_module("qwen3-tts-axera-russian_b200")
+    cfg, w, codes, ref, Gm = sibling_model_case(pkg)
+    taps = {}
+    out, lengths = VO.forward(codes, VO.Weights(w), cfg, taps)
+    assert tuple(out.shape) == ref.shape == (2, 22485)
+    # the transformer alone, then the whole chain
+    close(taps["xf"].permute(0, 2, 1), Gm["xf_out"], 5e-5)
+    err = float(np.abs(out.numpy() - ref).max())
+    assert err < 1e-4, err
+    assert 0.02 < float((np.abs(Gm["wav_unclamped"]) > 1).mean()) < 0.2 and float(np.abs(out.numpy()).max()) == 1.0
