@@ -17,7 +17,9 @@ decoder with explicit formulas.  What *is* pinned:
     non-reference evidence).
   * the composition of M4-M9 -> ``decode_tail`` against that sibling's whole forward after its front end
     (``tests/golden/sibling_tail.npz``, ``tests/golden/make_sibling_tail_golden.py``), and with the
-    pre-transformer included, M3-M9 (``tests/golden/sibling_model.npz``, ``make_sibling_model_golden.py``).
+    pre-transformer included, M3-M9 (``tests/golden/sibling_model.npz``, ``make_sibling_model_golden.py``);
+    at production dimensions against the sibling executed live with the same random weights
+    (``tests/test_oracle_blocks.py::test_production_size_oracle_matches_the_sibling_run_live``: 7e-6).
 
 All functions take ``x`` as ``[B, C, L]`` (torch layout) and a dict of named weights
 (layouts documented in ``weights.py``) and are dtype-generic (float32 = the stand-in for

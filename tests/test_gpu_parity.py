@@ -258,3 +258,47 @@ def test_cuda_path_matches_the_sibling_model_after_the_code_embedding(pkg, backe
         snr, mx = _report(f"sibling-model/{gemm}", ref, got)
         assert snr > 60.0 and mx < 3e-4, (gemm, snr, mx)
         assert float(np.abs(got).max()) == 1.0              # the clamp
+
+
+def test_production_size_decoder_matches_the_sibling_run_live(pkg, backend):
+    """Production dimensions (latent 1024, decoder 1536 -> 96 channels, strides 8/5/4/3, 64 frames -> 122 325 samples;
+    the sibling's own transformer shape: 8 layers, hidden 1024, 16 x 64 heads, SwiGLU 3072): the CUDA path against
+    ``transformers``' ``Qwen3OmniMoeCode2Wav`` EXECUTED HERE on the CPU with the same variance-preserving random
+    weights (copied into the torch module through tests/helpers.py::sibling_param_pairs).  Needs no golden file;
+    skipped where ``transformers`` has no such model."""
+    torch = pytest.importorskip("torch")
+    try:
+        import transformers.models.qwen3_omni_moe.modeling_qwen3_omni_moe as M
+        from transformers.models.qwen3_omni_moe.configuration_qwen3_omni_moe import Qwen3OmniMoeCode2WavConfig
+    except Exception as e:                                   # pragma: no cover
+        pytest.skip(f"no sibling implementation in this image: {e}")
+    from helpers import identity_front, sibling_param_pairs
+    H, T = 1024, 64
+    cfg = pkg.VocoderConfig(codebook_size=128, codebook_dim=H, rvq_dim=H, latent_dim=H, xf_hidden=H, xf_inter=3072,
+                            xf_layers=8, xf_heads=16, xf_head_dim=64)
+    w = pkg.init_weights(cfg, 11)
+    hcfg = Qwen3OmniMoeCode2WavConfig()                      # the published defaults = the production decoder
+    assert (hcfg.hidden_size, hcfg.decoder_dim, tuple(hcfg.upsample_rates), tuple(hcfg.upsampling_ratios)) == \
+           (H, cfg.decoder_dim, cfg.upsample_rates, cfg.upsampling_ratios)
+    hcfg._attn_implementation = "eager"
+    torch.manual_seed(0)
+    with torch.no_grad():
+        m = M.Qwen3OmniMoeCode2Wav(hcfg).eval()
+        for name, p in sibling_param_pairs(m):
+            assert tuple(p.shape) == w[name].shape, (name, tuple(p.shape), w[name].shape)
+            p.copy_(torch.from_numpy(w[name]))
+        rng = np.random.default_rng(5)
+        hidden = rng.standard_normal((1, T, H)).astype(np.float32)
+        x = m.pre_transformer(inputs_embeds=torch.from_numpy(hidden)).last_hidden_state.permute(0, 2, 1)
+        for blocks in m.upsample:
+            for blk in blocks:
+                x = blk(x)
+        for blk in m.decoder:
+            x = blk(x)
+        ref = x.clamp(min=-1, max=1)[:, 0, :].numpy()
+    codes = identity_front(w, cfg, hidden)
+    voc = backend.Vocoder(cfg, w, wave=1)
+    got = voc.infer_chunks(codes)
+    assert got.shape == ref.shape == (1, 122325)
+    snr, mx = _report("sibling-live/production-size", ref, got)
+    assert snr > 60.0 and mx < 1e-4, (snr, mx)

@@ -211,3 +211,41 @@ def test_sibling_whole_model_after_the_code_embedding():
     err = float(np.abs(out.numpy() - ref).max())
     assert err < 1e-4, err
     assert 0.02 < float((np.abs(Gm["wav_unclamped"]) > 1).mean()) < 0.2 and float(np.abs(out.numpy()).max()) == 1.0
+
+
+def test_production_size_oracle_matches_the_sibling_run_live():
+    """Production dimensions (latent 1024, decoder 1536 -> 96 channels, 64 frames -> 122 325 samples; the sibling's
+    transformer shape): the oracle's public ``forward`` with an identity front end against ``transformers``'
+    ``Qwen3OmniMoeCode2Wav`` executed here with the same random weights.  No golden file; ~15 s of CPU."""
+    import importlib
+    try:
+        import transformers.models.qwen3_omni_moe.modeling_qwen3_omni_moe as M
+        from transformers.models.qwen3_omni_moe.configuration_qwen3_omni_moe import Qwen3OmniMoeCode2WavConfig
+    except Exception as e:                                   # pragma: no cover
+        pytest.skip(f"no sibling implementation in this image: {e}")
+    from helpers import identity_front, sibling_param_pairs
+    pkg = importlib.import_module("qwen3-tts-axera-russian_b200")
+    H, T_ = 1024, 64
+    cfg = pkg.VocoderConfig(codebook_size=128, codebook_dim=H, rvq_dim=H, latent_dim=H, xf_hidden=H, xf_inter=3072,
+                            xf_layers=8, xf_heads=16, xf_head_dim=64)
+    w = pkg.init_weights(cfg, 11)
+    hcfg = Qwen3OmniMoeCode2WavConfig()
+    hcfg._attn_implementation = "eager"
+    with torch.no_grad():
+        m = M.Qwen3OmniMoeCode2Wav(hcfg).eval()
+        for name, p in sibling_param_pairs(m):
+            assert tuple(p.shape) == w[name].shape, name
+            p.copy_(torch.from_numpy(w[name]))
+        hidden = np.random.default_rng(5).standard_normal((1, T_, H)).astype(np.float32)
+        x = m.pre_transformer(inputs_embeds=torch.from_numpy(hidden)).last_hidden_state.permute(0, 2, 1)
+        for blocks in m.upsample:
+            for blk in blocks:
+                x = blk(x)
+        for blk in m.decoder:
+            x = blk(x)
+        ref = x.clamp(min=-1, max=1)[:, 0, :].numpy()
+    codes = identity_front(w, cfg, hidden)
+    out, lengths = VO.forward(codes, VO.Weights(w), cfg)
+    assert tuple(out.shape) == ref.shape == (1, 122325)
+    err = float(np.abs(out.numpy() - ref).max())
+    assert err < 5e-5, err
