@@ -5,6 +5,11 @@
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/mma_microbench tools/mma_microbench.cu && /tmp/mma_microbench
 //
+// NOTE: only the "same-accumulator" columns (a straight-line loop of 8) measure the pipe.  The general loop
+// behind the other columns and the gap / per-stage-cost rows carries a run-time modulo and tests, which makes the
+// issuing thread itself the limit (~118 cycles per MMA at every N) -- the mistake the real kernel was making too.
+// tools/mma_issue_bench.cu is the clean version of those experiments; this file is kept for its cta_group::2 rows.
+//
 // Bring-up instrument (run by hand on a B200); results are recorded in profiles/r1_mma_microbench.txt.
 #include <cuda_runtime.h>
 #include <cstdint>
