@@ -123,8 +123,15 @@ int voc_fade_tables(int ov, float* fade_out, float* fade_in);
 /* ---- diagnostics ---------------------------------------------------------------------*/
 const char* voc_last_error(void* h);       /* NULL handle: error of the last failed voc_create */
 long long   voc_kernel_launches(void* h);  /* kernels launched by this handle so far            */
-/* Options: "gemm" = "auto" | "simt" | "tc": kernel family of the dense layers.  "tc" (= "auto")
- *            runs them as tcgen05 tensor-core tiles on split-fp16 operands with FP32 accumulation;
+/* Request-path launches of a dense layer that did NOT run on the tcgen05 kernel (possible only with
+ * gemm = "auto" on architectures whose channel counts the tensor-core tiles do not take; with
+ * gemm = "tc" such a layer is an error, VOC_E_INVALID).  0 on the production architecture: asserted by
+ * tests/test_gpu_parity.py and reported by bench.py.  No reference counterpart (ORT has one CPU EP). */
+long long   voc_simt_launches(void* h);
+/* Options: "gemm" = "auto" | "simt" | "tc": kernel family of the dense layers.  "tc" runs them as tcgen05
+ *            tensor-core tiles on split-fp16 operands with FP32 accumulation and FAILS (VOC_E_INVALID) on a
+ *            layer shape that kernel does not take; "auto" does the same but lets such a layer (only tiny
+ *            test architectures have one) run on the CUDA-core kernel, counted by voc_simt_launches;
  *            "simt" is the all-float32 CUDA-core path (the on-device cross-check).
  *          "tc_flags" = experiment switches (bit 0 no tap reuse, bit 1 / 2 force 64- / 32-wide K
  *            chunks, bit 3 run-time epilogue only, bit 4 no double-length head segments, bit 7 no

@@ -54,6 +54,7 @@ SIGNATURES = {
     "voc_fade_tables": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
     "voc_last_error": (C.c_char_p, [C.c_void_p]),
     "voc_kernel_launches": (C.c_longlong, [C.c_void_p]),
+    "voc_simt_launches": (C.c_longlong, [C.c_void_p]),
     "voc_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
     "voc_stream": (C.c_void_p, [C.c_void_p]),
     "voc_profile_report": (C.c_longlong, [C.c_void_p, C.c_void_p, C.c_longlong]),
@@ -208,6 +209,11 @@ class Vocoder:
     @property
     def kernel_launches(self) -> int:
         return self.lib.voc_kernel_launches(self._h)
+
+    @property
+    def simt_launches(self) -> int:
+        """Request-path dense-layer launches that left the tcgen05 kernel family (0 on the production model)."""
+        return self.lib.voc_simt_launches(self._h)
 
     def out_samples(self, n_tokens: int) -> int:
         return self.lib.voc_out_samples(self._h, n_tokens)

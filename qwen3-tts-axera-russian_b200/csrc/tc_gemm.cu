@@ -50,6 +50,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -859,16 +860,26 @@ int pick_bn(int N) {
 }
 
 constexpr int SMEM_BUDGET = 232448 - 1024 - 5120;   // opt-in maximum minus alignment slack and static smem
+constexpr int VOC_MAX_DEVICES = 64;
+inline int current_device() {
+    int d = -1;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= VOC_MAX_DEVICES) return -1;
+    return d;
+}
 
 template <int BN, int BK, int EPI = EPI_GENERIC>
 cudaError_t launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, int grid, size_t smem,
                         cudaStream_t st) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    // the shared-memory opt-in is a per-device attribute: one flag per device ordinal (a process may hold
+    // handles on several GPUs)
+    static std::atomic<bool> attr_done[VOC_MAX_DEVICES];
+    const int dev = current_device();
+    if (dev < 0) return cudaErrorInvalidDevice;
+    if (!attr_done[dev].load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, BK, false, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              SMEM_BUDGET + 1024);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_done[dev].store(true, std::memory_order_release);
     }
     tapgemm_tc_kernel<BN, BK, false, EPI><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmB, a);
     return cudaGetLastError();
@@ -878,12 +889,14 @@ cudaError_t launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const Tc
 template <int BN, int BK, int EPI = EPI_GENERIC>
 cudaError_t launch_inst2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB2, const TcArgs& a,
                          int grid, size_t smem, cudaStream_t st) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static std::atomic<bool> attr_done[VOC_MAX_DEVICES];
+    const int dev = current_device();
+    if (dev < 0) return cudaErrorInvalidDevice;
+    if (!attr_done[dev].load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, BK, true, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              SMEM_BUDGET + 1024);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_done[dev].store(true, std::memory_order_release);
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;

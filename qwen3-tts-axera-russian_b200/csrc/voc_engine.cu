@@ -16,6 +16,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <set>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -158,10 +159,14 @@ struct Engine {
     cudaStream_t stream = nullptr;
     std::string err;
     long long launches = 0;
+    long long simt_launches = 0;                // request-path launches that left the tcgen05 family (gemm = "auto")
+    std::set<std::string> simt_warned;
     // CUDA graphs of small waves (the batch-1 streaming case is launch-bound: ~120 tiny kernels per window)
-    struct WaveGraph { cudaGraphExec_t exec = nullptr; long long launches = 0; int seen = 0; };
+    struct WaveGraph { cudaGraphExec_t exec = nullptr; long long launches = 0; int seen = 0; long long last_use = 0; };
     std::map<std::tuple<const void*, const void*, int, int, int, int, int, int>, WaveGraph> graphs;
     bool use_graphs = true;
+    int graph_cache_max = 64;  long long graph_clock = 0;
+    void drop_graphs() { for (auto& g : graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec); graphs.clear(); }
     int front_wave = 0;                        // windows per launch of the stages before the decoder blocks (>= wave)
     int graph_max_wave = 4;                    // waves of at most this many windows are replayed as graphs
     bool finalized = false;
@@ -363,7 +368,7 @@ static float* upload_named(Engine* E, const std::string& name, size_t n) {
     return upload(E, *v);
 }
 
-static cudaError_t run_gemm(Engine* E, TapGemmParams& p, cudaStream_t st, const char* tag = "gemm.other") {
+static cudaError_t run_gemm(Engine* E, TapGemmParams& p, cudaStream_t st, const char* tag = "gemm.other", bool force_simt = false) {
     const double flops = 2.0 * p.B * (double)p.M * p.N * p.K * p.ntaps;
     // algorithmic bytes: A once, W once, outputs / residual once
     double bytes = 4.0 * ((double)p.B * p.M * p.K + (double)p.ntaps * p.K * p.N);
@@ -371,12 +376,37 @@ static cudaError_t run_gemm(Engine* E, TapGemmParams& p, cudaStream_t st, const 
     if (p.S) bytes += 4.0 * p.B * (double)p.M * p.N;
     if (p.R) bytes += 4.0 * p.B * (double)p.M * p.N;
     ProfScope ps(E, st, tag, flops, bytes);
-    if (E->tc() && voc_tc_eligible(p)) {
-        const cudaError_t e = voc_launch_tapgemm_tc(p, st, E->num_sms, E->tc_flags);
+    if (force_simt || !E->tc()) return voc_launch_tapgemm_simt(p, st);
+    // Tensor-core family.  north_star: "no multi-backend dispatch" -- with gemm = "tc" a shape the tcgen05 kernel
+    // does not take is an error, never a silent change of kernel family.  gemm = "auto" (small test
+    // architectures whose channel counts are not multiples of 32) may use the FP32 CUDA-core kernel for such a
+    // layer; every such launch is counted (voc_simt_launches) and named once on stderr.
+    cudaError_t e = cudaErrorNotSupported;
+    if (voc_tc_eligible(p)) {
+        e = voc_launch_tapgemm_tc(p, st, E->num_sms, E->tc_flags);
         if (e != cudaErrorNotSupported) return e;
         (void)cudaGetLastError();
     }
+    if (E->gemm_mode == 2) {
+        E->err = std::string("layer ") + tag + " (K " + std::to_string(p.K) + ", N " + std::to_string(p.N) + ", taps " +
+                 std::to_string(p.ntaps) + ") is not eligible for the tcgen05 kernel and gemm = \"tc\" forbids another kernel family";
+        return cudaErrorNotSupported;
+    }
+    E->simt_launches++;
+    if (E->simt_warned.insert(tag).second && getenv("VOC_VERBOSE"))
+        fprintf(stderr, "voc_b200: layer %s (K %d, N %d) runs on the FP32 CUDA-core kernel (not tcgen05-eligible)\n", tag, p.K, p.N);
     return voc_launch_tapgemm_simt(p, st);
+}
+
+// run_gemm with the engine's error conventions: a refused shape under gemm = "tc" is the caller's mistake
+// (VOC_E_INVALID, message names the layer), anything else is a CUDA failure
+static int gemm_ck(Engine* E, TapGemmParams& p, cudaStream_t st, const char* tag) {
+    const cudaError_t e = run_gemm(E, p, st, tag);
+    if (e == cudaSuccess) return VOC_OK;
+    if (e == cudaErrorNotSupported && E->gemm_mode == 2) { const std::string m = E->err; return fail(E, VOC_E_INVALID, m); }
+    E->err = std::string("tap-GEMM ") + tag + ": " + cudaGetErrorString(e);
+    fprintf(stderr, "voc_b200: %s\n", E->err.c_str());
+    return VOC_E_CUDA;
 }
 
 // An activation buffer in the format of the current mode: float32 on the CUDA-core path, two
@@ -441,7 +471,9 @@ static int engine_finalize(Engine* E) {
             REQ(cb);
             TapGemmParams p = gp(q < c.num_semantic ? ps : pa, act_f32(cb), 0, c.codebook_size, 0, c.codebook_size, 1);
             setY(p, tables + q * tbl);
-            CK(run_gemm(E, p, E->stream));
+            // weight preparation, once per handle: an exact FP32 fold on the CUDA cores by design (its operand
+            // is the float32 codebook itself), not a request-path launch
+            CK(run_gemm(E, p, E->stream, "finalize.fold", true));
         }
         CK(cudaStreamSynchronize(E->stream));
         E->rvq_tables = tables;
@@ -590,7 +622,7 @@ static int run_front(Engine* E, const long long* d_codes, int n_frames, int win_
     const Cfg& c = E->cfg;
     const int T = c.chunk_frames;
 #define KLAUNCH(tag, flops, bytes, call) do { ProfScope _ps(E, st, tag, flops, bytes); CK(call); } while (0)
-#define GEMM(tag, p) CK(run_gemm(E, p, st, tag))
+#define GEMM(tag, p) do { if (int _r = gemm_ck(E, p, st, tag)) return _r; } while (0)
     // Operand tensors (everything a GEMM reads) are in the mode's operand format -- act(); the
     // residual streams (f_h, the up-sampled x while ConvNeXt needs it, bX) and the tensors the
     // non-GEMM kernels read (f_qkv, f_gu) stay float32.
@@ -774,13 +806,31 @@ static int run_windows(Engine* E, const long long* d_codes, int n_frames, int wi
         }
         const auto key = std::make_tuple((const void*)d_codes, (const void*)out, n_frames, win_step, w, nw,
                                          E->gemm_mode, E->tc_flags);
-        Engine::WaveGraph& G = E->graphs[key];
-        if (G.exec) {
-            CK(cudaGraphLaunch(G.exec, st));
-            E->launches += G.launches;
+        auto git = E->graphs.find(key);
+        if (git != E->graphs.end() && git->second.exec) {
+            git->second.last_use = ++E->graph_clock;
+            CK(cudaGraphLaunch(git->second.exec, st));
+            E->launches += git->second.launches;
             continue;
         }
-        if (G.seen++ == 0 || E->graphs.size() > 64) {
+        if (git == E->graphs.end()) {
+            // first sight runs eagerly (lazy set-up: kernel attributes, tensor maps); the key is remembered so
+            // that the second sight is captured.  The cache is bounded: the least recently used entry goes.
+            if (E->graphs.size() >= (size_t)E->graph_cache_max) {
+                auto lru = E->graphs.begin();
+                for (auto it = E->graphs.begin(); it != E->graphs.end(); ++it)
+                    if (it->second.last_use < lru->second.last_use) lru = it;
+                if (lru->second.exec) cudaGraphExecDestroy(lru->second.exec);
+                E->graphs.erase(lru);
+            }
+            Engine::WaveGraph& N = E->graphs[key];
+            N.seen = 1; N.last_use = ++E->graph_clock;
+            if (int r = run_wave(E, d_codes, n_frames, win_step, w, nw, out, st)) return r;
+            continue;
+        }
+        Engine::WaveGraph& G = git->second;
+        G.last_use = ++E->graph_clock;
+        if (G.seen < 0) {                                 // known not to be capturable
             if (int r = run_wave(E, d_codes, n_frames, win_step, w, nw, out, st)) return r;
             continue;
         }
@@ -869,7 +919,7 @@ static int ensure_i(Engine* E, size_t n) {
 }
 static int ensure_buf(Engine* E, DevBuf& b, size_t n) {
     if (b.n >= n) return VOC_OK;
-    if (b.p) cudaFree(b.p);
+    if (b.p) { CK(cudaStreamSynchronize(E->stream)); E->drop_graphs(); cudaFree(b.p); }   // captured graphs point into it
     b.p = nullptr; b.n = 0;
     CK(cudaMalloc(&b.p, n * sizeof(float))); b.n = n;
     return VOC_OK;
@@ -998,13 +1048,23 @@ static int synth_batch(Engine* E, const long long* d_codes, const int* lens, int
 
 static int ensure_codes(Engine* E, size_t n) {
     if (E->codes_cap >= n) return VOC_OK;
-    if (E->d_codes) cudaFree(E->d_codes);
+    if (E->d_codes) { CK(cudaStreamSynchronize(E->stream)); E->drop_graphs(); cudaFree(E->d_codes); }
     E->d_codes = nullptr; E->codes_cap = 0;
     CK(cudaMalloc(&E->d_codes, n * sizeof(long long))); E->codes_cap = n;
     return VOC_OK;
 }
 
 }  // namespace
+
+// No C++ exception may cross the C ABI (a std::bad_alloc / length_error from a vector or map on these paths would
+// otherwise reach std::terminate inside the server or the ctypes host).
+template <class F>
+static int guarded(void* h, F&& f) {
+    try { return f(); }
+    catch (const std::bad_alloc&) { if (h) ((Engine*)h)->err = "out of host memory"; return VOC_E_NOMEM; }
+    catch (const std::exception& e) { if (h) ((Engine*)h)->err = std::string("internal error: ") + e.what(); return VOC_E_INVALID; }
+    catch (...) { if (h) ((Engine*)h)->err = "internal error"; return VOC_E_INVALID; }
+}
 
 // ======================================================================================
 // C ABI
@@ -1013,7 +1073,7 @@ extern "C" {
 
 int voc_abi_version(void) { return 1; }
 
-void* voc_create(const char* cfg_json, int device, int wave) {
+static void* create_impl(const char* cfg_json, int device, int wave) {
     auto E = std::make_unique<Engine>();
     std::string err;
     if (!cfg_from_json(cfg_json, E->cfg, err)) { g_create_error = err; fprintf(stderr, "voc_create: %s\n", err.c_str()); return nullptr; }
@@ -1045,6 +1105,14 @@ void* voc_create(const char* cfg_json, int device, int wave) {
     return E.release();
 }
 
+void* voc_create(const char* cfg_json, int device, int wave) {
+    try { return create_impl(cfg_json, device, wave); }
+    catch (const std::exception& e) { g_create_error = std::string("voc_create: ") + e.what(); }
+    catch (...) { g_create_error = "voc_create: internal error"; }
+    fprintf(stderr, "%s\n", g_create_error.c_str());
+    return nullptr;
+}
+
 void voc_destroy(void* h) {
     if (!h) return;
     Engine* E = (Engine*)h;
@@ -1057,15 +1125,14 @@ int voc_set_tensor(void* h, const char* name, const float* data, long long n_ele
     Engine* E = (Engine*)h;
     if (!E || !name || !data || n_elem <= 0) return VOC_E_INVALID;
     if (E->finalized) return fail(E, VOC_E_STATE, "voc_set_tensor after voc_finalize");
-    E->raw[name].assign(data, data + n_elem);
-    return VOC_OK;
+    return guarded(h, [&]() -> int { E->raw[name].assign(data, data + n_elem); return VOC_OK; });
 }
 
 int voc_finalize(void* h) {
     Engine* E = (Engine*)h;
     if (!E) return VOC_E_INVALID;
     if (E->finalized) return fail(E, VOC_E_STATE, "already finalized");
-    return engine_finalize(E);
+    return guarded(h, [&]() -> int { return engine_finalize(E); });
 }
 
 // ---- model container (.b200voc = safetensors byte layout, written by weights.py:save_model) -----------
@@ -1137,7 +1204,7 @@ struct JsonCursor {
 };
 }  // namespace
 
-void* voc_create_from_file(const char* path, int device, int wave) {
+static void* create_from_file_impl(const char* path, int device, int wave) {
     auto bad = [&](const std::string& m) -> void* {
         g_create_error = std::string(path ? path : "(null)") + ": " + m;
         fprintf(stderr, "voc_create_from_file: %s\n", g_create_error.c_str());
@@ -1166,7 +1233,18 @@ void* voc_create_from_file(const char* path, int device, int wave) {
             auto it = nums.find("data_offsets");
             if (it == nums.end() || it->second.size() != 2) { c.ok = false; break; }
             if (strs["dtype"] != "F32") { fclose(f); return bad("tensor " + key + " is not F32"); }
-            tensors.push_back({key, {(long long)it->second[0], (long long)it->second[1]}});
+            // offsets are JSON numbers: integral, non-negative, ordered, 4-byte multiples, matching the shape
+            const double a = it->second[0], b = it->second[1];
+            if (!(a >= 0.0) || !(b > a) || b > 9.0e15 || a != std::floor(a) || b != std::floor(b)) { fclose(f); return bad("tensor " + key + ": bad data_offsets"); }
+            long long elems = 1;
+            auto sh = nums.find("shape");
+            if (sh != nums.end()) for (double d : sh->second) {
+                if (!(d >= 0.0) || d != std::floor(d) || d > 4.0e9 || (d > 0 && elems > (1LL << 40) / (long long)d)) { fclose(f); return bad("tensor " + key + ": bad shape"); }
+                elems *= (long long)d;
+            }
+            const long long la = (long long)a, lb = (long long)b;
+            if ((lb - la) % 4 || (sh != nums.end() && elems * 4 != lb - la)) { fclose(f); return bad("tensor " + key + ": data_offsets do not match shape"); }
+            tensors.push_back({key, {la, lb}});
         }
         if (c.eat(',')) continue;
         if (c.eat('}')) break;
@@ -1174,15 +1252,18 @@ void* voc_create_from_file(const char* path, int device, int wave) {
     }
     if (!c.ok) { fclose(f); return bad("malformed header"); }
     if (cfg_json.empty()) { fclose(f); return bad("no voc_config in metadata"); }
+    const long long base = 8 + (long long)hl;
+    long long fsize = 0;
+    if (fseeko(f, 0, SEEK_END) != 0 || (fsize = (long long)ftello(f)) < base) { fclose(f); return bad("cannot size the file"); }
+    for (auto& t : tensors)
+        if (t.second.second > fsize - base) { fclose(f); return bad("tensor " + t.first + " runs past the end of the file"); }
     void* h = voc_create(cfg_json.c_str(), device, wave);
     if (!h) { fclose(f); return nullptr; }
-    const long long base = 8 + (long long)hl;
     std::vector<float> buf;
     for (auto& t : tensors) {
         const long long n = (t.second.second - t.second.first) / 4;
-        if (n <= 0) { fclose(f); voc_destroy(h); return bad("empty tensor " + t.first); }
         buf.resize((size_t)n);
-        if (fseek(f, (long)(base + t.second.first), SEEK_SET) != 0 || fread(buf.data(), 4, (size_t)n, f) != (size_t)n) {
+        if (fseeko(f, (off_t)(base + t.second.first), SEEK_SET) != 0 || fread(buf.data(), 4, (size_t)n, f) != (size_t)n) {
             fclose(f); voc_destroy(h); return bad("truncated tensor " + t.first);
         }
         if (voc_set_tensor(h, t.first.c_str(), buf.data(), n) != VOC_OK) { fclose(f); voc_destroy(h); return bad("voc_set_tensor failed"); }
@@ -1194,6 +1275,14 @@ void* voc_create_from_file(const char* path, int device, int wave) {
         return nullptr;
     }
     return h;
+}
+
+void* voc_create_from_file(const char* path, int device, int wave) {
+    try { return create_from_file_impl(path, device, wave); }
+    catch (const std::exception& e) { g_create_error = std::string("voc_create_from_file: ") + e.what(); }
+    catch (...) { g_create_error = "voc_create_from_file: internal error"; }
+    fprintf(stderr, "%s\n", g_create_error.c_str());
+    return nullptr;
 }
 
 int voc_max_tokens(void* h) { return h ? ((Engine*)h)->cfg.chunk_frames : VOC_E_INVALID; }
@@ -1215,7 +1304,7 @@ int voc_infer_chunks_dev(void* h, const long long* d_codes, int B, float* d_out,
     CK(cudaSetDevice(E->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : E->stream;
     const int T = E->cfg.chunk_frames;
-    return run_windows(E, d_codes, B * T, T, 0, B, d_out, st);
+    return guarded(h, [&]() -> int { return run_windows(E, d_codes, B * T, T, 0, B, d_out, st); });
 }
 
 int voc_infer_chunks(void* h, const long long* codes, int B, float* out) {
@@ -1229,8 +1318,10 @@ int voc_infer_chunks(void* h, const long long* codes, int B, float* out) {
     const size_t nc = (size_t)B * T * 16;
     if (int r = ensure_codes(E, nc)) return r;
     if (int r = ensure_buf(E, E->chunks, (size_t)B * Lc)) return r;
+    // a flag left behind by an unchecked *_dev call must not fail this unrelated request
+    CK(cudaMemsetAsync(E->d_err, 0, sizeof(int), E->stream));
     CK(cudaMemcpyAsync(E->d_codes, codes, nc * sizeof(long long), cudaMemcpyHostToDevice, E->stream));
-    if (int r = run_windows(E, E->d_codes, B * T, T, 0, B, E->chunks.p, E->stream)) return r;
+    if (int r = guarded(h, [&]() -> int { return run_windows(E, E->d_codes, B * T, T, 0, B, E->chunks.p, E->stream); })) return r;
     if (int r = check_codes_flag(E, E->stream)) return r;
     CK(cudaMemcpyAsync(out, E->chunks.p, (size_t)B * Lc * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
     CK(cudaStreamSynchronize(E->stream));
@@ -1243,7 +1334,7 @@ int voc_synthesize_range_dev(void* h, const long long* d_codes, int n_tokens, in
     if (!E) return VOC_E_INVALID;
     if (!d_codes || (!d_out_f32 && !d_out_i16)) return fail(E, VOC_E_INVALID, "bad argument");
     cudaStream_t st = stream ? (cudaStream_t)stream : E->stream;
-    return synth_range(E, d_codes, n_tokens, w0, w1, d_out_f32, d_out_i16, cap, out_offset, n_out, st);
+    return guarded(h, [&]() -> int { return synth_range(E, d_codes, n_tokens, w0, w1, d_out_f32, d_out_i16, cap, out_offset, n_out, st); });
 }
 
 int voc_synthesize_dev(void* h, const long long* d_codes, int n_tokens, float* d_out_f32, short* d_out_i16,
@@ -1262,6 +1353,7 @@ static int synth_host(void* h, const long long* codes, int n, float* of, short* 
     const long long total = make_plan(E->cfg, n).total;
     if (total > cap) return fail(E, VOC_E_INVALID, "output buffer too small");
     if (int r = ensure_codes(E, (size_t)n * 16)) return r;
+    CK(cudaMemsetAsync(E->d_err, 0, sizeof(int), E->stream));
     CK(cudaMemcpyAsync(E->d_codes, codes, (size_t)n * 16 * sizeof(long long), cudaMemcpyHostToDevice, E->stream));
     float* df = nullptr; short* di = nullptr;
     if (of) { if (int r = ensure_buf(E, E->stitch_f32, (size_t)total)) return r; df = E->stitch_f32.p; }
@@ -1274,7 +1366,7 @@ static int synth_host(void* h, const long long* codes, int n, float* of, short* 
         di = E->d_pcm;
     }
     long long off = 0, cnt = 0;
-    if (int r = synth_range(E, E->d_codes, n, 0, 1 << 30, df, di, total, &off, &cnt, E->stream)) return r;
+    if (int r = guarded(h, [&]() -> int { return synth_range(E, E->d_codes, n, 0, 1 << 30, df, di, total, &off, &cnt, E->stream); })) return r;
     if (int r = check_codes_flag(E, E->stream)) return r;
     if (of) CK(cudaMemcpyAsync(of, df, (size_t)cnt * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
     if (oi) CK(cudaMemcpyAsync(oi, di, (size_t)cnt * sizeof(short), cudaMemcpyDeviceToHost, E->stream));
@@ -1306,13 +1398,14 @@ int voc_synthesize_batch_pcm16(void* h, const long long* codes, const int* n_tok
     if (total > cap) return fail(E, VOC_E_INVALID, "output buffer too small");
     if (frames > 0x7fffffffLL / 16) return fail(E, VOC_E_INVALID, "too many frames in one batch");
     if (int r = ensure_codes(E, (size_t)frames * 16)) return r;
+    CK(cudaMemsetAsync(E->d_err, 0, sizeof(int), E->stream));
     CK(cudaMemcpyAsync(E->d_codes, codes, (size_t)frames * 16 * sizeof(long long), cudaMemcpyHostToDevice, E->stream));
     if (E->pcm_cap < (size_t)total) {
         if (E->d_pcm) cudaFree(E->d_pcm);
         E->d_pcm = nullptr; E->pcm_cap = 0;
         CK(cudaMalloc(&E->d_pcm, (size_t)total * sizeof(short))); E->pcm_cap = (size_t)total;
     }
-    if (int r = synth_batch(E, E->d_codes, n_tokens, n_requests, nullptr, E->d_pcm, total, out_offsets, E->stream)) return r;
+    if (int r = guarded(h, [&]() -> int { return synth_batch(E, E->d_codes, n_tokens, n_requests, nullptr, E->d_pcm, total, out_offsets, E->stream); })) return r;
     if (int r = check_codes_flag(E, E->stream)) return r;
     CK(cudaMemcpyAsync(out, E->d_pcm, (size_t)total * sizeof(short), cudaMemcpyDeviceToHost, E->stream));
     CK(cudaStreamSynchronize(E->stream));
@@ -1355,6 +1448,7 @@ const char* voc_last_error(void* h) {
     return ((Engine*)h)->err.c_str();
 }
 long long voc_kernel_launches(void* h) { return h ? ((Engine*)h)->launches : 0; }
+long long voc_simt_launches(void* h) { return h ? ((Engine*)h)->simt_launches : 0; }
 
 int voc_set_option(void* h, const char* key, const char* value) {
     Engine* E = (Engine*)h;
@@ -1484,14 +1578,13 @@ int voc_test_tapgemm(int device, int mode, int tc_flags, int B, int a_rows, int 
     if (Y) setY(p, (d_R && getenv("VOC_TEST_INPLACE")) ? d_R : dY);
     if (S) setS(p, act(E, dS), sp.a ? &sp : nullptr);
     if (mode == 2 && !voc_tc_eligible(p)) return 1;
-    if (mode == 1) p.Wtc = nullptr;                 // keeps run_gemm on the CUDA-core kernel
-    CK(run_gemm(E, p, E->stream, "test"));
+    CK(run_gemm(E, p, E->stream, "test", mode != 2));
     CK(cudaStreamSynchronize(E->stream));
     if (iters > 0 && ms) {
         cudaEvent_t e0, e1;
         CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
         CK(cudaEventRecord(e0, E->stream));
-        for (int i = 0; i < iters; ++i) CK(run_gemm(E, p, E->stream, "test"));
+        for (int i = 0; i < iters; ++i) CK(run_gemm(E, p, E->stream, "test", mode != 2));
         CK(cudaEventRecord(e1, E->stream));
         CK(cudaStreamSynchronize(E->stream));
         float t = 0.f; CK(cudaEventElapsedTime(&t, e0, e1));

@@ -302,3 +302,93 @@ def test_production_size_decoder_matches_the_sibling_run_live(pkg, backend):
     assert got.shape == ref.shape == (1, 122325)
     snr, mx = _report("sibling-live/production-size", ref, got)
     assert snr > 60.0 and mx < 1e-4, (snr, mx)
+
+
+def test_full_chunk_parity_trim_right(pkg, backend):
+    """The other setting of ambiguity A1 at full size: ``transconv_trim="right"`` (length-preserving,
+    122 880 samples per 64-frame window) against the oracle, same gate."""
+    cfg = pkg.VocoderConfig(transconv_trim="right")
+    w = pkg.init_weights(cfg, 0)
+    voc = backend.Vocoder(cfg, w, wave=2)
+    voc.set_option("gemm", "tc")
+    codes = _codes(cfg, (2, 64, 16), seed=3)
+    got = voc.infer_chunks(codes)
+    ref, _ = VO.forward(codes, VO.Weights(w), cfg)
+    ref = ref.numpy()
+    assert got.shape == ref.shape == (2, 122880)
+    snr, mx = _report("full/64 trim=right", ref, got)
+    assert snr >= SNR_GATE_DB and mx <= MAXABS_GATE
+    assert voc.simt_launches == 0
+    voc.close()
+
+
+def test_benchmarked_configuration_parity(pkg, backend):
+    """The configuration bench.py times (BASELINE configs[2]: 256 windows per call, decoder waves of 32, front wave of
+    256, gemm = "tc") is itself checked against the oracle on four of its windows -- the first and last of the batch
+    and the two either side of a wave boundary -- and nothing on that path leaves the tcgen05 kernel family."""
+    import torch
+    cfg = pkg.VocoderConfig()
+    w = pkg.init_weights(cfg, 0)
+    voc = backend.Vocoder(cfg, w, wave=32)
+    voc.set_option("gemm", "tc")
+    B = 256
+    codes = _codes(cfg, (B, 64, 16), seed=1)
+    d_codes = torch.from_numpy(codes).cuda()
+    d_out = torch.empty(B, voc.chunk_samples, dtype=torch.float32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    voc.infer_chunks_dev(d_codes, B, d_out, st)
+    voc.check_dev(st)
+    assert voc.simt_launches == 0
+    pick = [0, 31, 32, 255]
+    got = d_out[pick].cpu().numpy()
+    ref, _ = VO.forward(codes[pick], VO.Weights(w), cfg)
+    ref = ref.numpy()
+    for i, k in enumerate(pick):
+        snr, mx = _report(f"bench-config window {k}", ref[i], got[i])
+        assert snr >= SNR_GATE_DB and mx <= MAXABS_GATE, (k, snr, mx)
+    # and the same windows alone (batch 4, one wave) give the same bits: the result does not depend on the wave
+    alone = voc.infer_chunks(codes[pick])
+    assert np.array_equal(alone, got)
+    voc.close()
+
+
+def test_tc_mode_refuses_a_shape_the_tensor_kernel_does_not_take(pkg, backend):
+    """north_star: no multi-backend dispatch.  With gemm = "tc" a layer the tcgen05 kernel cannot run is an error
+    (VOC_E_INVALID naming the layer), not a silent switch to the CUDA-core kernel; gemm = "auto" runs it there and
+    counts the launches."""
+    cfg = pkg.VocoderConfig.tiny(chunk_frames=8)        # 64 >> 4 = 4 channels in the last block: not tensor-core shaped
+    w = pkg.init_weights(cfg, 0)
+    codes = _codes(cfg, (1, 8, 16))
+    voc = backend.Vocoder(cfg, w, wave=1)
+    voc.set_option("gemm", "tc")
+    with pytest.raises(backend.VocoderError) as e:
+        voc.infer_chunks(codes)
+    assert e.value.code == backend.VOC_E_INVALID and "not eligible" in str(e.value)
+    voc.set_option("gemm", "auto")
+    n0 = voc.simt_launches
+    got = voc.infer_chunks(codes)
+    assert voc.simt_launches > n0
+    ref, _ = VO.forward(codes, VO.Weights(w), cfg)
+    snr, mx = _report("tiny/auto", ref.numpy(), got)
+    assert snr >= SNR_GATE_DB and mx <= MAXABS_GATE
+    voc.close()
+
+
+def test_two_handles_on_two_devices_in_one_process(pkg, backend):
+    """The ABI promises one handle per GPU, any number per process: the >48 KB shared-memory opt-in of the tcgen05
+    kernels is a per-device attribute (round-1 bug: a process-wide flag).  Needs two GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    cfg = pkg.VocoderConfig(chunk_frames=8)
+    w = pkg.init_weights(cfg, 0)
+    codes = _codes(cfg, (2, 8, 16))
+    a = backend.Vocoder(cfg, w, device=0, wave=2)
+    b = backend.Vocoder(cfg, w, device=1, wave=2)
+    for v in (a, b):
+        v.set_option("gemm", "tc")
+    ga = a.infer_chunks(codes)
+    gb = b.infer_chunks(codes)
+    ga2 = a.infer_chunks(codes)
+    assert np.array_equal(ga, gb) and np.array_equal(ga, ga2)
+    a.close(); b.close()

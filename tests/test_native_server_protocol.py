@@ -93,7 +93,8 @@ def server(tmp_path_factory, backend):
     model.write_bytes(b"stub")
     sock = str(d / "v.sock")
     env = dict(os.environ, LD_PRELOAD=stub)
-    proc = subprocess.Popen([SERVER, "--model", str(model), "--socket", sock, "--window-us", "5000"], env=env,
+    proc = subprocess.Popen([SERVER, "--model", str(model), "--socket", sock, "--window-us", "5000",
+                             "--recv-timeout-ms", "700", "--send-timeout-ms", "1500", "--max-conns", "24"], env=env,
                             stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     t0 = time.time()
     while not os.path.exists(sock):
@@ -164,4 +165,55 @@ def test_bad_input_is_closed_without_reply_and_neighbours_survive(server):
         except ConnectionResetError:
             pass
         s.close()
+    assert len(restated_client(server, good)) == 20 * 1920
+
+
+def test_a_stalled_sender_is_dropped_and_a_deaf_receiver_blocks_nobody(server):
+    """Hardening beyond the reference (which serialises connections): a peer that announces a body and never sends
+    it is dropped at the receive deadline; a peer that never reads its reply does not delay other requests."""
+    stall = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    stall.settimeout(10)
+    stall.connect(server)
+    stall.sendall(struct.pack("<i", 10000) + b"\x00" * 64)           # 1.28 MB announced, 64 bytes sent
+    deaf = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    deaf.connect(server)
+    big = _codes(2000, 77)                                            # reply of ~7.7 MB, never read
+    deaf.sendall(struct.pack("<i", len(big)) + big.astype("<i8").tobytes())
+    t0 = time.time()
+    good = _codes(20, 3)
+    assert len(restated_client(server, good)) == 20 * 1920           # served while both others are pending
+    assert time.time() - t0 < 5.0
+    try:
+        assert stall.recv(4) == b""                                   # closed without a reply at the deadline
+    except ConnectionResetError:
+        pass
+    assert time.time() - t0 < 8.0
+    stall.close()
+    deaf.close()
+    assert len(restated_client(server, good)) == 20 * 1920
+
+
+def test_connections_beyond_the_cap_are_refused(server):
+    held = []
+    try:
+        for _ in range(24):
+            s = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+            s.settimeout(10)
+            s.connect(server)
+            held.append(s)
+        time.sleep(0.2)
+        extra = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        extra.settimeout(10)
+        extra.connect(server)
+        try:
+            extra.sendall(struct.pack("<i", 1))
+            assert extra.recv(4) == b""                               # accepted and closed at once
+        except (ConnectionResetError, BrokenPipeError):
+            pass
+        extra.close()
+    finally:
+        for s in held:
+            s.close()
+    time.sleep(0.2)
+    good = _codes(20, 3)
     assert len(restated_client(server, good)) == 20 * 1920
