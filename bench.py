@@ -94,6 +94,15 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
+def bench_config(args, cfg):
+    """The `config` object of the JSON line -- the same for both arms (the workload, not the engine)."""
+    return {"workload": f"{args.batch} independent 64-frame x 16-codebook chunks per GPU (BASELINE configs[2])",
+            "architecture": "qwen3-tts-12hz decoder, decoder_dim 1536, 114 M params, random init seed 0",
+            "transconv_trim": cfg.transconv_trim, "wave": args.wave, "gemm": args.gemm,
+            "l2": "activations streamed per step exceed L2 by >100x; no flush needed",
+            "audio_seconds_per_chunk": CHUNK_AUDIO_S}
+
+
 # ----------------------------------------------------------------------------------------
 # CPU arm: the oracle (the only executable restatement of the reference's model call here)
 # ----------------------------------------------------------------------------------------
@@ -129,16 +138,20 @@ def run_reference(args, rank: int):
     ts = time_oracle(cfg, weights, sample, args.steps, max(1, min(args.warmup, 2)), threads)
     t = sum(ts) / len(ts)
     xrt = sample * CHUNK_AUDIO_S / t
+    # BASELINE configs[0] as written: intra_op_num_threads = 4 (dual_npu/vocoder_server.py:41), one chunk
+    t4 = time_oracle(cfg, weights, 1, 2, 1, 4)
+    xrt4 = CHUNK_AUDIO_S / (sum(t4) / len(t4))
     line = {
         "impl": "reference", "metric": "vocoder_xrt", "value": xrt, "unit": "audio-s/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "256 independent 64-frame x 16-codebook chunks per GPU (BASELINE configs[2])",
-                   "architecture": "qwen3-tts-12hz decoder, decoder_dim 1536, 114 M params, random init seed 0",
-                   "transconv_trim": cfg.transconv_trim},
+        "config": bench_config(args, cfg),
         "cpu_baseline": {"value": xrt, "unit": "audio-s/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample} of the 256 chunks per step (torch CPU FP32 oracle; "
-                                   "onnxruntime and the .onnx file are absent from this image)"},
+                         "sample": f"{sample} of the {args.batch} chunks per step, per-chunk rate extrapolated (torch CPU "
+                                   "FP32 oracle, all host threads; onnxruntime and the .onnx file are absent from this image)",
+                         "threads_4": {"value": xrt4, "cores": 4,
+                                       "sample": "1 chunk x 2 after 1 warm-up at torch.set_num_threads(4) = the "
+                                                 "reference's intra_op_num_threads (BASELINE configs[0])"}},
         "e2e": {"value": xrt, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gflops": cfg.flops_per_chunk() * sample / t / 1e9,
     }
@@ -225,19 +238,156 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     e2e = world * B * CHUNK_AUDIO_S / (ms_e2e / 1e3)
     checksum = float(h_out[0, :1000].double().abs().sum())
 
-    # ---- (3) batch-1 streaming latency (BASELINE configs[1]), host to host, p50 over 30
+    pick = sorted({0, min(args.wave - 1, B - 1), min(args.wave, B - 1), B - 1})
+    got_pick = h_out[pick].numpy().copy() if rank == 0 else None      # for the parity check (4)
+    simt_launches = int(voc.simt_launches)
+
+    # ---- (3) batch-1 streaming latency (BASELINE configs[1]), host to host, p50 / p95 over 200
     lat = []
     one = h_codes[:1].contiguous().pin_memory()
-    for i in range(35):
+    for i in range(220):
         t0 = time.perf_counter()
         voc.lib.voc_infer_chunks(voc._h, one.data_ptr(), 1, h_out.data_ptr())
-        if i >= 5:
+        if i >= 20:
             lat.append((time.perf_counter() - t0) * 1e3)
+    lat.sort()
+
+    # ---- (4) parity of THIS configuration: four windows of the batch just timed (first, last, either side of
+    # a wave boundary) against the CPU oracle, computed after the timed regions; rank 0 only
+
+    # ---- (5) BASELINE configs[3]: one 10-minute utterance (7 500 frames, 157 windows) split into contiguous window
+    # ranges over the ranks, each rank stitching the span its windows own, int16 PCM gathered to rank 0 (NCCL),
+    # D2H on rank 0.  Timed with CUDA events on one stream that carries the H2D, the kernels, the gather and the D2H.
+    S = importlib.import_module("qwen3-tts-axera-russian_b200.sharding")
+    utt = None
+    if not args.no_legs:
+        n_u = 7500
+        u_codes = torch.from_numpy(np.random.default_rng(7).integers(0, cfg.codebook_size, (n_u, 16), dtype=np.int64)).pin_memory()
+        nw_u = voc.num_windows(n_u)
+        total_u = voc.out_samples(n_u)
+        ranges = S.window_ranges(nw_u, world)
+        w0, w1 = ranges[rank]
+        d_u = torch.empty(n_u, 16, dtype=torch.int64, device=dev)
+        d_pcm = torch.empty(total_u, dtype=torch.int16, device=dev)
+        h_pcm = torch.empty(total_u, dtype=torch.int16).pin_memory()
+        counts = None
+
+        def utt_step():
+            nonlocal counts
+            with torch.cuda.stream(st):
+                d_u.copy_(u_codes, non_blocking=True)
+                off, cnt = voc.synthesize_range_dev(d_u, n_u, w0, w1, d_out_i16=d_pcm, cap=total_u, stream=st.cuda_stream)
+                if world > 1:
+                    if counts is None:
+                        c = torch.tensor([cnt], dtype=torch.int64, device=dev)
+                        allc = [torch.zeros_like(c) for _ in range(world)]
+                        dist.all_gather(allc, c)
+                        counts = [int(x.item()) for x in allc]
+                    mx = max(counts)
+                    send = d_pcm[:mx].view(torch.uint8)
+                    glist = [torch.empty_like(send) for _ in range(world)] if rank == 0 else None
+                    dist.gather(send, glist, dst=0)
+                    if rank == 0:
+                        o = 0
+                        for r in range(world):
+                            h_pcm[o:o + counts[r]].copy_(glist[r].view(torch.int16)[:counts[r]], non_blocking=True)
+                            o += counts[r]
+                else:
+                    h_pcm[:cnt].copy_(d_pcm[:cnt], non_blocking=True)
+            return cnt
+
+        for _ in range(2):
+            utt_step()
+        voc.check_dev(st.cuda_stream)
+        barrier()
+        reps_u = 3
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        u0.record(st)
+        for _ in range(reps_u):
+            utt_step()
+        u1.record(st)
+        barrier()
+        ms_u = max_over_ranks(u0.elapsed_time(u1) / reps_u)
+        bit_equal = None
+        if rank == 0:
+            alone = voc.synthesize_pcm16(u_codes.numpy())            # the same request on this GPU alone
+            bit_equal = bool(len(alone) == total_u and np.array_equal(alone, h_pcm.numpy()))
+        utt = {"workload": "one 10-minute utterance: 7500 frames, 157 windows of 64 frames, stride 48, crossfade 16 "
+                           "(BASELINE configs[3]); contiguous window ranges per rank, NCCL gather of int16 PCM to rank 0",
+               "value": n_u * 0.08 / (ms_u / 1e3), "unit": "audio-s/s", "ms": ms_u, "n_gpus": world,
+               "windows_per_rank": [b - a for a, b in ranges], "out_samples": int(total_u),
+               "pcm_gather_bytes": int(2 * total_u) if world > 1 else 0, "bit_equal_to_one_gpu": bit_equal,
+               "timed": "H2D codes + kernels + stitch + PCM gather + D2H on rank 0, CUDA events, max over ranks"}
+
+    # ---- (6) BASELINE configs[4]: 1000 mixed-length utterances (lengths round(exp(N(ln 100, 0.8^2))) clipped to
+    # [8, 3750] frames, seed 2), sharded over the ranks by longest-processing-time balance; every rank synthesises
+    # its whole shard with ONE voc_synthesize_batch_pcm16 call (host codes in, host PCM out); no collective.
+    corpus = None
+    if not args.no_legs:
+        rng2 = np.random.default_rng(2)
+        lengths = np.clip(np.round(np.exp(rng2.normal(np.log(100), 0.8, args.corpus))), 8, 3750).astype(int)
+        bins = S.shard_corpus(lengths, world, cfg.chunk_frames)
+        mine = bins[rank]
+        my_lens = np.asarray([int(lengths[i]) for i in mine], dtype=np.int32)
+        frames_mine = int(my_lens.sum())
+        c_codes = torch.from_numpy(np.random.default_rng(1000 + rank).integers(
+            0, cfg.codebook_size, (max(frames_mine, 1), 16), dtype=np.int64)).pin_memory()
+        cap_c = int(sum(voc.out_samples(int(n)) for n in my_lens))
+        c_out = torch.empty(max(cap_c, 1), dtype=torch.int16).pin_memory()
+        offs = np.zeros(len(mine) + 1, dtype=np.int64)
+
+        def corpus_step():
+            if not len(mine):
+                return
+            rc = voc.lib.voc_synthesize_batch_pcm16(voc._h, c_codes.data_ptr(), my_lens.ctypes.data, len(mine),
+                                                    c_out.data_ptr(), cap_c, offs.ctypes.data)
+            if rc:
+                raise RuntimeError(voc.lib.voc_last_error(voc._h))
+
+        corpus_step()
+        barrier()
+        reps_c = 2
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(own)
+        for _ in range(reps_c):
+            corpus_step()
+        c1.record(own)
+        barrier()
+        ms_c = max_over_ranks(c0.elapsed_time(c1) / reps_c)
+        # spot check on rank 0: the first utterance of the shard alone gives the same PCM
+        same = None
+        if rank == 0 and len(mine):
+            a = voc.synthesize_pcm16(c_codes[: int(my_lens[0])].numpy())
+            same = bool(np.array_equal(a, c_out[: int(offs[1])].numpy()))
+        nwin_c = int(sum(voc.num_windows(int(n)) for n in lengths))
+        corpus = {"workload": f"{args.corpus} utterances, lengths round(exp(N(ln 100, 0.8^2))) in [8, 3750] frames, seed 2 "
+                              "(BASELINE configs[4]); LPT shard per rank, one batched call per rank, no collective",
+                  "value": float(lengths.sum()) * 0.08 / (ms_c / 1e3), "unit": "audio-s/s", "ms": ms_c, "n_gpus": world,
+                  "frames": int(lengths.sum()), "windows": nwin_c,
+                  "window_frames_over_utterance_frames": nwin_c * 64 / float(lengths.sum()),
+                  "first_utterance_equals_single_request": same,
+                  "timed": "host int64 codes -> host int16 PCM through voc_synthesize_batch_pcm16, CUDA events on the "
+                           "handle's stream, max over ranks"}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+
+    parity = None
+    try:
+        from oracle import vocoder_oracle as VO
+        torch.set_num_threads(os.cpu_count() or 1)
+        ref, _ = VO.forward(h_codes[pick].numpy(), VO.Weights(weights), cfg)
+        ref = ref.numpy().astype(np.float64)
+        err = ref - got_pick
+        snrs = [10 * np.log10((ref[i] ** 2).sum() / max((err[i] ** 2).sum(), 1e-300)) for i in range(len(pick))]
+        parity = {"windows": pick, "snr_db": float(min(snrs)), "max_abs": float(np.abs(err).max()),
+                  "gate": "snr_db >= 60 and max_abs <= 1e-4 vs the FP32 CPU oracle on the same codes",
+                  "pass": bool(min(snrs) >= 60.0 and np.abs(err).max() <= 1e-4),
+                  "what": "windows of the timed 256-window batch (wave 32, front wave 256), host-to-host call"}
+    except Exception as e:                                    # the bench line must still print
+        parity = {"error": repr(e)}
 
     # ---- roofline of the dominant kernel family (the tap-GEMM that runs every conv/linear)
     peaks, peak_src = _peaks()
@@ -290,6 +440,8 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     threads = os.cpu_count() or 1
     ts = time_oracle(cfg, weights, 1, 3, 1, threads)
     cpu_xrt = CHUNK_AUDIO_S / (sum(ts) / len(ts))
+    t4 = time_oracle(cfg, weights, 1, 2, 1, 4)                 # the reference's intra_op_num_threads = 4
+    cpu_xrt4 = CHUNK_AUDIO_S / (sum(t4) / len(t4))
 
     line = {
         "metric": "vocoder_xrt", "value": value, "unit": "audio-s/s", "n_gpus": world,
@@ -297,23 +449,28 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if args.gemm == "simt" else "f16x3-f32acc",
         "data": "synthetic",
-        "config": {"workload": f"{B} independent 64-frame x 16-codebook chunks per GPU (BASELINE configs[2])",
-                   "architecture": "qwen3-tts-12hz decoder, decoder_dim 1536, 114 M params, random init seed 0",
-                   "transconv_trim": cfg.transconv_trim, "wave": args.wave, "gemm": args.gemm,
-                   "l2": "activations streamed per step exceed L2 by >100x; no flush needed",
-                   "audio_seconds_per_chunk": CHUNK_AUDIO_S},
-        "tflops_algorithmic": world * B * cfg.flops_per_chunk() / (ms_dev / 1e3) / 1e12,
+        "config": bench_config(args, cfg),
+        "tflops_algorithmic_nominal": world * B * cfg.flops_per_chunk() / (ms_dev / 1e3) / 1e12,
+        "tflops_note": "nominal 317.49 GFLOP per window (SURVEY 8d); the executed graph (transconv_trim) does "
+                       f"{cfg.flops_per_chunk(nominal=False) / 1e9:.2f} GFLOP",
         "e2e": {"value": e2e, "unit": "audio-s/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(h_codes.numel() * 8), "d2h_bytes_per_step": int(B * Lc * 4),
-                "call": "voc_infer_chunks (host int64 codes -> host float32 audio)", "checksum": checksum},
-        "latency_ms": {"workload": "1 chunk, batch 1, host to host (BASELINE configs[1])",
-                       "p50": statistics.median(lat), "p95": sorted(lat)[int(0.95 * len(lat)) - 1]},
+                "call": "voc_infer_chunks (host int64 codes -> host float32 audio)", "checksum": checksum,
+                "parity": parity,
+                "latency_ms": {"workload": "1 chunk, batch 1, host to host incl. H2D of 8 KB codes and D2H of the "
+                                           "window (BASELINE configs[1]); 200 calls after 20 warm-ups",
+                               "p50": lat[len(lat) // 2], "p95": lat[int(0.95 * len(lat)) - 1]},
+                "utterance_10min": utt, "corpus_1k": corpus},
         "gpu_launches": int(launches),
+        "simt_launches": simt_launches,
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": {"value": cpu_xrt, "unit": "audio-s/s", "cores": threads, "kind": "port",
                          "sample": "3 chunks after 1 warm-up, torch CPU FP32 oracle, all host threads "
-                                   "(onnxruntime / the .onnx file are absent from this image)"},
+                                   "(onnxruntime / the .onnx file are absent from this image)",
+                         "threads_4": {"value": cpu_xrt4, "cores": 4,
+                                       "sample": "2 chunks after 1 warm-up at torch.set_num_threads(4), the reference's "
+                                                 "intra_op_num_threads (dual_npu/vocoder_server.py:41; BASELINE configs[0])"}},
         "breakdown": breakdown,
     }
     print(json.dumps(line), flush=True)
@@ -329,7 +486,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="chunks per GPU per step")
     ap.add_argument("--wave", type=int, default=32, help="chunks resident in HBM at once")
-    ap.add_argument("--gemm", default="auto", choices=["auto", "simt", "tc"])
+    ap.add_argument("--gemm", default="tc", choices=["auto", "simt", "tc"])
+    ap.add_argument("--corpus", type=int, default=1000, help="utterances of the corpus leg")
+    ap.add_argument("--no-legs", action="store_true", help="skip the 10-minute-utterance and corpus legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -148,3 +148,23 @@ def test_bad_requests_are_closed_without_reply(server):
     s.sendall(struct.pack("<i", 64) + b"\x00" * 100)
     s.close()
     assert np.array_equal(client_request(sock, good), voc.synthesize_pcm16(good))
+
+
+@pytest.mark.parametrize("n", [40, 100, 200])
+def test_server_reply_matches_the_oracle(server, pkg, n):
+    """The native server against the CPU restatement itself (not against the same library in-process): the reply to
+    a request equals stitch_oracle.synthesize driven by vocoder_oracle's chunk function, converted with the
+    reference's truncating PCM16 rule, to within 1 LSB (the float outputs agree to ~2e-5, so a truncation boundary
+    can fall between them)."""
+    from oracle import stitch_oracle as SO
+    from oracle import vocoder_oracle as VO
+    cfg, voc, sock, _ = server
+    w = pkg.init_weights(cfg, 0)
+    codes = _codes(cfg, n, 300 + n)
+    got = client_request(sock, codes)
+    orc = VO.OracleVocoder(cfg, w)
+    ref = SO.to_pcm16(SO.synthesize(codes, orc._inference_chunk, cfg.chunk_frames))
+    assert got.shape == ref.shape
+    d = np.abs(got.astype(np.int32) - ref.astype(np.int32))
+    print(f"server vs oracle n={n}: max diff {int(d.max())} LSB, differing samples {float((d > 0).mean()):.4f}")
+    assert int(d.max()) <= 1
