@@ -404,19 +404,19 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     top = max(gemm, key=lambda q: q["ms"]) if gemm else None
     traffic = None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
         if top and args.wave == tr.get("wave") and B % args.wave == 0 and top["tag"] in tr and args.gemm != "simt":
             traffic = tr[top["tag"]]["dram_bytes_per_launch"]
     except Exception:
         traffic = None
     achieved = top["flops"] / (top["ms"] / 1e3) / 1e12 if top and top["ms"] > 0 else 0.0
     roofline = {
-        "kernel": (f"tapgemm_tc_kernel (tcgen05 tap-GEMM), layer {top['tag']}" if args.gemm != "simt"
-                   else f"tapgemm_simt_kernel, layer {top['tag']}") if top else None,
+        "kernel": (f"tapgemm_simt_kernel, layer {top['tag']}" if args.gemm == "simt"
+                   else f"ru_fused_kernel (tcgen05: conv7 -> Snake -> conv1 -> + residual in one launch), layer {top['tag']}"
+                   if top["tag"].endswith(".fused") else f"tapgemm_tc_kernel (tcgen05 tap-GEMM), layer {top['tag']}") if top else None,
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
         "frac": achieved / peak, "traffic": traffic,
-        "traffic_note": "DRAM bytes of one launch of that layer (ncu --set full, profiles/r1_traffic.json); "
-                        "equals its algorithmic bytes (operand in, operand out)" if traffic else None,
+        "traffic_note": "DRAM bytes of one launch of that layer (ncu --set full, profiles/r2_traffic.json)" if traffic else None,
         "peak_source": f"{peak_src} bf16 dense sustained (MEASURED_PEAKS.json)",
         "launches_per_step": top["calls"] / args.steps if top else None,
         "avg_launch_ms": top["ms"] / max(top["calls"], 1) if top else None,

@@ -137,6 +137,9 @@ long long   voc_simt_launches(void* h);
  *            chunks, bit 3 run-time epilogue only, bit 4 no double-length head segments, bit 7 no
  *            cta_group::2 pairs, bits 8.. = MMAs accumulated in the tensor core per round-to-nearest
  *            flush, default 24)
+ *          "fuse_ru" = "1" | "0": residual units of the blocks with C <= 192 as ONE kernel (conv7 -> Snake ->
+ *            conv1 -> + residual, the intermediate operand in shared memory) or as two tap-GEMM launches; the
+ *            results are bit-identical
  *          "graphs" = "1" | "0": replay recurring waves of <= "graph_max_wave" (default 4) windows as
  *            CUDA graphs (batch-1 streaming latency is launch-bound)
  *          "front_wave" = windows per launch of the stages before the decoder blocks (codebook sum,
@@ -169,6 +172,17 @@ int voc_test_tapgemm(int device, int mode, int tc_flags, int B, int a_rows, int 
                      const float* bias, const float* scale, int act_kind, const float* R,
                      const float* sn_a, const float* sn_invb, float* Y, float* S, int iters,
                      float* ms);
+
+/* Kernel-level test / micro-benchmark hook for one residual unit:
+ *   T = Snake2(conv_k(A) + b7) with dilation `dil`;  x' = R + conv1x1(T) + b1;  Y = x';  S = Snake_next(x')
+ * fused = 1 runs the single fused kernel (ru_fused.cu), fused = 0 the two tap-GEMM launches it replaces; both on the
+ * tcgen05 path and bit-identical.  A, R, Y, S are [B][L][C] float32 (A is split to fp16 hi/lo here), W7 [ksz*C][C],
+ * W1 [C][C].  Returns 0, a negative error, or 1 if the fused kernel does not take the shape.  No reference counterpart
+ * (ONNX Runtime's operators are not individually callable from dual_npu/vocoder_server.py).                         */
+int voc_test_ru(int device, int fused, int tc_flags, int B, int L, int C, int ksz, int dil, const float* A,
+                const float* W7, const float* b7, const float* sn2_a, const float* sn2_invb, const float* W1,
+                const float* b1, const float* R, const float* snn_a, const float* snn_invb, float* Y, float* S,
+                int iters, float* ms);
 
 #ifdef __cplusplus
 }

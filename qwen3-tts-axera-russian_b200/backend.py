@@ -61,6 +61,7 @@ SIGNATURES = {
     "voc_debug_stage": (C.c_longlong, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_longlong]),
     "voc_test_tapgemm": (C.c_int, [C.c_int] * 10 + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 5
                          + [C.c_int, C.c_void_p]),
+    "voc_test_ru": (C.c_int, [C.c_int] * 8 + [C.c_void_p] * 12 + [C.c_int, C.c_void_p]),
 }
 
 _lib = None
@@ -138,6 +139,26 @@ def test_tapgemm(mode: int, A: np.ndarray, W: np.ndarray, tap_off, M: int, a_row
     rc = lib.voc_test_tapgemm(device, mode, tc_flags, B, a_rows, K, N, M, a_row0, ntaps, to.ctypes.data,
                               A.ctypes.data, W.ctypes.data, _ptr(bias), _ptr(scale), act, _ptr(R), _ptr(sn_a),
                               _ptr(sn_invb), _ptr(Y), _ptr(S), iters, C.addressof(ms))
+    return rc, Y, S, ms.value
+
+
+def test_ru(fused: int, A: np.ndarray, W7: np.ndarray, b7, sn2_a, sn2_invb, W1: np.ndarray, b1, R: np.ndarray,
+            snn_a, snn_invb, dil: int, ksz: int = 7, want_y: bool = True, tc_flags: int = 0, iters: int = 0,
+            device: int = 0):
+    """One residual unit through ``voc_test_ru``: A (= Snake1(x)) and R (= x) are [B, L, C] f32.
+    Returns (rc, Y or None, S, ms)."""
+    lib = load_library()
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    A, W7, W1, R = f(A), f(W7), f(W1), f(R)
+    b7, sn2_a, sn2_invb, b1, snn_a, snn_invb = map(f, (b7, sn2_a, sn2_invb, b1, snn_a, snn_invb))
+    B, L, Cc = A.shape
+    assert W7.shape == (ksz * Cc, Cc) and W1.shape == (Cc, Cc) and R.shape == A.shape
+    Y = np.zeros_like(A) if want_y else None
+    S = np.zeros_like(A)
+    ms = C.c_float(0.0)
+    rc = lib.voc_test_ru(device, fused, tc_flags, B, L, Cc, ksz, dil, A.ctypes.data, W7.ctypes.data, b7.ctypes.data,
+                         sn2_a.ctypes.data, sn2_invb.ctypes.data, W1.ctypes.data, b1.ctypes.data, R.ctypes.data,
+                         snn_a.ctypes.data, snn_invb.ctypes.data, _ptr(Y), S.ctypes.data, iters, C.addressof(ms))
     return rc, Y, S, ms.value
 
 

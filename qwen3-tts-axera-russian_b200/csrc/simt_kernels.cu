@@ -614,7 +614,7 @@ cudaError_t voc_launch_head(VocAct S, long long s_bstride, int L, int C, int ksz
 // K8: overlap-crossfade stitch + optional PCM16  (dual_npu/vocoder_server.py:101-117,175).
 // Every overlap involves exactly two windows when each non-final window emits >= 2*ov
 // samples (the planner checks this), so all windows are stitched in one launch.
-//   win_meta[w] = {dst, a_len, blended, next_blended, prev_a_len, _}
+//   win_meta[w] = {dst, a_len, blended, next_blended, prev_a_len, chunk slot, previous window's slot, _}
 // numpy evaluates  result*fade_out  and  chunk*fade_in  as two rounded float32 products
 // followed by a rounded add -- no FMA contraction here, hence the explicit _rn intrinsics.
 // PCM16: float32 multiply by 32767, clip, truncate toward zero (:175).
@@ -630,14 +630,16 @@ __global__ void stitch_kernel(const float* __restrict__ chunks, long long chunk_
                               const float* __restrict__ fade_out, const float* __restrict__ fade_in,
                               float* __restrict__ out_f32, short* __restrict__ out_i16) {
     const int w = blockIdx.y;
-    const int dst = win_meta[w * 6 + 0], a_len = win_meta[w * 6 + 1];
-    const int blended = win_meta[w * 6 + 2], next_blended = win_meta[w * 6 + 3];
-    const int prev_a = win_meta[w * 6 + 4];
-    const float* cur = chunks + (long long)w * chunk_stride;
+    const int* m = win_meta + (long long)w * 8;
+    const int dst = m[0], a_len = m[1];
+    const int blended = m[2], next_blended = m[3];
+    const int prev_a = m[4];
+    const float* cur = chunks + (long long)m[5] * chunk_stride;          // this window's chunk slot
+    const float* prev = chunks + (long long)m[6] * chunk_stride;         // the slot of the window before it
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a_len; i += gridDim.x * blockDim.x) {
         float v;
         if (blended && i < ov) {
-            const float r = chunks[(long long)(w - 1) * chunk_stride + (prev_a - ov + i)];
+            const float r = prev[prev_a - ov + i];
             v = __fadd_rn(__fmul_rn(r, fade_out[i]), __fmul_rn(cur[i], fade_in[i]));
         } else if (next_blended && i >= a_len - ov) {
             continue;                     // written by window w+1's blend

@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <string>
 
+struct CUtensorMap_st;
+
 #define VOC_MAX_TAPS 8
 
 // ---- error codes of the C ABI (include/voc_b200.h) ----
@@ -107,8 +109,29 @@ struct VocAct {
 // host-side launch wrappers (tc_gemm.cu): returns cudaErrorNotSupported when the shape is not
 // eligible for the tensor-core kernel (the caller then uses the CUDA-core kernel)
 bool voc_tc_eligible(const TapGemmParams& p);
+// cached 4-D fp16 tensor map {d0 (contiguous), d1, d2, 2 planes} with box {bk, box_rows, 1, box_planes}; strides in bytes
+bool voc_tc_get_map(const void* base, long long d0, long long d1, long long d2, long long s1, long long s2, long long s3,
+                    int bk, int box_rows, int box_planes, CUtensorMap_st* out);
 cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int num_sms, int flags);
 void voc_tc_clear_cache();
+
+// ------------------------------------------------------------------------------------
+// Fused residual unit (ru_fused.cu):  one kernel per unit
+//   T  = Snake2( conv7_dil(A) + b7 )            A = Snake1(x), the split-fp16 operand the previous layer wrote
+//   x' = x + conv1(T) + b1                      T never leaves the SM (split-fp16 operand in shared memory)
+//   Y  = x' (float32, optional)                 S = Snake_next(x') (split-fp16 operand of the next layer)
+// All tensors channels-last and dense: [B][L][C].  Bit-identical to the two tap-GEMM launches it replaces.
+// ------------------------------------------------------------------------------------
+struct RuFusedParams {
+    const __half* A_hi;  const __half* A_lo;  int L;  int C;  int B;  int dil;  int ksz;
+    const __half* W7tc;  long long w7_plane;  float w7scale;  const float* bias7;
+    const float* sn2_a;  const float* sn2_invb;
+    const __half* W1tc;  long long w1_plane;  float w1scale;  const float* bias1;
+    const float* R;  float* Y;
+    __half* S_hi;  __half* S_lo;  const float* snn_a;  const float* snn_invb;
+};
+bool voc_ru_fused_eligible(const RuFusedParams& p);
+cudaError_t voc_launch_ru_fused(const RuFusedParams& p, cudaStream_t st, int num_sms, int flags);
 // flags: bit 0 no tap reuse, bit 1 / bit 2 force 64- / 32-wide K chunks, bit 3 run-time (generic) epilogue only,
 // bit 4 no double-length head segments, bit 6 / bit 7 always / never cta_group::2 pairs, bits 8.. MMAs into the main
 // accumulator per round-to-nearest flush (default 24)

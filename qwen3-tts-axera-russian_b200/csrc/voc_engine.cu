@@ -93,9 +93,24 @@ struct Cfg {
     int attn_dim() const { return xf_heads * xf_head_dim; }
     int samples_per_frame() const { int p = 1; for (int r : upsampling_ratios) p *= r; for (int r : upsample_rates) p *= r; return p; }
     int tlen(int L, int s) const { return trim_both ? (L - 1) * s : L * s; }
-    int chunk_samples() const {
-        int t = chunk_frames; for (int r : upsampling_ratios) t *= r;
+    int chunk_samples_for(int frames) const {
+        int t = frames; for (int r : upsampling_ratios) t *= r;
         for (int s : upsample_rates) t = tlen(t, s);
+        return t;
+    }
+    int chunk_samples() const { return chunk_samples_for(chunk_frames); }
+    // How many frames of a window must be computed for its first `len` frames' samples to come out exactly as from
+    // the full chunk_frames-frame window (the reference pads a short window with code 0 and slices the output,
+    // vocoder_server.py:77-81,92-99).  Every layer is causal except the transposed convolutions under trim "both",
+    // which look ahead by one input step each: less than two steps of the decoder's input rate in total, i.e.
+    // ceil(2 / prod(upsampling_ratios)) frames.  Rounded up to a multiple of 8 frames so that windows bucket.
+    int frames_needed(int len) const {
+        if (len >= chunk_frames) return chunk_frames;
+        int up = 1; for (int r : upsampling_ratios) up *= r;
+        const int la = trim_both ? (2 + up - 1) / up : 0;
+        int t = std::min(chunk_frames, (len + la + 7) / 8 * 8);
+        const long long want = std::min<long long>(chunk_samples(), (long long)len * 1920);
+        while (t < chunk_frames && chunk_samples_for(t) < want) t = std::min(chunk_frames, t + 8);
         return t;
     }
 };
@@ -172,6 +187,8 @@ struct Engine {
     bool finalized = false;
     int gemm_mode = 0;          // 0 auto (= tc), 1 simt (FP32 CUDA cores), 2 tc (tcgen05, split fp16)
     int tc_flags = 0;           // VOC_TC_* experiment switches
+    bool fuse_ru = true;        // residual units with C <= 192 as one kernel (ru_fused.cu)
+    bool short_windows = true;  // a request's short last window computes only the frames it needs
     int num_sms = 148;
     bool debug = false;
     bool tc() const { return gemm_mode != 1; }
@@ -618,9 +635,8 @@ static int engine_finalize(Engine* E) {
 // pre-conv, transformer and up-sampling stages -> *x_out [nw][*L_out][latent] in operand format
 // --------------------------------------------------------------------------------------
 static int run_front(Engine* E, const long long* d_codes, int n_frames, int win_step, int w_begin, int nw,
-                     cudaStream_t st, const int* d_wmeta, float** x_out, int* L_out) {
+                     cudaStream_t st, const int* d_wmeta, float** x_out, int* L_out, int T) {
     const Cfg& c = E->cfg;
-    const int T = c.chunk_frames;
 #define KLAUNCH(tag, flops, bytes, call) do { ProfScope _ps(E, st, tag, flops, bytes); CK(call); } while (0)
 #define GEMM(tag, p) do { if (int _r = gemm_ck(E, p, st, tag)) return _r; } while (0)
     // Operand tensors (everything a GEMM reads) are in the mode's operand format -- act(); the
@@ -703,7 +719,7 @@ static VocAct act_at(Engine* E, float* base, size_t elems) {
 // one wave of the decoder: windows [x_win0, x_win0 + nw) of a front wave's output (nw <= wave) through conv-in,
 // the decoder blocks and the head -> chunk_out[nw][Lc]
 // --------------------------------------------------------------------------------------
-static int run_back(Engine* E, float* x, int x_win0, int L, int nw, float* chunk_out, cudaStream_t st) {
+static int run_back(Engine* E, float* x, int x_win0, int L, int nw, float* chunk_out, long long o_bstride, cudaStream_t st) {
     const Cfg& c = E->cfg;
     // K4: decoder conv-in, emits only Snake_0(conv_in(x)) -- the operand of block 0
     float* bX = E->big[0].p; float* bS = E->big[1].p; float* bT = E->big[2].p; float* bX2 = E->big[3].p;
@@ -734,6 +750,31 @@ static int run_back(Engine* E, float* x, int x_win0, int L, int nw, float* chunk
         const int C = Bk.cout;
         for (size_t j = 0; j < Bk.ru.size(); ++j) {
             auto& R = Bk.ru[j];
+            const bool last_ru_f = (j + 1 == Bk.ru.size());
+            const SnakeP& nxt_f = !last_ru_f ? Bk.ru[j + 1].s1
+                                : (b + 1 < E->blocks.size() ? E->blocks[b + 1].s_in : E->head_snake);
+            if (E->tc() && E->fuse_ru) {
+                // the whole unit in one kernel where a tile spans all channels (C <= 192): conv7 -> Snake2 -> conv1 ->
+                // + residual, the Snake2'd operand staying in shared memory (ru_fused.cu)
+                RuFusedParams f;
+                memset(&f, 0, sizeof f);
+                const VocAct Ain = act(E, bS), Sout = act(E, bT);
+                f.A_hi = Ain.hi; f.A_lo = Ain.lo; f.L = L; f.C = C; f.B = nw; f.dil = c.dilations[j]; f.ksz = c.conv_kernel;
+                f.W7tc = R.c1.Wtc; f.w7_plane = R.c1.wtc_plane; f.w7scale = R.c1.wscale; f.bias7 = R.c1.bias;
+                f.sn2_a = R.s2.a; f.sn2_invb = R.s2.invb;
+                f.W1tc = R.c2.Wtc; f.w1_plane = R.c2.wtc_plane; f.w1scale = R.c2.wscale; f.bias1 = R.c2.bias;
+                f.R = bX; f.Y = (!last_ru_f || E->debug) ? bX2 : nullptr;
+                f.S_hi = Sout.hi; f.S_lo = Sout.lo; f.snn_a = nxt_f.a; f.snn_invb = nxt_f.invb;
+                if (voc_ru_fused_eligible(f)) {
+                    static const char* const T_FU[] = {"dec0.ru.fused", "dec1.ru.fused", "dec2.ru.fused", "dec3.ru.fused", "decN.ru.fused"};
+                    const double el = (double)nw * L * C;
+                    ProfScope ps(E, st, T_FU[ti], 2.0 * el * C * (c.conv_kernel + 1), 4.0 * el * (f.Y ? 4.0 : 3.0));
+                    CK(voc_launch_ru_fused(f, st, E->num_sms, E->tc_flags));
+                    std::swap(bS, bT);
+                    if (f.Y) std::swap(bX, bX2);
+                    continue;
+                }
+            }
             {   // conv k7 dilated on Snake1(x) -> Snake2(.) only
                 TapGemmParams p = gp(R.c1, act(E, bS), (long long)L * C, L, 0, L, nw);
                 setS(p, act(E, bT), &R.s2);
@@ -760,20 +801,25 @@ static int run_back(Engine* E, float* x, int x_win0, int L, int nw, float* chunk
     // K7: head
     const int ch = c.decoder_dim >> c.upsample_rates.size();
     KLAUNCH("head", 2.0 * nw * L * ch * c.conv_kernel, 4.0 * nw * L * (ch + 1.0),
-            voc_launch_head(act(E, bS), (long long)L * ch, L, ch, c.conv_kernel, E->head_w, E->head_b, chunk_out, L, nw, st));
+            voc_launch_head(act(E, bS), (long long)L * ch, L, ch, c.conv_kernel, E->head_w, E->head_b, chunk_out, o_bstride, nw, st));
 #undef KLAUNCH
 #undef GEMM
     return VOC_OK;
 }
 
-// windows [w_begin, w_begin + nw) of a request (nw <= front_wave) -> chunk_out[nw][Lc]
+// windows [w_begin, w_begin + nw) of a request -> chunk_out[nw][Lc]; T = frames computed per window (chunk_frames, or
+// fewer for windows whose tail is padding: Cfg::frames_needed), nw <= front_capacity(T)
+static int front_capacity(const Engine* E, int T) { return std::max(1, (int)((long long)E->front_wave * E->cfg.chunk_frames / T)); }
+static int back_capacity(const Engine* E, int T) { return std::max(1, (int)((long long)E->wave * E->cfg.chunk_frames / T)); }
 static int run_wave(Engine* E, const long long* d_codes, int n_frames, int win_step, int w_begin, int nw,
-                    float* chunk_out, cudaStream_t st, const int* d_wmeta = nullptr) {
+                    float* chunk_out, cudaStream_t st, const int* d_wmeta = nullptr, int T = 0) {
+    if (T <= 0) T = E->cfg.chunk_frames;
     float* x = nullptr; int L = 0;
-    if (int r = run_front(E, d_codes, n_frames, win_step, w_begin, nw, st, d_wmeta, &x, &L)) return r;
+    if (int r = run_front(E, d_codes, n_frames, win_step, w_begin, nw, st, d_wmeta, &x, &L, T)) return r;
     const long long Lc = E->cfg.chunk_samples();
-    for (int s = 0; s < nw; s += E->wave) {
-        if (int r = run_back(E, x, s, L, std::min(E->wave, nw - s), chunk_out + (long long)s * Lc, st)) return r;
+    const int bw = E->debug ? E->wave : back_capacity(E, T);
+    for (int s = 0; s < nw; s += bw) {
+        if (int r = run_back(E, x, s, L, std::min(bw, nw - s), chunk_out + (long long)s * Lc, Lc, st)) return r;
     }
     return VOC_OK;
 }
@@ -790,9 +836,10 @@ static int check_codes_flag(Engine* E, cudaStream_t st) {
 }
 
 static int run_windows(Engine* E, const long long* d_codes, int n_frames, int win_step, int w0, int w1,
-                       float* chunk_out, cudaStream_t st) {
+                       float* chunk_out, cudaStream_t st, int T = 0) {
+    if (T <= 0) T = E->cfg.chunk_frames;
     const long long Lc = E->cfg.chunk_samples();
-    const int fw = E->debug ? E->wave : E->front_wave;      // debug captures describe one decoder wave
+    const int fw = E->debug ? E->wave : front_capacity(E, T);      // debug captures describe one decoder wave
     for (int w = w0; w < w1; w += fw) {
         const int nw = std::min(fw, w1 - w);
         float* out = chunk_out + (long long)(w - w0) * Lc;
@@ -801,11 +848,11 @@ static int run_windows(Engine* E, const long long* d_codes, int n_frames, int wi
         // eagerly (lazy set-up: kernel attributes, tensor maps), second sight is captured, later ones replay.
         const bool graphable = E->use_graphs && nw <= E->graph_max_wave && !E->profile && !E->debug;
         if (!graphable) {
-            if (int r = run_wave(E, d_codes, n_frames, win_step, w, nw, out, st)) return r;
+            if (int r = run_wave(E, d_codes, n_frames, win_step, w, nw, out, st, nullptr, T)) return r;
             continue;
         }
         const auto key = std::make_tuple((const void*)d_codes, (const void*)out, n_frames, win_step, w, nw,
-                                         E->gemm_mode, E->tc_flags);
+                                         E->gemm_mode, E->tc_flags * 128 + T);
         auto git = E->graphs.find(key);
         if (git != E->graphs.end() && git->second.exec) {
             git->second.last_use = ++E->graph_clock;
@@ -825,25 +872,25 @@ static int run_windows(Engine* E, const long long* d_codes, int n_frames, int wi
             }
             Engine::WaveGraph& N = E->graphs[key];
             N.seen = 1; N.last_use = ++E->graph_clock;
-            if (int r = run_wave(E, d_codes, n_frames, win_step, w, nw, out, st)) return r;
+            if (int r = run_wave(E, d_codes, n_frames, win_step, w, nw, out, st, nullptr, T)) return r;
             continue;
         }
         Engine::WaveGraph& G = git->second;
         G.last_use = ++E->graph_clock;
         if (G.seen < 0) {                                 // known not to be capturable
-            if (int r = run_wave(E, d_codes, n_frames, win_step, w, nw, out, st)) return r;
+            if (int r = run_wave(E, d_codes, n_frames, win_step, w, nw, out, st, nullptr, T)) return r;
             continue;
         }
         const long long l0 = E->launches;
         CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
-        const int r = run_wave(E, d_codes, n_frames, win_step, w, nw, out, st);
+        const int r = run_wave(E, d_codes, n_frames, win_step, w, nw, out, st, nullptr, T);
         cudaGraph_t graph = nullptr;
         const cudaError_t ce = cudaStreamEndCapture(st, &graph);
         if (r) { if (graph) cudaGraphDestroy(graph); return r; }
         if (ce != cudaSuccess || !graph) {           // not capturable here: stay eager for this key
             (void)cudaGetLastError();
             G.seen = -1000000;
-            if (int r2 = run_wave(E, d_codes, n_frames, win_step, w, nw, out, st)) return r2;
+            if (int r2 = run_wave(E, d_codes, n_frames, win_step, w, nw, out, st, nullptr, T)) return r2;
             continue;
         }
         G.launches = E->launches - l0;
@@ -948,12 +995,21 @@ static int synth_range(Engine* E, const long long* d_codes, int n, int w0, int w
     const int wc0 = (w0 > 0 && P.blended[w0]) ? w0 - 1 : w0;   // recompute the neighbour for the blend
     const int nwc = w1 - wc0;
     if (int r = ensure_buf(E, E->chunks, (size_t)nwc * Lc)) return r;
-    if (int r = run_windows(E, d_codes, n, P.step, wc0, w1, E->chunks.p, st)) return r;
+    {
+        // every window but possibly the request's last is full; a short last window computes only the frames its
+        // samples depend on (bit-identical to computing all chunk_frames and slicing: Cfg::frames_needed)
+        const int last = P.n_windows - 1;
+        const int Tl = (w1 == P.n_windows && E->short_windows) ? E->cfg.frames_needed(P.len[last]) : E->cfg.chunk_frames;
+        const int w_full = Tl < E->cfg.chunk_frames ? w1 - 1 : w1;
+        if (w_full > wc0) if (int r = run_windows(E, d_codes, n, P.step, wc0, w_full, E->chunks.p, st)) return r;
+        if (w_full < w1 && w_full >= wc0)
+            if (int r = run_windows(E, d_codes, n, P.step, w_full, w1, E->chunks.p + (long long)(w_full - wc0) * Lc, st, Tl)) return r;
+    }
     if (P.pairwise) {
-        std::vector<int> meta((size_t)nwc * 6);
+        std::vector<int> meta((size_t)nwc * 8);
         int max_a = 0;
         for (int w = wc0; w < w1; ++w) {
-            int* m = &meta[(size_t)(w - wc0) * 6];
+            int* m = &meta[(size_t)(w - wc0) * 8];
             const bool owned = w >= w0;
             m[0] = (int)(P.dst[w] - o_begin);
             m[1] = owned ? P.a_len[w] : 0;           // the recomputed neighbour writes nothing
@@ -961,7 +1017,7 @@ static int synth_range(Engine* E, const long long* d_codes, int n, int w0, int w
             // the trailing ov of the last owned window belongs to the next range's first window
             m[3] = (w + 1 < P.n_windows) ? P.blended[w + 1] : 0;
             m[4] = w > 0 ? P.a_len[w - 1] : 0;
-            m[5] = 0;
+            m[5] = w - wc0; m[6] = w - wc0 - 1; m[7] = 0;    // chunk slots of this window and of the one before it
             max_a = std::max(max_a, m[1]);
         }
         if (int r = ensure_i(E, meta.size())) return r;
@@ -997,7 +1053,10 @@ static int synth_batch(Engine* E, const long long* d_codes, const int* lens, int
     if (!E->finalized) return fail(E, VOC_E_STATE, "voc_finalize has not been called");
     CK(cudaSetDevice(E->device));
     const long long Lc = E->cfg.chunk_samples();
-    std::vector<int> wmeta, smeta;                    // {first frame, frames} and the 6-int stitch records
+    // every window of every request: {first frame, frames}, frames to compute, stitch record, previous window
+    struct BW { int first, len, T, dst, a_len, blended, next_blended, prev_a, prev; };
+    std::vector<BW> win;
+    std::vector<int> utt_first;                       // index of each request's first window (+ sentinel)
     long long total = 0, frame0 = 0;
     int max_a = 0;
     for (int u = 0; u < n_utt; ++u) {
@@ -1006,42 +1065,69 @@ static int synth_batch(Engine* E, const long long* d_codes, const int* lens, int
         const Plan P = make_plan(E->cfg, n);
         if (!P.pairwise) return fail(E, VOC_E_INVALID, "batched synthesis needs the pairwise-overlap regime");
         out_off[u] = total;
+        utt_first.push_back((int)win.size());
         for (int w = 0; w < P.n_windows; ++w) {
-            wmeta.push_back((int)(frame0 + P.start[w])); wmeta.push_back(P.len[w]);
             const long long dst = total + P.dst[w];
             if (dst + P.a_len[w] > 0x7fffffffLL) return fail(E, VOC_E_INVALID, "batch output exceeds 2^31 samples");
-            smeta.push_back((int)dst); smeta.push_back(P.a_len[w]); smeta.push_back(P.blended[w]);
-            smeta.push_back(w + 1 < P.n_windows ? P.blended[w + 1] : 0);
-            smeta.push_back(w > 0 ? P.a_len[w - 1] : 0); smeta.push_back(0);
+            BW x;
+            x.first = (int)(frame0 + P.start[w]); x.len = P.len[w];
+            x.T = E->short_windows ? E->cfg.frames_needed(P.len[w]) : E->cfg.chunk_frames;
+            x.dst = (int)dst; x.a_len = P.a_len[w]; x.blended = P.blended[w];
+            x.next_blended = w + 1 < P.n_windows ? P.blended[w + 1] : 0;
+            x.prev_a = w > 0 ? P.a_len[w - 1] : 0;
+            x.prev = w > 0 ? (int)win.size() - 1 : -1;
+            win.push_back(x);
             max_a = std::max(max_a, P.a_len[w]);
         }
         total += P.total; frame0 += n;
     }
+    utt_first.push_back((int)win.size());
     out_off[n_utt] = total;
     if (total > cap) return fail(E, VOC_E_INVALID, "output buffer too small");
-    const int nwin = (int)(wmeta.size() / 2);
-    if (int r = ensure_i(E, wmeta.size() + smeta.size())) return r;
-    int* d_wmeta = E->d_meta; int* d_smeta = E->d_meta + wmeta.size();
-    CK(cudaMemcpyAsync(d_wmeta, wmeta.data(), wmeta.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(d_smeta, smeta.data(), smeta.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    CK(cudaStreamSynchronize(st));                     // the host vectors go out of scope
-    // windows in groups that bound the chunk buffer (a blend reads the previous window, so a group
-    // never starts on a blended window)
-    const int group_max = std::max(E->wave * 8, 64);
-    for (int g0 = 0; g0 < nwin;) {
-        int g1 = std::min(nwin, g0 + group_max);
-        while (g1 < nwin && smeta[(size_t)g1 * 6 + 2]) ++g1;
-        const int ng = g1 - g0;
-        if (int r = ensure_buf(E, E->chunks, (size_t)ng * Lc)) return r;
-        const int fw = E->debug ? E->wave : E->front_wave;
-        for (int w = g0; w < g1; w += fw) {
-            const int nw = std::min(fw, g1 - w);
-            if (int r = run_wave(E, d_codes, (int)frame0, 0, w, nw, E->chunks.p + (long long)(w - g0) * Lc, st, d_wmeta)) return r;
+    // Groups of whole requests bound the chunk buffer (0.49 MB per window).  Inside a group the windows are
+    // processed in order of the frames they compute -- full 64-frame windows first, then the requests' short last
+    // windows bucketed by length -- so that every wave is dense; the stitch finds a window's chunk and its
+    // predecessor's through slot indices.
+    const int group_cap = E->debug ? std::max(E->wave, 1) * 8 : 4096;
+    std::vector<int> order, slot(win.size()), wmeta, smeta;
+    for (size_t u0 = 0; u0 + 1 < utt_first.size();) {
+        size_t u1 = u0 + 1;
+        while (u1 + 1 < utt_first.size() && utt_first[u1 + 1] - utt_first[u0] <= group_cap) ++u1;
+        const int g0 = utt_first[u0], g1 = utt_first[u1], ng = g1 - g0;
+        order.resize(ng);
+        for (int i = 0; i < ng; ++i) order[i] = g0 + i;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return win[x].T > win[y].T; });
+        for (int i = 0; i < ng; ++i) slot[order[i]] = i;
+        wmeta.resize((size_t)ng * 2); smeta.resize((size_t)ng * 8);
+        for (int i = 0; i < ng; ++i) {
+            const BW& x = win[order[i]];
+            wmeta[2 * i] = x.first; wmeta[2 * i + 1] = x.len;
+            int* m = &smeta[(size_t)i * 8];
+            m[0] = x.dst; m[1] = x.a_len; m[2] = x.blended; m[3] = x.next_blended; m[4] = x.prev_a;
+            m[5] = i; m[6] = x.prev >= 0 ? slot[x.prev] : 0; m[7] = 0;
         }
-        ProfScope ps(E, st, "stitch", 0.0, 0.0);
-        CK(voc_launch_stitch(E->chunks.p, Lc, d_smeta + (size_t)g0 * 6, ng, 16 * 1920, E->d_fade_out, E->d_fade_in, d_f32,
-                             d_i16, max_a, st));
-        g0 = g1;
+        if (int r = ensure_i(E, wmeta.size() + smeta.size())) return r;
+        int* d_wmeta = E->d_meta; int* d_smeta = E->d_meta + wmeta.size();
+        CK(cudaMemcpyAsync(d_wmeta, wmeta.data(), wmeta.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_smeta, smeta.data(), smeta.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));                 // the host vectors are reused by the next group
+        if (int r = ensure_buf(E, E->chunks, (size_t)ng * Lc)) return r;
+        for (int p0 = 0; p0 < ng;) {
+            const int T = win[order[p0]].T;
+            int p1 = p0;
+            while (p1 < ng && win[order[p1]].T == T) ++p1;
+            const int fw = E->debug ? E->wave : front_capacity(E, T);
+            for (int w = p0; w < p1; w += fw) {
+                const int nw = std::min(fw, p1 - w);
+                if (int r = run_wave(E, d_codes, (int)frame0, 0, w, nw, E->chunks.p + (long long)w * Lc, st, d_wmeta, T)) return r;
+            }
+            p0 = p1;
+        }
+        {
+            ProfScope ps(E, st, "stitch", 0.0, 0.0);
+            CK(voc_launch_stitch(E->chunks.p, Lc, d_smeta, ng, 16 * 1920, E->d_fade_out, E->d_fade_in, d_f32, d_i16, max_a, st));
+        }
+        u0 = u1;
     }
     return VOC_OK;
 }
@@ -1095,6 +1181,7 @@ static void* create_impl(const char* cfg_json, int device, int wave) {
     // experiment hooks (the documented switch is voc_set_option)
     if (const char* g = getenv("VOC_GEMM")) E->gemm_mode = !strcmp(g, "simt") ? 1 : !strcmp(g, "tc") ? 2 : 0;
     if (const char* f = getenv("VOC_TC_FLAGS")) E->tc_flags = atoi(f);
+    if (const char* f = getenv("VOC_FUSE_RU")) E->fuse_ru = atoi(f) != 0;
     if (const char* f = getenv("VOC_GRAPH_MAX_WAVE")) E->graph_max_wave = atoi(f);
     if (const char* f = getenv("VOC_FRONT_WAVE")) E->front_wave = atoi(f);
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -1460,6 +1547,8 @@ int voc_set_option(void* h, const char* key, const char* value) {
         return VOC_OK;
     }
     if (k == "tc_flags") { E->tc_flags = atoi(v.c_str()); return VOC_OK; }
+    if (k == "fuse_ru") { E->fuse_ru = (v == "1"); return VOC_OK; }
+    if (k == "short_windows") { E->short_windows = (v == "1"); return VOC_OK; }
     if (k == "graphs") { E->use_graphs = (v == "1"); return VOC_OK; }
     if (k == "graph_max_wave") { E->graph_max_wave = atoi(v.c_str()); return VOC_OK; }
     if (k == "front_wave") {
@@ -1602,6 +1691,95 @@ int voc_test_tapgemm(int device, int mode, int tc_flags, int B, int a_rows, int 
             CK(cudaStreamSynchronize(E->stream));
             CK(cudaMemcpy(S, tmp, (size_t)B * M * N * 4, cudaMemcpyDeviceToHost));
         }
+    }
+    CK(cudaDeviceSynchronize());
+    return VOC_OK;
+}
+
+
+// ---- kernel-level hook: one residual unit on caller data, fused (1) or as the two tap-GEMM launches (0) ----------
+// A [B][L][C] = Snake1(x) (float32, split here), W7 [ksz*C][C] and W1 [C][C] in the CUDA-core layout, R = x [B][L][C].
+// Outputs Y = x' and S = Snake_next(x') [B][L][C] float32.  Returns 0, a negative VOC_E_*, or 1 when the fused kernel
+// does not take the shape.
+int voc_test_ru(int device, int fused, int tc_flags, int B, int L, int C, int ksz, int dil, const float* A,
+                const float* W7, const float* b7, const float* sn2_a, const float* sn2_invb, const float* W1,
+                const float* b1, const float* R, const float* snn_a, const float* snn_invb, float* Y, float* S,
+                int iters, float* ms) {
+    if (!A || !W7 || !W1 || !b7 || !b1 || !R || !sn2_a || !sn2_invb || !snn_a || !snn_invb || B < 1 || L < 1 ||
+        ksz < 1 || ksz > VOC_MAX_TAPS) return VOC_E_INVALID;
+    Engine EE; Engine* E = &EE;
+    E->device = device;
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    E->num_sms = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking));
+    E->gemm_mode = 2; E->tc_flags = tc_flags;
+    GemmW g7, g1;
+    g7.K = C; g7.N = C; g7.ntaps = ksz;
+    for (int i = 0; i < ksz; ++i) g7.tap_off[i] = -(ksz - 1 - i) * dil;
+    g1.K = C; g1.N = C; g1.ntaps = 1; g1.tap_off[0] = 0;
+    std::vector<float> w7(W7, W7 + (size_t)ksz * C * C), w1(W1, W1 + (size_t)C * C);
+    g7.W = upload(E, w7); g1.W = upload(E, w1);
+    if (!g7.W || !g1.W || !make_wtc(E, w7, g7) || !make_wtc(E, w1, g1)) return fail(E, VOC_E_CUDA, "weight upload failed");
+    auto up = [&](const float* h, size_t n) -> float* { return upload(E, std::vector<float>(h, h + n)); };
+    g7.bias = up(b7, C); g1.bias = up(b1, C);
+    SnakeP s2, sn; s2.a = up(sn2_a, C); s2.invb = up(sn2_invb, C); sn.a = up(snn_a, C); sn.invb = up(snn_invb, C);
+    const size_t ne = (size_t)B * L * C, na = (ne + 63) / 64 * 64;
+    float* dR = up(R, ne);
+    float *dA = nullptr, *dT = nullptr, *dY = nullptr, *dS = nullptr, *tmp = nullptr;
+    CK(cudaMalloc(&dA, na * 4)); E->owned.push_back(dA); E->cap[dA] = na;
+    CK(cudaMalloc(&dT, na * 4)); E->owned.push_back(dT); E->cap[dT] = na;
+    CK(cudaMalloc(&dS, na * 4)); E->owned.push_back(dS); E->cap[dS] = na;
+    CK(cudaMalloc(&dY, na * 4)); E->owned.push_back(dY);
+    CK(cudaMalloc(&tmp, na * 4)); E->owned.push_back(tmp);
+    CK(cudaMemsetAsync(dY, 0, na * 4, E->stream)); CK(cudaMemsetAsync(dS, 0, na * 4, E->stream));
+    {
+        std::vector<__half> h(2 * na);
+        for (size_t i = 0; i < ne; ++i) {
+            const float v = std::min(65504.f, std::max(-65504.f, A[i]));
+            h[i] = __float2half_rn(v);
+            h[na + i] = __float2half_rn(v - __half2float(h[i]));
+        }
+        CK(cudaMemcpyAsync(dA, h.data(), h.size() * 2, cudaMemcpyHostToDevice, E->stream));
+        CK(cudaStreamSynchronize(E->stream));
+    }
+    RuFusedParams f;
+    memset(&f, 0, sizeof f);
+    const VocAct Ain = act(E, dA), Sout = act(E, dS);
+    f.A_hi = Ain.hi; f.A_lo = Ain.lo; f.L = L; f.C = C; f.B = B; f.dil = dil; f.ksz = ksz;
+    f.W7tc = g7.Wtc; f.w7_plane = g7.wtc_plane; f.w7scale = g7.wscale; f.bias7 = g7.bias; f.sn2_a = s2.a; f.sn2_invb = s2.invb;
+    f.W1tc = g1.Wtc; f.w1_plane = g1.wtc_plane; f.w1scale = g1.wscale; f.bias1 = g1.bias;
+    f.R = dR; f.Y = Y ? dY : nullptr; f.S_hi = Sout.hi; f.S_lo = Sout.lo; f.snn_a = sn.a; f.snn_invb = sn.invb;
+    if (fused && !voc_ru_fused_eligible(f)) return 1;
+    auto once = [&]() -> int {
+        if (fused) { CK(voc_launch_ru_fused(f, E->stream, E->num_sms, E->tc_flags)); return VOC_OK; }
+        TapGemmParams p = gp(g7, act(E, dA), (long long)L * C, L, 0, L, B);
+        setS(p, act(E, dT), &s2);
+        CK(run_gemm(E, p, E->stream, "test.conv7"));
+        TapGemmParams p2 = gp(g1, act(E, dT), (long long)L * C, L, 0, L, B);
+        setR(p2, dR); if (Y) setY(p2, dY); setS(p2, act(E, dS), &sn);
+        CK(run_gemm(E, p2, E->stream, "test.conv1"));
+        return VOC_OK;
+    };
+    if (int r = once()) return r;
+    CK(cudaStreamSynchronize(E->stream));
+    if (iters > 0 && ms) {
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        CK(cudaEventRecord(e0, E->stream));
+        for (int i = 0; i < iters; ++i) if (int r = once()) return r;
+        CK(cudaEventRecord(e1, E->stream));
+        CK(cudaStreamSynchronize(E->stream));
+        float t = 0.f; CK(cudaEventElapsedTime(&t, e0, e1));
+        *ms = t / iters;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    if (Y) CK(cudaMemcpy(Y, dY, ne * 4, cudaMemcpyDeviceToHost));
+    if (S) {
+        CK(voc_launch_unsplit(Sout.hi, Sout.lo, tmp, (long long)ne, E->stream));
+        CK(cudaStreamSynchronize(E->stream));
+        CK(cudaMemcpy(S, tmp, ne * 4, cudaMemcpyDeviceToHost));
     }
     CK(cudaDeviceSynchronize());
     return VOC_OK;

@@ -1,0 +1,81 @@
+"""The fused residual-unit kernel (csrc/ru_fused.cu) through the C ABI hook voc_test_ru:
+conv7(dilated) -> Snake -> conv1x1 -> + residual in one launch, against (a) a float64 numpy restatement of the unit
+(sibling :3686-3702 via oracle/vocoder_oracle.py's formulas) and (b) the two tap-GEMM launches it replaces, with
+which it must agree bit for bit (same segment schedule, pass order and epilogue arithmetic)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def snake64(x, a, invb):
+    return x + invb * np.sin(x * a) ** 2
+
+
+def ref_unit(A, W7, b7, s2a, s2b, W1, b1, R, sna, snb, dil, ksz=7):
+    """float64: A [B, L, C] is already Snake1(x); causal dilated conv = taps at -(k-1-j)*dil with zero left padding."""
+    B, L, C = A.shape
+    A = A.astype(np.float64)
+    acc = np.zeros((B, L, C))
+    for j in range(ksz):
+        off = (ksz - 1 - j) * dil
+        sh = np.zeros_like(A)
+        if off < L:
+            sh[:, off:, :] = A[:, : L - off, :]
+        acc += sh @ W7[j * C:(j + 1) * C].astype(np.float64)
+    T = snake64(acc + b7, s2a, s2b)
+    y = R.astype(np.float64) + T @ W1.astype(np.float64) + b1
+    return y, snake64(y, sna, snb)
+
+
+def make_case(C, L, B, dil, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((B, L, C)).astype(np.float32)
+    s1a = np.exp(rng.normal(0, 0.1, C)).astype(np.float32)
+    s1b = (1.0 / (np.exp(rng.normal(0, 0.1, C)) + 1e-9)).astype(np.float32)
+    A = snake64(x.astype(np.float64), s1a, s1b).astype(np.float32)
+    W7 = (rng.standard_normal((7 * C, C)) / np.sqrt(7 * C)).astype(np.float32)
+    W1 = (rng.standard_normal((C, C)) / np.sqrt(C) * 0.5).astype(np.float32)
+    b7 = rng.normal(0, 0.01, C).astype(np.float32)
+    b1 = rng.normal(0, 0.01, C).astype(np.float32)
+    f = lambda: np.exp(rng.normal(0, 0.1, C)).astype(np.float32)
+    g = lambda: (1.0 / (np.exp(rng.normal(0, 0.1, C)) + 1e-9)).astype(np.float32)
+    return dict(A=A, W7=W7, b7=b7, sn2_a=f(), sn2_invb=g(), W1=W1, b1=b1, R=x, snn_a=f(), snn_invb=g(), dil=dil)
+
+
+CASES = [(96, 300, 2, 1), (96, 1000, 3, 3), (96, 777, 2, 9), (192, 300, 2, 1), (192, 1000, 2, 3), (192, 641, 3, 9),
+         (96, 129, 1, 9), (192, 4096, 1, 9)]
+
+
+@pytest.mark.parametrize("C,L,B,dil", CASES)
+def test_fused_unit_matches_float64_and_the_two_launch_path(backend, C, L, B, dil):
+    k = make_case(C, L, B, dil, seed=C + L + dil)
+    rc, Yf, Sf, _ = backend.test_ru(1, **k)
+    assert rc == 0, rc
+    rc, Yu, Su, _ = backend.test_ru(0, **k)
+    assert rc == 0, rc
+    y_ref, s_ref = ref_unit(k["A"], k["W7"], k["b7"], k["sn2_a"], k["sn2_invb"], k["W1"], k["b1"], k["R"],
+                            k["snn_a"], k["snn_invb"], dil)
+    ey, es = float(np.abs(Yf - y_ref).max()), float(np.abs(Sf - s_ref).max())
+    print(f"C={C} L={L} B={B} d={dil}: max-abs Y {ey:.2e} S {es:.2e} (|y| max {float(np.abs(y_ref).max()):.2f}); "
+          f"bit-equal to two launches: Y {np.array_equal(Yf, Yu)} S {np.array_equal(Sf, Su)}")
+    assert ey < 2e-5 and es < 3e-5
+    assert np.array_equal(Yf, Yu) and np.array_equal(Sf, Su)
+
+
+def test_fused_unit_without_the_float32_output(backend):
+    """The last unit of a block emits only the next layer's operand."""
+    k = make_case(96, 500, 2, 3, seed=4)
+    rc, Y, S1, _ = backend.test_ru(1, want_y=False, **k)
+    assert rc == 0 and Y is None
+    rc, _, S2, _ = backend.test_ru(1, **k)
+    assert np.array_equal(S1, S2)
+
+
+def test_shapes_the_fused_kernel_does_not_take(backend):
+    k = make_case(64, 300, 1, 1, seed=1)
+    rc, *_ = backend.test_ru(1, **k)
+    assert rc == 1
+    k = make_case(96, 100, 1, 1, seed=1)              # a single M tile: the pair form does not apply
+    rc, *_ = backend.test_ru(1, **k)
+    assert rc == 1
