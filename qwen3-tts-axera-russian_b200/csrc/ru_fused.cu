@@ -22,9 +22,15 @@
 // The arithmetic -- segment schedule, pass order, k-step order, epilogue formulas -- is that of the two unfused
 // launches, so the results are bit-identical to them (tests/test_gpu_ru_fused.py).
 //
-// C = 192: T (96 KB as two fp16 planes) does not fit next to a double-buffered 2 x 48 KB halo ring and the weight
-// ring, so there (ALIAS) T overlays the halo ring: the issuing warp holds back the ring's last hand-backs of a tile
-// until the 1x1 chain is issued, i.e. the producer's prefetch of the next tile's halo waits for it.
+// Order of work (PIPE, C = 96): the issuing warp runs conv7 of tile i+1 BEFORE the 1x1 chain of tile i, and the
+// epilogue warps run  drain7(i+1) -> drain1(i) + final(i) -> Snake/split(i+1) -> T,  so that the tensor pipe works on
+// tile i+1 while the epilogue warps finish tile i: neither waits for the other's whole phase.  The conv7 sums of tile
+// i+1 wait in registers meanwhile, which is why the 1x1 accumulator is drained 16 columns at a time there.
+// C = 192 keeps the simple order (conv7(i), T(i), conv1(i)): its 64 columns per thread do not leave registers for a
+// second tile, and its tensor time per tile (28 k cycles) is twice its epilogue time anyway.
+// C = 192, dilation 9: T (96 KB as two fp16 planes) does not fit next to a double-buffered 2 x 47 KB halo ring and the
+// weight ring, so there (ALIAS) T overlays the halo ring: the issuing warp holds back the ring's last hand-backs of a
+// tile until the 1x1 chain is issued, i.e. the producer's prefetch of the next tile's halo waits for it.
 #include "voc_common.cuh"
 #include "tc_ptx.cuh"
 
@@ -74,17 +80,17 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-template <int BN, int CP, bool ALIAS>
+template <int BN, int CP, bool ALIAS, bool PIPE>
 __global__ void __launch_bounds__(64 + 128 * CP, 1)
 ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmW1,
                 const __grid_constant__ CUtensorMap tmW1b, const __grid_constant__ FuArgs a) {
     static_assert(BN == 96 || BN == 192, "the decoder blocks with C <= 192");
     static_assert((BN / CP) % 16 == 0, "the epilogue handles 16 operand columns (one 32-byte sector) at a time");
+    static_assert(!(ALIAS && PIPE), "the pipelined order keeps the halo ring busy while T is live");
     constexpr int BK = 64;
     constexpr int EPI_WARPS = 4 * CP;
     constexpr int HN = BN / CP;                               // columns per epilogue thread
-    constexpr int PB = HN <= 32 ? HN : 16;                    // residual prefetch window (columns)
     constexpr uint32_t ROWB = BK * 2;
     constexpr bool CAT = BN <= 128;                           // see tc_gemm.cu: A_hi x [B_hi; B_lo] as one N = 2 BN MMA
     constexpr int BROWS = BN / 2;
@@ -140,7 +146,10 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == 0) {
         // ================================ TMA producer ================================
         int sa = 0, pa = 0, sb = 0, pb = 0;
-        for (int tile = walker; tile < a.total_tiles; tile += walkers) {
+        const int n_my = walker < a.total_tiles ? (a.total_tiles - walker + walkers - 1) / walkers : 0;
+        for (int s = 0; s < n_my + (PIPE ? 1 : 0); ++s) {
+          if (!PIPE || s < n_my) {
+            const int tile = walker + s * walkers;
             const int m_tile = 2 * (tile % a.m_tiles) + (int)rank, b = tile / a.m_tiles;
             const int row0 = m_tile * BM + a.a_min_off;
             const int n0 = CAT ? 0 : (int)rank * BROWS;
@@ -168,7 +177,10 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     if (++sb == a.SB) { sb = 0; pb ^= 1; }
                 }
             }
+          }
+          if (!PIPE || s > 0) {
             // the 1x1 weights, chunk by chunk, through the same ring
+            const int n0 = CAT ? 0 : (int)rank * BROWS;
             for (int kc = 0; kc < NKC2; ++kc) {
                 mbar_wait(&bar_b_empty[sb], pb ^ 1);
                 if (elect_one()) {
@@ -183,6 +195,7 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
                 if (++sb == a.SB) { sb = 0; pb ^= 1; }
             }
+          }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer (leader) =========================
@@ -206,8 +219,11 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t a2_desc0 = reg(smem_desc_lo(smA2));
             int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pas = 0, p_a2 = 0;
             uint32_t b_lo = b_desc0;
-            for (int tile = walker; tile < a.total_tiles; tile += walkers) {
-                uint32_t tmem_acc = 0, accum = 0;
+            const int n_my = walker < a.total_tiles ? (a.total_tiles - walker + walkers - 1) / walkers : 0;
+            for (int s = 0; s < n_my + (PIPE ? 1 : 0); ++s) {
+              uint32_t tmem_acc = 0;
+              if (!PIPE || s < n_my) {
+                uint32_t accum = 0;
                 int seg_left = 0, iters_left = ipt, seg_idx = 0;
                 for (int fill = 0; fill < n_fills; ++fill) {
                     mbar_spin_a(a_full0 + 8 * sa, pa);
@@ -272,6 +288,8 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     }
                     if (++sa == SA) { sa = 0; pa ^= 1; }
                 }
+              }
+              if (!PIPE || s > 0) {
                 // ---- the 1x1 convolution on the T tiles both CTAs' epilogue warps have written to shared memory
                 mbar_spin_acq_cluster(a2_full, (uint32_t)p_a2);
                 p_a2 ^= 1;
@@ -320,13 +338,14 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if constexpr (ALIAS) {
                     // now the halo ring may be refilled: hand back the stages held since the conv7 loop
                     const int held = n_fills < SA ? n_fills : SA;
-                    int s = sa - held; if (s < 0) s += SA;
+                    int hs = sa - held; if (hs < 0) hs += SA;
                     for (int i = 0; i < held; ++i) {
-                        if (elect_one()) mma2_commit_both_a(a_empty0 + 8 * s);
+                        if (elect_one()) mma2_commit_both_a(a_empty0 + 8 * hs);
                         __syncwarp();
-                        if (++s == SA) s = 0;
+                        if (++hs == SA) hs = 0;
                     }
                 }
+              }
             }
         }
     } else {
@@ -354,11 +373,13 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t trow = (uint32_t)(q * 32 + lane);                        // row of the tile this thread owns
         const uint32_t t_row_addr = smA2 + trow * ROWB;
         const uint32_t sw = trow & 7u;                                          // 128B swizzle: 16-byte granule ^= row % 8
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)n0;
 
+        // one accumulator buffer of the ring -> registers (added in FP32, round-to-nearest), buffer handed back
         auto drain = [&](float (&acc)[HN], bool first) {
             mbar_wait(&bar_acc_full[as], pas);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * ACC_COLS + (uint32_t)n0;
+            const uint32_t taddr = tlane + (uint32_t)as * ACC_COLS;
             if constexpr (CAT) {
 #pragma unroll
                 for (int c0 = 0; c0 < HN / 8; c0 += 2) {
@@ -373,7 +394,7 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const float v = __uint_as_float(tm[c][j]) + __uint_as_float(tc[c][j]);
-                                acc[(c0 + c) * 8 + j] = first ? 0.f + v : acc[(c0 + c) * 8 + j] + v;
+                                acc[(c0 + c) * 8 + j] = first ? v : acc[(c0 + c) * 8 + j] + v;
                             }
                         }
                 }
@@ -400,7 +421,7 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const float v = __uint_as_float(tr[c][j]);
-                                acc[(c0 + c) * 8 + j] = first ? 0.f + v : acc[(c0 + c) * 8 + j] + v;
+                                acc[(c0 + c) * 8 + j] = first ? v : acc[(c0 + c) * 8 + j] + v;
                             }
                         }
                 }
@@ -408,16 +429,10 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (++as == NBUF) { as = 0; pas ^= 1; }
         };
 
-        for (int tile = walker; tile < a.total_tiles; tile += walkers) {
-            const int m_tile = 2 * (tile % a.m_tiles) + (int)rank, b = tile / a.m_tiles;
-            const int m = m_tile * BM + (int)trow;
-            const bool valid = m < a.M;
-            float acc[HN];
-            // ---- conv7 accumulation segments (added in FP32 with round-to-nearest, as in the unfused kernel)
-            for (int seg = 0; seg < nseg; ++seg) drain(acc, seg == 0);
-            // ---- T = Snake2(conv7 + b7) -> split fp16 -> this thread's row of the T tile in shared memory.
-            // The previous tile's 1x1 chain has finished reading the tile: this thread waited for that chain's
-            // accumulator (and, with ALIAS, every conv7 MMA that read the halo ring is in the segments just drained).
+        // T = Snake2(conv7 + b7) -> split fp16 -> this thread's row of the T tile in shared memory, then the hand-over
+        // to the issuing warp.  The previous 1x1 chain has finished reading the tile: this thread has drained that
+        // chain's accumulator (and, with ALIAS, every conv7 MMA that read the halo ring is in the segments just drained).
+        auto emit_t = [&](const float (&acc)[HN]) {
 #pragma unroll
             for (int g16 = 0; g16 < HN; g16 += 16) {
                 uint32_t hi16[8], lo16[8];
@@ -460,57 +475,105 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core's reads
             __syncwarp();
             if (lane == 0) mbar_arrive_release_cluster(a2_full_leader);
-            // ---- the residual row does not depend on the MMAs: its loads fly while the 1x1 chain runs
-            const float* Rrow = valid ? a.R + (long long)b * a.r_bstride + (long long)m * a.ldr + n0 : nullptr;
-            float rpf[2][PB / 8][8];
-            if (Rrow) {
+        };
+
+        // 16 columns of the unit's output: x' = conv1 * 2^-e + b1 + x -> Y; Snake_next, split -> S
+        auto final16 = [&](const float* v16, int g16, const float (&res)[2][8], float* Yrow, long long soff) {
+            uint32_t hi16[8], lo16[8];
 #pragma unroll
-                for (int i = 0; i < PB / 8; ++i) ldg256(Rrow + 8 * i, rpf[0][i]);
-            }
-            // ---- the 1x1 accumulator (one segment: at most 12 MMAs into it)
-            drain(acc, true);
-            if (!valid) continue;
-            float* Yrow = a.Y ? a.Y + (long long)b * a.y_bstride + (long long)m * a.ldy + n0 : nullptr;
-            const long long soff = (long long)b * a.s_bstride + (long long)m * a.lds + n0;
+            for (int gg = 0; gg < 16; gg += 8) {
+                const int pc = n0 + g16 + gg;
+                float v[8];
 #pragma unroll
-            for (int g16 = 0; g16 < HN; g16 += 16) {
-                uint32_t hi16[8], lo16[8];
+                for (int j = 0; j < 8; ++j) v[j] = v16[gg + j] * a.wscale1;
+                const float4 b0 = *reinterpret_cast<const float4*>(&epi_par[3][pc]);
+                const float4 b1 = *reinterpret_cast<const float4*>(&epi_par[3][pc + 4]);
+                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
 #pragma unroll
-                for (int g = g16; g < g16 + 16; g += 8) {
-                    const int pc = n0 + g;
-                    const int pcur = (g / PB) & 1;
-                    if ((g % PB) == 0 && g + PB < HN) {
+                for (int j = 0; j < 8; ++j) v[j] += res[gg / 8][j];
+                if (Yrow) stg256(Yrow + g16 + gg, v);
+                const float4 a0 = *reinterpret_cast<const float4*>(&epi_par[4][pc]);
+                const float4 a1 = *reinterpret_cast<const float4*>(&epi_par[4][pc + 4]);
+                const float4 i0 = *reinterpret_cast<const float4*>(&epi_par[5][pc]);
+                const float4 i1 = *reinterpret_cast<const float4*>(&epi_par[5][pc + 4]);
+                v[0] = voc_snake(v[0], a0.x, i0.x); v[1] = voc_snake(v[1], a0.y, i0.y);
+                v[2] = voc_snake(v[2], a0.z, i0.z); v[3] = voc_snake(v[3], a0.w, i0.w);
+                v[4] = voc_snake(v[4], a1.x, i1.x); v[5] = voc_snake(v[5], a1.y, i1.y);
+                v[6] = voc_snake(v[6], a1.z, i1.z); v[7] = voc_snake(v[7], a1.w, i1.w);
 #pragma unroll
-                        for (int i = 0; i < PB / 8; ++i) ldg256(Rrow + g + PB + 8 * i, rpf[pcur ^ 1][i]);
-                    }
-                    float v[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = acc[g + j] * a.wscale1;
-                    const float4 b0 = *reinterpret_cast<const float4*>(&epi_par[3][pc]);
-                    const float4 b1 = *reinterpret_cast<const float4*>(&epi_par[3][pc + 4]);
-                    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] += rpf[pcur][(g % PB) / 8][j];
-                    if (Yrow) stg256(Yrow + g, v);
-                    const float4 a0 = *reinterpret_cast<const float4*>(&epi_par[4][pc]);
-                    const float4 a1 = *reinterpret_cast<const float4*>(&epi_par[4][pc + 4]);
-                    const float4 i0 = *reinterpret_cast<const float4*>(&epi_par[5][pc]);
-                    const float4 i1 = *reinterpret_cast<const float4*>(&epi_par[5][pc + 4]);
-                    v[0] = voc_snake(v[0], a0.x, i0.x); v[1] = voc_snake(v[1], a0.y, i0.y);
-                    v[2] = voc_snake(v[2], a0.z, i0.z); v[3] = voc_snake(v[3], a0.w, i0.w);
-                    v[4] = voc_snake(v[4], a1.x, i1.x); v[5] = voc_snake(v[5], a1.y, i1.y);
-                    v[6] = voc_snake(v[6], a1.z, i1.z); v[7] = voc_snake(v[7], a1.w, i1.w);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        __half2 hh, ll;
-                        voc_split2(v[2 * j], v[2 * j + 1], hh, ll);
-                        hi16[(g - g16) / 2 + j] = *reinterpret_cast<uint32_t*>(&hh);
-                        lo16[(g - g16) / 2 + j] = *reinterpret_cast<uint32_t*>(&ll);
-                    }
+                for (int j = 0; j < 4; ++j) {
+                    __half2 hh, ll;
+                    voc_split2(v[2 * j], v[2 * j + 1], hh, ll);
+                    hi16[gg / 2 + j] = *reinterpret_cast<uint32_t*>(&hh);
+                    lo16[gg / 2 + j] = *reinterpret_cast<uint32_t*>(&ll);
                 }
-                stg256u(a.S_hi + soff + g16, hi16);
-                stg256u(a.S_lo + soff + g16, lo16);
+            }
+            stg256u(a.S_hi + soff + g16, hi16);
+            stg256u(a.S_lo + soff + g16, lo16);
+        };
+
+        // the 1x1 accumulator of `tile` -> its output rows
+        auto finish_tile = [&](int tile, float (&acc)[HN]) {
+            const int m_tile = 2 * (tile % a.m_tiles) + (int)rank, b = tile / a.m_tiles;
+            const int m = m_tile * BM + (int)trow;
+            const bool valid = m < a.M;
+            // the residual row does not depend on the MMAs: its first loads fly while the 1x1 chain runs
+            const float* Rrow = a.R + (long long)b * a.r_bstride + (long long)(valid ? m : 0) * a.ldr + n0;
+            float* Yrow = (a.Y && valid) ? a.Y + (long long)b * a.y_bstride + (long long)m * a.ldy + n0 : nullptr;
+            const long long soff = (long long)b * a.s_bstride + (long long)m * a.lds + n0;
+            float res[2][2][8];                       // two 16-column windows of the residual row, alternating
+            if (valid) { ldg256(Rrow, res[0][0]); ldg256(Rrow + 8, res[0][1]); }
+            if constexpr (PIPE) {
+                // 16 columns at a time straight from TMEM (main + correction block): the conv7 sums of the next tile
+                // occupy the registers a whole-row drain would need
+                mbar_wait(&bar_acc_full[as], pas);
+                tc_fence_after();
+                const uint32_t taddr = tlane + (uint32_t)as * ACC_COLS;
+#pragma unroll
+                for (int g16 = 0; g16 < HN; g16 += 16) {
+                    uint32_t tm[2][8], tc[2][8];
+                    tmem_ld8(taddr + g16, tm[0]); tmem_ld8(taddr + g16 + 8, tm[1]);
+                    tmem_ld8(taddr + BN + g16, tc[0]); tmem_ld8(taddr + BN + g16 + 8, tc[1]);
+                    if (valid && g16 + 16 < HN) { ldg256(Rrow + g16 + 16, res[((g16 >> 4) & 1) ^ 1][0]); ldg256(Rrow + g16 + 24, res[((g16 >> 4) & 1) ^ 1][1]); }
+                    tmem_ld_wait();
+                    if (g16 + 16 >= HN) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(acc_empty_leader[as]);
+                    }
+                    float v16[16];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        v16[j] = __uint_as_float(tm[0][j]) + __uint_as_float(tc[0][j]);
+                        v16[8 + j] = __uint_as_float(tm[1][j]) + __uint_as_float(tc[1][j]);
+                    }
+                    if (valid) final16(v16, g16, res[(g16 >> 4) & 1], Yrow, soff);
+                }
+                if (++as == NBUF) { as = 0; pas ^= 1; }
+            } else {
+                drain(acc, true);                    // (the conv7 sums in these registers have been emitted)
+                if (!valid) return;
+#pragma unroll
+                for (int g16 = 0; g16 < HN; g16 += 16) {
+                    if (g16 + 16 < HN) { ldg256(Rrow + g16 + 16, res[((g16 >> 4) & 1) ^ 1][0]); ldg256(Rrow + g16 + 24, res[((g16 >> 4) & 1) ^ 1][1]); }
+                    final16(&acc[g16], g16, res[(g16 >> 4) & 1], Yrow, soff);
+                }
+            }
+        };
+
+        const int n_my = walker < a.total_tiles ? (a.total_tiles - walker + walkers - 1) / walkers : 0;
+        float acc7[HN];
+        for (int s = 0; s < n_my + (PIPE ? 1 : 0); ++s) {
+            const bool do7 = !PIPE || s < n_my;
+            // ---- conv7 accumulation segments of tile s (added in FP32 with round-to-nearest, as in the unfused kernel)
+            if (do7) for (int seg = 0; seg < nseg; ++seg) drain(acc7, seg == 0);
+            if constexpr (!PIPE) {
+                emit_t(acc7);
+                finish_tile(walker + s * walkers, acc7);
+            } else {
+                if (s > 0) finish_tile(walker + (s - 1) * walkers, acc7);
+                if (do7) emit_t(acc7);
             }
         }
     }
@@ -521,14 +584,14 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == 1) tmem_dealloc2(tmem_base, TMEM_COLS);
 }
 
-template <int BN, int CP, bool ALIAS>
+template <int BN, int CP, bool ALIAS, bool PIPE>
 cudaError_t launch_fused(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB2, const CUtensorMap& tmW1,
                          const CUtensorMap& tmW1b, const FuArgs& a, int grid, size_t smem, cudaStream_t st) {
     static std::atomic<bool> attr_done[FU_MAX_DEVICES];
     int dev = -1;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= FU_MAX_DEVICES) return cudaErrorInvalidDevice;
     if (!attr_done[dev].load(std::memory_order_acquire)) {
-        cudaError_t e = cudaFuncSetAttribute(ru_fused_kernel<BN, CP, ALIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(ru_fused_kernel<BN, CP, ALIAS, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              SMEM_BUDGET + 1024);
         if (e != cudaSuccess) return e;
         attr_done[dev].store(true, std::memory_order_release);
@@ -539,7 +602,7 @@ cudaError_t launch_fused(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, ru_fused_kernel<BN, CP, ALIAS>, tmA, tmB, tmB2, tmW1, tmW1b, a);
+    return cudaLaunchKernelEx(&cfg, ru_fused_kernel<BN, CP, ALIAS, PIPE>, tmA, tmB, tmB2, tmW1, tmW1b, a);
 }
 
 struct FuPlan { int box_rows, SA, SB; bool alias; size_t smem; };
@@ -548,16 +611,17 @@ bool plan_fused(const RuFusedParams& p, FuPlan& pl) {
     const int BN = p.C, BK = 64;
     const bool cat = BN <= 128;
     const int span = (p.ksz - 1) * p.dil;
-    pl.box_rows = ((BM + span + 15) / 16) * 16;
+    pl.box_rows = ((BM + span + 7) / 8) * 8;                 // whole 8-row swizzle groups
     if (pl.box_rows > 256) return false;                     // one TMA box
     const int a_stage = 2 * pl.box_rows * BK * 2;
     const int b_stage = cat ? (BN + BN / 2) * BK * 2 : 2 * (BN / 2) * BK * 2;
     const int nkc2 = (BN + 63) / 64;
     const int a2 = 2 * nkc2 * BM * BK * 2;
     pl.SA = 2;
-    // T next to the halo ring where that leaves at least three weight stages, else overlaid on it
+    // T next to the halo ring where that leaves at least two weight stages (a stage holds 450-1150 cycles of MMAs and
+    // is refilled from L2; round 1 measured no difference between 2 and 8 stages), else overlaid on the ring
     int left = SMEM_BUDGET - pl.SA * a_stage - a2;
-    pl.alias = left < 3 * b_stage;
+    pl.alias = left < 2 * b_stage;
     if (pl.alias) left = SMEM_BUDGET - std::max(pl.SA * a_stage, a2);
     pl.SB = std::min(MAX_STAGES, left / b_stage);
     if (pl.SB < 2) return false;
@@ -633,10 +697,12 @@ cudaError_t voc_launch_ru_fused(const RuFusedParams& p, cudaStream_t st, int num
 
     const int sms = num_sms > 0 ? num_sms : 148;
     const int grid = 2 * std::min(a.total_tiles, sms / 2);
+    const bool pipe = !pl.alias && BN == 96 && !(flags & VOC_TC_NO_PIPE);
     if (BN == 96) {
-        return pl.alias ? launch_fused<96, 3, true>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st)
-                        : launch_fused<96, 3, false>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st);
+        if (pl.alias) return launch_fused<96, 3, true, false>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st);
+        return pipe ? launch_fused<96, 3, false, true>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st)
+                    : launch_fused<96, 3, false, false>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st);
     }
-    return pl.alias ? launch_fused<192, 3, true>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st)
-                    : launch_fused<192, 3, false>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st);
+    return pl.alias ? launch_fused<192, 3, true, false>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st)
+                    : launch_fused<192, 3, false, false>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st);
 }

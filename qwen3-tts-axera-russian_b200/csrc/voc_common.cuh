@@ -53,52 +53,53 @@ struct TapGemmParams {
     float* Y;        long long y_bstride;  int ldy;
     float* S;        long long s_bstride;  int lds;
     __half* S_hi;  __half* S_lo;                // split-fp16 form of S (same strides)
-    const float* sn_a;  const float* sn_invb;   // [N]: exp(alpha), 1/(exp(beta)+eps); null = S is v itself
+    const float* sn_a;  const float* sn_invb;   // [N]: 2*exp(alpha), 1/(exp(beta)+eps); null = S is v itself
     // tensor-core form of the weights (tc_gemm.cu): two fp16 planes [2][ntaps][N][K] of W * 2^wexp
     const __half* Wtc;  long long wtc_plane;  float wscale;   // wscale = 2^-wexp
 };
 
 enum { VOC_ACT_NONE = 0, VOC_ACT_GELU = 1 };
 
-// sin^2(t), absolute error <= 3e-7 for |t| < 1e4.  sin^2 has period pi, so one Cody-Waite
-// reduction to r in [-pi/2, pi/2] and an even polynomial in r^2 -- no quadrant logic.
-__device__ __forceinline__ float voc_sin2(float t) {
-    const float k = rintf(t * 0.31830988618379067f);
-    float r = fmaf(-k, 3.140625f, t);
-    r = fmaf(-k, 0.0009670257568359375f, r);
-    r = fmaf(-k, 6.278329465203569e-07f, r);
-    const float u = r * r;
-    float p = 8.086376368510173e-08f;
-    p = fmaf(p, u, -4.2304154703742824e-06f);
-    p = fmaf(p, u, 0.00014101542183198035f);
-    p = fmaf(p, u, -0.0031745336018502712f);
-    p = fmaf(p, u, 0.04444441571831703f);
-    p = fmaf(p, u, -0.3333333432674408f);
-    p = fmaf(p, u, 1.0f);
-    return p * u;
+// SnakeBeta: x + 1/(e^beta + eps) * sin^2(x * e^alpha)  (sibling :3645-3683).
+// Device convention: the per-channel arrays hold a2 = 2 * e^alpha and invb = 1/(e^beta + eps) (make_snake in
+// voc_engine.cu), because sin^2(t) = 0.5 - 0.5 cos(2t): the doubled argument is reduced to [-pi, pi] by a two-term
+// Cody-Waite step (round-to-nearest by the 1.5 * 2^23 trick, two FMAs) and the cosine is one SFU evaluation
+// (cos.approx: max abs error 2^-21.19 on [-pi, pi], CUDA C Programming Guide; i.e. <= 2.2e-7 on sin^2, measured in
+// tests/test_gpu_tapgemm.py::test_snake_accuracy).  9 instructions per element against 16 for the round-1
+// polynomial: the epilogue warps of the tensor-core kernels are issue-bound.
+__device__ __forceinline__ float voc_sin2_half(float t2) {
+    const float k = fmaf(t2, 0.15915494309189535f, 12582912.f) - 12582912.f;     // rint(t2 / 2 pi), |t2| < 2^22
+    float r = fmaf(-k, 6.2831854820251465f, t2);
+    r = fmaf(-k, -1.7484555e-07f, r);
+    return fmaf(-0.5f, __cosf(r), 0.5f);
 }
-
-// SnakeBeta with pre-exponentiated parameters: x + invb * sin^2(a*x)
-__device__ __forceinline__ float voc_snake(float x, float a, float invb) {
-    return fmaf(invb, voc_sin2(x * a), x);
+__device__ __forceinline__ float voc_snake(float x, float a2, float invb) {
+    return fmaf(invb, voc_sin2_half(x * a2), x);
 }
 
 __device__ __forceinline__ float voc_gelu(float x) {
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
 }
 
-// fp32 -> (hi, lo) float16 pair; saturating so that a stray huge activation cannot become inf
+// fp32 -> (hi, lo) float16 pair.  The conversions saturate to the largest finite fp16 (F2FP.SATFINITE), so a stray
+// huge activation cannot become inf; no separate clamp instructions.
+__device__ __forceinline__ uint32_t voc_cvt_f16x2_sat(float a, float b) {
+    uint32_t h;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %2, %1;" : "=r"(h) : "f"(a), "f"(b));      // low half = a
+    return h;
+}
 __device__ __forceinline__ void voc_split2(float a, float b, __half2& hi, __half2& lo) {
-    a = fminf(65504.f, fmaxf(-65504.f, a));
-    b = fminf(65504.f, fmaxf(-65504.f, b));
-    hi = __floats2half2_rn(a, b);
-    const float2 h = __half22float2(hi);
-    lo = __floats2half2_rn(a - h.x, b - h.y);
+    const uint32_t h = voc_cvt_f16x2_sat(a, b);
+    hi = *reinterpret_cast<const __half2*>(&h);
+    const float2 f = __half22float2(hi);
+    const uint32_t l = voc_cvt_f16x2_sat(a - f.x, b - f.y);
+    lo = *reinterpret_cast<const __half2*>(&l);
 }
 __device__ __forceinline__ void voc_split1(float a, __half& hi, __half& lo) {
-    a = fminf(65504.f, fmaxf(-65504.f, a));
-    hi = __float2half_rn(a);
-    lo = __float2half_rn(a - __half2float(hi));
+    __half2 h2, l2;
+    voc_split2(a, 0.f, h2, l2);
+    hi = __low2half(h2);
+    lo = __low2half(l2);
 }
 
 // An activation tensor as the kernels see it: float32 (f) or split float16 (hi, lo).
@@ -136,7 +137,7 @@ cudaError_t voc_launch_ru_fused(const RuFusedParams& p, cudaStream_t st, int num
 // bit 4 no double-length head segments, bit 6 / bit 7 always / never cta_group::2 pairs, bits 8.. MMAs into the main
 // accumulator per round-to-nearest flush (default 24)
 enum { VOC_TC_NO_REUSE = 1, VOC_TC_BK64 = 2, VOC_TC_BK32 = 4, VOC_TC_GENERIC_EPI = 8, VOC_TC_NO_SEG_HEAD = 16,
-       VOC_TC_FORCE_PAIR = 64, VOC_TC_NO_PAIR = 128 };
+       VOC_TC_NO_PIPE = 32 /* fused residual unit: simple order of work */, VOC_TC_FORCE_PAIR = 64, VOC_TC_NO_PAIR = 128 };
 
 // host-side launch wrappers (simt_kernels.cu)
 cudaError_t voc_launch_tapgemm_simt(const TapGemmParams& p, cudaStream_t st);

@@ -374,7 +374,7 @@ static bool make_snake(Engine* E, const std::string& p, int C, int tile, SnakeP&
     auto* be = get_raw(E, p + ".beta", C); if (!be) return false;
     std::vector<float> a((size_t)C * tile), ib((size_t)C * tile);
     for (int r = 0; r < tile; ++r) for (int c = 0; c < C; ++c) {
-        a[(size_t)r * C + c] = expf((*al)[c]);
+        a[(size_t)r * C + c] = 2.0f * expf((*al)[c]);      // device convention: the doubled argument (voc_common.cuh)
         ib[(size_t)r * C + c] = 1.0f / (expf((*be)[c]) + (float)E->cfg.snake_eps);
     }
     sp.a = upload(E, a); sp.invb = upload(E, ib);
@@ -1642,7 +1642,13 @@ int voc_test_tapgemm(int device, int mode, int tc_flags, int B, int a_rows, int 
     g.bias = up(bias, N);
     float* d_scale = up(scale, N);
     float* d_R = up(R, (size_t)B * M * N);
-    SnakeP sp; sp.a = up(sn_a, N); sp.invb = up(sn_invb, N);
+    auto up_doubled = [&](const float* h, size_t n) -> float* {      // device convention: 2 * e^alpha
+        if (!h) return nullptr;
+        std::vector<float> v(h, h + n);
+        for (auto& x : v) x *= 2.0f;
+        return upload(E, v);
+    };
+    SnakeP sp; sp.a = up_doubled(sn_a, N); sp.invb = up(sn_invb, N);
     const size_t na = ((size_t)B * a_rows * K + 63) / 64 * 64, no = ((size_t)B * M * N + 63) / 64 * 64;
     float *dA = nullptr, *dY = nullptr, *dS = nullptr;
     CK(cudaMalloc(&dA, na * 4)); E->owned.push_back(dA); E->cap[dA] = na;
@@ -1724,7 +1730,12 @@ int voc_test_ru(int device, int fused, int tc_flags, int B, int L, int C, int ks
     if (!g7.W || !g1.W || !make_wtc(E, w7, g7) || !make_wtc(E, w1, g1)) return fail(E, VOC_E_CUDA, "weight upload failed");
     auto up = [&](const float* h, size_t n) -> float* { return upload(E, std::vector<float>(h, h + n)); };
     g7.bias = up(b7, C); g1.bias = up(b1, C);
-    SnakeP s2, sn; s2.a = up(sn2_a, C); s2.invb = up(sn2_invb, C); sn.a = up(snn_a, C); sn.invb = up(snn_invb, C);
+    auto up_doubled = [&](const float* h, size_t n) -> float* {      // device convention: 2 * e^alpha
+        std::vector<float> v(h, h + n);
+        for (auto& x : v) x *= 2.0f;
+        return upload(E, v);
+    };
+    SnakeP s2, sn; s2.a = up_doubled(sn2_a, C); s2.invb = up(sn2_invb, C); sn.a = up_doubled(snn_a, C); sn.invb = up(snn_invb, C);
     const size_t ne = (size_t)B * L * C, na = (ne + 63) / 64 * 64;
     float* dR = up(R, ne);
     float *dA = nullptr, *dT = nullptr, *dY = nullptr, *dS = nullptr, *tmp = nullptr;

@@ -44,7 +44,7 @@ def make_case(C, L, B, dil, seed):
 
 
 CASES = [(96, 300, 2, 1), (96, 1000, 3, 3), (96, 777, 2, 9), (192, 300, 2, 1), (192, 1000, 2, 3), (192, 641, 3, 9),
-         (96, 129, 1, 9), (192, 4096, 1, 9)]
+         (96, 129, 1, 9), (192, 4096, 1, 9), (96, 40000, 2, 9), (192, 20000, 2, 3)]       # the last two: many tiles per CTA pair
 
 
 @pytest.mark.parametrize("C,L,B,dil", CASES)
@@ -61,6 +61,9 @@ def test_fused_unit_matches_float64_and_the_two_launch_path(backend, C, L, B, di
           f"bit-equal to two launches: Y {np.array_equal(Yf, Yu)} S {np.array_equal(Sf, Su)}")
     assert ey < 2e-5 and es < 3e-5
     assert np.array_equal(Yf, Yu) and np.array_equal(Sf, Su)
+    # the simple order of work (tc_flags bit 5: no software pipelining across tiles) gives the same bits
+    rc, Yn, Sn, _ = backend.test_ru(1, tc_flags=32, **k)
+    assert rc == 0 and np.array_equal(Yf, Yn) and np.array_equal(Sf, Sn)
 
 
 def test_fused_unit_without_the_float32_output(backend):

@@ -141,3 +141,25 @@ def test_ineligible_shape_is_reported(backend):
     assert rc == 0
     v_ref, _ = ref_tapgemm(A, W, [0], 40, 0)
     assert float(np.abs(Y - v_ref).max()) < 2e-5
+
+
+def test_snake_accuracy():
+    """SnakeBeta on the device (csrc/voc_common.cuh: two-term Cody-Waite reduction of the doubled argument + SFU cosine)
+    against float64 x + invb * sin^2(a x), isolated from everything else: identity weights and inputs
+    that are exact in fp16, through the FP32 CUDA-core kernel whose S output is plain float32.  Arguments up to
+    |a x| = 40 exercise the range reduction."""
+    import importlib
+    backend = importlib.import_module("qwen3-tts-axera-russian_b200.backend")
+    rng = np.random.default_rng(12)
+    K = 32
+    A = (rng.integers(-256, 257, (2, 512, K)) / 64.0).astype(np.float32)           # multiples of 2^-6 in [-4, 4]
+    W = np.eye(K, dtype=np.float32)
+    sn_a = np.linspace(0.25, 10.0, K).astype(np.float32)
+    sn_invb = np.ones(K, dtype=np.float32)
+    rc, _, S, _ = backend.test_tapgemm(0, A, W, [0], 512, 0, sn_a=sn_a, sn_invb=sn_invb, want_y=False, want_s=True)
+    assert rc == 0
+    x = A.astype(np.float64)
+    ref = x + np.sin(x * sn_a.astype(np.float64)) ** 2
+    err = float(np.abs(S - ref).max())
+    print(f"snake max abs error {err:.3e} (|a x| up to {float(np.abs(x * sn_a).max()):.1f})")
+    assert err < 6e-7          # 2.2e-7 from the SFU cosine + float32 rounding of a result of magnitude <= 5
