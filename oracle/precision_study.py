@@ -42,12 +42,21 @@ def _split(x: torch.Tensor, kind: str):
     return hi, lo
 
 
+def _round_mant(x: torch.Tensor, bits: int) -> torch.Tensor:
+    """Round-to-nearest-even to `bits` explicit mantissa bits, unlimited exponent range: the BEST case of an 8-bit
+    float operand (e4m3: bits = 3, e5m2: bits = 2) under ideal power-of-two scaling of the plane."""
+    sh = 23 - bits
+    i = x.contiguous().view(torch.int32)
+    r = ((i >> sh) & 1) + ((1 << (sh - 1)) - 1)
+    return ((i + r) & ~((1 << sh) - 1)).view(torch.float32)
+
+
 class SplitF(types.SimpleNamespace):
     """Stand-in for torch.nn.functional inside the oracle: dense ops use split operands."""
 
-    def __init__(self, kind: str, passes: int):
+    def __init__(self, kind: str, passes: int, cross_bits: int = 0):
         super().__init__()
-        self.kind, self.passes = kind, passes
+        self.kind, self.passes, self.cross_bits = kind, passes, cross_bits
         for name in ("pad", "layer_norm", "gelu", "silu"):
             setattr(self, name, getattr(TF, name))
 
@@ -57,7 +66,12 @@ class SplitF(types.SimpleNamespace):
         y = fn(xh, wh, None, **kw)
         if self.passes == 2:            # activations split, weights rounded once: (xh + xl) * wh
             y = y + fn(xl, wh, None, **kw)
-        if self.passes >= 3:
+        if self.passes >= 3 and self.cross_bits:
+            # the two cross terms as 8-bit-float MMAs (kind::f8f6f4): both factors of hi*lo and
+            # lo*hi carry only `cross_bits` mantissa bits
+            q = lambda t: _round_mant(t, self.cross_bits)
+            y = y + fn(q(xh), q(wl), None, **kw) + fn(q(xl), q(wh), None, **kw)
+        elif self.passes >= 3:
             y = y + fn(xh, wl, None, **kw) + fn(xl, wh, None, **kw)
         if self.passes >= 4:
             y = y + fn(xl, wl, None, **kw)
@@ -78,9 +92,12 @@ class SplitF(types.SimpleNamespace):
 
 
 def run(cfg, weights, codes, mode: str) -> np.ndarray:
+    cross = 0
+    if "c" in mode[4:]:                      # e.g. fp16x3c3: three passes, cross terms with 3 mantissa bits (e4m3)
+        mode, cross = mode[:mode.rindex("c")], int(mode[mode.rindex("c") + 1:])
     kind, passes = mode[:-2], int(mode[-1])
     saved = O.F
-    O.F = SplitF(kind, passes)
+    O.F = SplitF(kind, passes, cross)
     try:
         a, _ = O.forward(codes, O.Weights(weights, torch.float32), cfg)
     finally:

@@ -38,6 +38,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <type_traits>
 
 namespace {
@@ -62,19 +63,30 @@ struct FuArgs {
     __half* S_hi;  __half* S_lo;  long long s_bstride;  int lds;
 };
 
-// waits / arrives that order ordinary shared-memory writes of BOTH CTAs of the pair against the leader's MMA issue
-__device__ __forceinline__ void mbar_spin_acq_cluster(uint32_t addr, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "SPINC_WAIT:\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra SPINC_DONE;\n\t"
-        "bra SPINC_WAIT;\n\t"
-        "SPINC_DONE:\n\t}"
-        :: "r"(addr), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+// Bring-up profiling (-DVOC_TC_PROF, tools/ab_build.sh): cycles each role spends waiting, summed over CTAs
+#ifdef VOC_TC_PROF
+enum { RF_MMA_TOTAL, RF_MMA_W_A, RF_MMA_W_B, RF_MMA_W_ACC, RF_MMA_W_T, RF_EPI_TOTAL, RF_EPI_W_ACC7, RF_EPI_W_ACC1, RF_EPI_EMIT,
+       RF_EPI_FINAL, RF_PROD_TOTAL, RF_PROD_W_A, RF_PROD_W_B, RF_CTAS, RF_TILES, RF_N };
+__device__ unsigned long long g_ru_prof[RF_N];
+#define PF_DECL(name) long long name = 0
+#define PF_T0(t) const long long t = clock64()
+#define PF_ACC(name, t) name += clock64() - (t)
+#define PF_FLUSH(idx, name) atomicAdd(&g_ru_prof[idx], (unsigned long long)(name))
+#else
+#define PF_DECL(name)
+#define PF_T0(t)
+#define PF_ACC(name, t)
+#define PF_FLUSH(idx, name)
+#endif
+
+// The hand-over of a T tile: every epilogue thread has written its row (st.shared) and issued fence.proxy.async, which
+// makes those generic-proxy writes visible to the async proxy (the tensor core) of ITS OWN SM; the arrive on the
+// leader's barrier then only has to be ordered after them in program order, for which the default semantics of
+// mbarrier.arrive (.release at .cta scope) are enough -- each SM's tensor core reads its own CTA's shared memory.
+// (A .release.cluster arrive compiles to MEMBAR.ALL.GPU + ERRBAR and waits for the warp's outstanding global stores:
+// 10 % of all stall samples, profiles/r2_ncu_ru_fused.txt.)  CUTLASS's ClusterBarrier::arrive(cta_id) is the same form.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -146,6 +158,7 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == 0) {
         // ================================ TMA producer ================================
         int sa = 0, pa = 0, sb = 0, pb = 0;
+        PF_DECL(pf_w_a); PF_DECL(pf_w_b); PF_T0(pf_t0);
         const int n_my = walker < a.total_tiles ? (a.total_tiles - walker + walkers - 1) / walkers : 0;
         for (int s = 0; s < n_my + (PIPE ? 1 : 0); ++s) {
           if (!PIPE || s < n_my) {
@@ -156,14 +169,14 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int kc = 0; kc < a.k_chunks; ++kc) {
                 for (int tap = 0; tap < a.ntaps; ++tap) {
                     if (tap == 0) {
-                        mbar_wait(&bar_a_empty[sa], pa ^ 1);
+                        { PF_T0(tw); mbar_wait(&bar_a_empty[sa], pa ^ 1); PF_ACC(pf_w_a, tw); }
                         if (elect_one()) {
                             if (rank == 0) mbar_expect_tx(&bar_a_full[sa], 2 * a_stage);
                             tma_load_4d_2sm(smA + sa * a_stage, &tmA, mapa_u32(&bar_a_full[sa], 0), kc * a.kc_steps * 16, row0, b, 0);
                         }
                         if (++sa == a.SA) { sa = 0; pa ^= 1; }
                     }
-                    mbar_wait(&bar_b_empty[sb], pb ^ 1);
+                    { PF_T0(tw); mbar_wait(&bar_b_empty[sb], pb ^ 1); PF_ACC(pf_w_b, tw); }
                     if (elect_one()) {
                         if (rank == 0) mbar_expect_tx(&bar_b_full[sb], 2 * B_STAGE);
                         const uint32_t lb = mapa_u32(&bar_b_full[sb], 0);
@@ -197,6 +210,9 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
           }
         }
+#ifdef VOC_TC_PROF
+        if (lane == 0) { PF_FLUSH(RF_PROD_TOTAL, clock64() - pf_t0); PF_FLUSH(RF_PROD_W_A, pf_w_a); PF_FLUSH(RF_PROD_W_B, pf_w_b); }
+#endif
     } else if (warp == 1) {
         // ================================ MMA issuer (leader) =========================
         if (rank == 0) {
@@ -219,6 +235,7 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t a2_desc0 = reg(smem_desc_lo(smA2));
             int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pas = 0, p_a2 = 0;
             uint32_t b_lo = b_desc0;
+            PF_DECL(pf_w_a); PF_DECL(pf_w_b); PF_DECL(pf_w_acc); PF_DECL(pf_w_t); PF_T0(pf_t0);
             const int n_my = walker < a.total_tiles ? (a.total_tiles - walker + walkers - 1) / walkers : 0;
             for (int s = 0; s < n_my + (PIPE ? 1 : 0); ++s) {
               uint32_t tmem_acc = 0;
@@ -226,21 +243,21 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 uint32_t accum = 0;
                 int seg_left = 0, iters_left = ipt, seg_idx = 0;
                 for (int fill = 0; fill < n_fills; ++fill) {
-                    mbar_spin_a(a_full0 + 8 * sa, pa);
+                    { PF_T0(tw); mbar_spin_a(a_full0 + 8 * sa, pa); PF_ACC(pf_w_a, tw); }
                     uint32_t a_lo = a_desc0 + (uint32_t)sa * a_stage16;
                     const int ks_this = fill < first_short ? ks_regular : ks_last;
                     auto stages = [&](auto nks) {
                     constexpr int NKS = decltype(nks)::value;
                     for (int t = 0; t < n_inner; ++t) {
                         if (seg_left == 0) {
-                            mbar_spin_a(acc_empty0 + 8 * as, pas ^ 1);
+                            { PF_T0(tw); mbar_spin_a(acc_empty0 + 8 * as, pas ^ 1); PF_ACC(pf_w_acc, tw); }
                             tmem_acc = tmem_base + (uint32_t)as * ACC_COLS;
                             accum = 0;
                             const int want = seg_idx < seg_head ? 2 * seg_iters : seg_iters;
                             seg_left = iters_left < want ? iters_left : want;
                             ++seg_idx;
                         }
-                        mbar_spin_a(b_full0 + 8 * sb, pb);
+                        { PF_T0(tw); mbar_spin_a(b_full0 + 8 * sb, pb); PF_ACC(pf_w_b, tw); }
                         tc_fence_after();
                         --seg_left; --iters_left;
                         const bool last_of_seg = seg_left == 0;
@@ -291,15 +308,15 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               }
               if (!PIPE || s > 0) {
                 // ---- the 1x1 convolution on the T tiles both CTAs' epilogue warps have written to shared memory
-                mbar_spin_acq_cluster(a2_full, (uint32_t)p_a2);
+                { PF_T0(tw); mbar_spin_a(a2_full, (uint32_t)p_a2); PF_ACC(pf_w_t, tw); }
                 p_a2 ^= 1;
-                mbar_spin_a(acc_empty0 + 8 * as, pas ^ 1);
+                { PF_T0(tw); mbar_spin_a(acc_empty0 + 8 * as, pas ^ 1); PF_ACC(pf_w_acc, tw); }
                 tmem_acc = tmem_base + (uint32_t)as * ACC_COLS;
 #pragma unroll
                 for (int kc = 0; kc < NKC2; ++kc) {
                     constexpr int FULL = 4;
                     const int nks = kc == NKC2 - 1 ? KS2_LAST : FULL;
-                    mbar_spin_a(b_full0 + 8 * sb, pb);
+                    { PF_T0(tw); mbar_spin_a(b_full0 + 8 * sb, pb); PF_ACC(pf_w_b, tw); }
                     tc_fence_after();
                     if (elect_one()) {
                         const uint32_t t_lo = a2_desc0 + (uint32_t)kc * (A2_CHUNK >> 4);
@@ -347,6 +364,12 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
               }
             }
+#ifdef VOC_TC_PROF
+            if (lane == 0) {
+                PF_FLUSH(RF_MMA_TOTAL, clock64() - pf_t0); PF_FLUSH(RF_MMA_W_A, pf_w_a); PF_FLUSH(RF_MMA_W_B, pf_w_b);
+                PF_FLUSH(RF_MMA_W_ACC, pf_w_acc); PF_FLUSH(RF_MMA_W_T, pf_w_t); PF_FLUSH(RF_CTAS, 1); PF_FLUSH(RF_TILES, n_my);
+            }
+#endif
         }
     } else {
         // ================================ epilogue ====================================
@@ -376,8 +399,14 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)n0;
 
         // one accumulator buffer of the ring -> registers (added in FP32, round-to-nearest), buffer handed back
+        PF_DECL(pf_w7); PF_DECL(pf_w1); PF_DECL(pf_emit); PF_DECL(pf_final); PF_T0(pf_t0);
+        bool pf_is1 = false; (void)pf_is1;
         auto drain = [&](float (&acc)[HN], bool first) {
-            mbar_wait(&bar_acc_full[as], pas);
+            { PF_T0(tw); mbar_wait(&bar_acc_full[as], pas);
+#ifdef VOC_TC_PROF
+              if (pf_is1) pf_w1 += clock64() - tw; else pf_w7 += clock64() - tw;
+#endif
+            }
             tc_fence_after();
             const uint32_t taddr = tlane + (uint32_t)as * ACC_COLS;
             if constexpr (CAT) {
@@ -474,7 +503,7 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core's reads
             __syncwarp();
-            if (lane == 0) mbar_arrive_release_cluster(a2_full_leader);
+            if (lane == 0) mbar_arrive_remote(a2_full_leader);
         };
 
         // 16 columns of the unit's output: x' = conv1 * 2^-e + b1 + x -> Y; Snake_next, split -> S
@@ -527,7 +556,7 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if constexpr (PIPE) {
                 // 16 columns at a time straight from TMEM (main + correction block): the conv7 sums of the next tile
                 // occupy the registers a whole-row drain would need
-                mbar_wait(&bar_acc_full[as], pas);
+                { PF_T0(tw); mbar_wait(&bar_acc_full[as], pas); PF_ACC(pf_w1, tw); }
                 tc_fence_after();
                 const uint32_t taddr = tlane + (uint32_t)as * ACC_COLS;
 #pragma unroll
@@ -552,7 +581,9 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
                 if (++as == NBUF) { as = 0; pas ^= 1; }
             } else {
+                pf_is1 = true;
                 drain(acc, true);                    // (the conv7 sums in these registers have been emitted)
+                pf_is1 = false;
                 if (!valid) return;
 #pragma unroll
                 for (int g16 = 0; g16 < HN; g16 += 16) {
@@ -569,13 +600,19 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             // ---- conv7 accumulation segments of tile s (added in FP32 with round-to-nearest, as in the unfused kernel)
             if (do7) for (int seg = 0; seg < nseg; ++seg) drain(acc7, seg == 0);
             if constexpr (!PIPE) {
-                emit_t(acc7);
-                finish_tile(walker + s * walkers, acc7);
+                { PF_T0(te); emit_t(acc7); PF_ACC(pf_emit, te); }
+                { PF_T0(tf); finish_tile(walker + s * walkers, acc7); PF_ACC(pf_final, tf); }
             } else {
-                if (s > 0) finish_tile(walker + (s - 1) * walkers, acc7);
-                if (do7) emit_t(acc7);
+                if (s > 0) { PF_T0(tf); finish_tile(walker + (s - 1) * walkers, acc7); PF_ACC(pf_final, tf); }
+                if (do7) { PF_T0(te); emit_t(acc7); PF_ACC(pf_emit, te); }
             }
         }
+#ifdef VOC_TC_PROF
+        if (warp == 2 && lane == 0) {
+            PF_FLUSH(RF_EPI_TOTAL, clock64() - pf_t0); PF_FLUSH(RF_EPI_W_ACC7, pf_w7); PF_FLUSH(RF_EPI_W_ACC1, pf_w1);
+            PF_FLUSH(RF_EPI_EMIT, pf_emit); PF_FLUSH(RF_EPI_FINAL, pf_final);
+        }
+#endif
     }
     __syncwarp();
     tc_fence_before();
@@ -630,6 +667,17 @@ bool plan_fused(const RuFusedParams& p, FuPlan& pl) {
 }
 
 }  // namespace
+
+#ifdef VOC_TC_PROF
+extern "C" int voc_ru_prof_read(unsigned long long* out, int n, int reset) {
+    unsigned long long h[RF_N];
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(h, g_ru_prof, sizeof(h)) != cudaSuccess) return -1;
+    for (int i = 0; i < n && i < RF_N; ++i) out[i] = h[i];
+    if (reset) { memset(h, 0, sizeof(h)); cudaMemcpyToSymbol(g_ru_prof, h, sizeof(h)); }
+    return RF_N;
+}
+#endif
 
 bool voc_ru_fused_eligible(const RuFusedParams& p) {
     if (p.C != 96 && p.C != 192) return false;
@@ -698,11 +746,24 @@ cudaError_t voc_launch_ru_fused(const RuFusedParams& p, cudaStream_t st, int num
     const int sms = num_sms > 0 ? num_sms : 148;
     const int grid = 2 * std::min(a.total_tiles, sms / 2);
     const bool pipe = !pl.alias && BN == 96 && !(flags & VOC_TC_NO_PIPE);
+    static const int cp_env = []() { const char* e = getenv("VOC_RU_CP"); return e ? atoi(e) : 0; }();   // experiment hook
     if (BN == 96) {
         if (pl.alias) return launch_fused<96, 3, true, false>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st);
+        if (cp_env == 6)
+            return pipe ? launch_fused<96, 6, false, true>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st)
+                        : launch_fused<96, 6, false, false>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st);
+        if (cp_env == 2)
+            return pipe ? launch_fused<96, 2, false, true>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st)
+                        : launch_fused<96, 2, false, false>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st);
         return pipe ? launch_fused<96, 3, false, true>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st)
                     : launch_fused<96, 3, false, false>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st);
     }
+    if (cp_env == 6 || cp_env == 4)
+        return pl.alias ? launch_fused<192, 4, true, false>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st)
+                        : launch_fused<192, 4, false, false>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st);
+    if (cp_env == 2)
+        return pl.alias ? launch_fused<192, 2, true, false>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st)
+                        : launch_fused<192, 2, false, false>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st);
     return pl.alias ? launch_fused<192, 3, true, false>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st)
                     : launch_fused<192, 3, false, false>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st);
 }
