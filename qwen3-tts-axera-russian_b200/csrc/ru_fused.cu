@@ -16,21 +16,27 @@
 //               read it through shifted descriptors), the conv7 weights per (tap, chunk), then the 1x1 weights
 //   warp 1      MMA issuer (leader CTA): conv7 in accumulation segments exactly as the unfused kernel, then waits
 //               for both CTAs' T tiles and issues the 1x1 chain into the next TMEM buffer of the same ring
-//   warps 2..   epilogue (4 TMEM lane quadrants x CP column parts): drain conv7 segments -> registers; bias, Snake2,
-//               split -> shared memory (st.shared, 128B swizzle by hand), fence.proxy.async, arrive; prefetch the
-//               residual row; drain the 1x1 accumulator; + bias + residual -> Y; Snake_next, split -> S
+//   warps 2-3   idle (they fill warpgroup 0, the unit of setmaxnreg)
+//   group A     4 CP warps, the conv7 side (4 TMEM lane quadrants x CP column parts): drain conv7 segments -> registers;
+//               bias, Snake2, split -> the T tile in shared memory (st.shared, 128B swizzle by hand), fence.proxy.async,
+//               arrive
+//   group B     4 CP warps, the conv1 side: prefetch the residual rows into L2 a tile ahead; the 1x1 accumulator 16
+//               columns at a time straight from TMEM; + bias + residual -> Y; Snake_next, split -> S
+// Two groups because the two halves of the epilogue work are of equal weight and independent across tiles: A emits
+// T(i+1) while B finishes tile i, each thread holding ONE tile's values (with a single group the conv7 sums of tile
+// i+1 had to wait in registers through the final phase of tile i: no room at C = 192).
 // The arithmetic -- segment schedule, pass order, k-step order, epilogue formulas -- is that of the two unfused
 // launches, so the results are bit-identical to them (tests/test_gpu_ru_fused.py).
 //
-// Order of work (PIPE, C = 96): the issuing warp runs conv7 of tile i+1 BEFORE the 1x1 chain of tile i, and the
-// epilogue warps run  drain7(i+1) -> drain1(i) + final(i) -> Snake/split(i+1) -> T,  so that the tensor pipe works on
-// tile i+1 while the epilogue warps finish tile i: neither waits for the other's whole phase.  The conv7 sums of tile
-// i+1 wait in registers meanwhile, which is why the 1x1 accumulator is drained 16 columns at a time there.
-// C = 192 keeps the simple order (conv7(i), T(i), conv1(i)): its 64 columns per thread do not leave registers for a
-// second tile, and its tensor time per tile (28 k cycles) is twice its epilogue time anyway.
-// C = 192, dilation 9: T (96 KB as two fp16 planes) does not fit next to a double-buffered 2 x 47 KB halo ring and the
-// weight ring, so there (ALIAS) T overlays the halo ring: the issuing warp holds back the ring's last hand-backs of a
-// tile until the 1x1 chain is issued, i.e. the producer's prefetch of the next tile's halo waits for it.
+// Order of work (PIPE, C = 96): the issuing warp runs conv7 of tile i+1 BEFORE the 1x1 chain of tile i, so the tensor
+// pipe works on tile i+1 while group A turns tile i's sums into T; a commit after each 1x1 chain (t_free) tells group A
+// when T may be overwritten.
+// C = 192: T (96 KB as two fp16 planes) does not fit next to a double-buffered 2 x 47 KB halo ring and a weight ring
+// deep enough to cover the TMA latency (measured: with two weight stages the issuing warp waits for weights 27 % of
+// the time), so there (ALIAS) T overlays the halo ring and the order is conv7(i), T(i), conv1(i): the issuing warp
+// holds back the ring's last hand-backs of a tile until the 1x1 chain is issued, i.e. the producer's prefetch of the
+// next tile's halo waits for it.  Group B's final phase still overlaps conv7(i+1).  Group A's 96 accumulators per
+// thread need more than the 96 registers a 640-thread CTA starts with: warpgroup 0 gives registers up (setmaxnreg).
 #include "voc_common.cuh"
 #include "tc_ptx.cuh"
 
@@ -93,7 +99,7 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 }
 
 template <int BN, int CP, bool ALIAS, bool PIPE>
-__global__ void __launch_bounds__(64 + 128 * CP, 1)
+__global__ void __launch_bounds__(128 + 256 * CP, 1)
 ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmW1,
                 const __grid_constant__ CUtensorMap tmW1b, const __grid_constant__ FuArgs a) {
@@ -101,8 +107,17 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     static_assert((BN / CP) % 16 == 0, "the epilogue handles 16 operand columns (one 32-byte sector) at a time");
     static_assert(!(ALIAS && PIPE), "the pipelined order keeps the halo ring busy while T is live");
     constexpr int BK = 64;
-    constexpr int EPI_WARPS = 4 * CP;
+    constexpr int EPI_WARPS = 4 * CP;                         // warps per epilogue group (A: conv7 side, B: conv1 side)
     constexpr int HN = BN / CP;                               // columns per epilogue thread
+    // register budgets (setmaxnreg, multiples of 8): a 640-thread CTA starts at 96 per thread; group A at C = 192 holds
+    // 96 accumulators per thread
+    constexpr bool REBALANCE = HN > 48;
+    // setmaxnreg.inc can only take what setmaxnreg.dec has released inside the CTA (the SM's never-allocated registers
+    // are not in that pool: an inc that asks for more blocks for ever)
+    constexpr int REGS_START = 96, REGS_WG0 = 56, REGS_A = 128, REGS_B = 80;
+    static_assert((REGS_START - REGS_WG0) * 128 + (REGS_START - REGS_B) * 32 * EPI_WARPS >= (REGS_A - REGS_START) * 32 * EPI_WARPS,
+                  "register pool: released < requested");
+    static_assert((128 + 64 * EPI_WARPS) * REGS_START <= 65536, "launch register budget");
     constexpr uint32_t ROWB = BK * 2;
     constexpr bool CAT = BN <= 128;                           // see tc_gemm.cu: A_hi x [B_hi; B_lo] as one N = 2 BN MMA
     constexpr int BROWS = BN / 2;
@@ -116,13 +131,17 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // T tile: K chunks of 64 channels (128-byte rows, 128 rows, SWIZZLE_128B), two planes
     constexpr int NKC2 = (BN + 63) / 64;
     constexpr int KS2_LAST = (BN - (NKC2 - 1) * 64) / 16;     // k-steps of the last chunk (2 at C = 96)
-    constexpr uint32_t A2_CHUNK = BM * ROWB, A2_PLANE = NKC2 * A2_CHUNK;
+    constexpr uint32_t A2_CHUNK = BM * ROWB;
+    // C = 96: the second chunk holds 32 channels only -- 64-byte rows in the SWIZZLE_64B layout (16 KB less per tile,
+    // which buys a fourth weight stage)
+    constexpr bool T64 = (BN % 64) == 32;
+    constexpr uint32_t A2_PLANE = T64 ? (NKC2 - 1) * A2_CHUNK + BM * 64 : NKC2 * A2_CHUNK;
 
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_a_full[MAX_STAGES], bar_a_empty[MAX_STAGES];
     __shared__ __align__(8) uint64_t bar_b_full[MAX_STAGES], bar_b_empty[MAX_STAGES];
     __shared__ __align__(8) uint64_t bar_acc_full[NBUF], bar_acc_empty[NBUF];
-    __shared__ __align__(8) uint64_t bar_a2_full;
+    __shared__ __align__(8) uint64_t bar_a2_full, bar_t_free;
     __shared__ uint32_t tmem_slot;
     // per-channel epilogue parameters: conv7 bias, Snake2 a / 1/b, conv1 bias, next Snake a / 1/b
     __shared__ __align__(16) float epi_par[6][BN];
@@ -145,6 +164,7 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int i = 0; i < a.SB; ++i) { mbar_init(&bar_b_full[i], 1); mbar_init(&bar_b_empty[i], 1); }
         for (int i = 0; i < NBUF; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], 2 * EPI_WARPS); }
         mbar_init(&bar_a2_full, 2 * EPI_WARPS);
+        mbar_init(&bar_t_free, 1);
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -154,6 +174,9 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
+    if (warp < 4) {
+        if constexpr (REBALANCE) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_WG0));
+    }
 
     if (warp == 0) {
         // ================================ TMA producer ================================
@@ -219,7 +242,7 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t a_full0 = opaque_u32(smem_u32(&bar_a_full[0])), a_empty0 = opaque_u32(smem_u32(&bar_a_empty[0]));
             const uint32_t b_full0 = opaque_u32(smem_u32(&bar_b_full[0])), b_empty0 = opaque_u32(smem_u32(&bar_b_empty[0]));
             const uint32_t acc_full0 = opaque_u32(smem_u32(&bar_acc_full[0])), acc_empty0 = opaque_u32(smem_u32(&bar_acc_empty[0]));
-            const uint32_t a2_full = opaque_u32(smem_u32(&bar_a2_full));
+            const uint32_t a2_full = opaque_u32(smem_u32(&bar_a2_full)), t_free = opaque_u32(smem_u32(&bar_t_free));
             const uint32_t rt0 = tmem_base >> 24;
             auto reg = [&](uint32_t x) { return opaque_u32(x + rt0); };
             const int ks_regular = (int)reg((uint32_t)a.kc_steps), ks_last = (int)reg((uint32_t)a.kc_last);
@@ -321,13 +344,15 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     if (elect_one()) {
                         const uint32_t t_lo = a2_desc0 + (uint32_t)kc * (A2_CHUNK >> 4);
                         if constexpr (CAT) {
+                            // (the 32-channel last chunk of T is a SWIZZLE_64B tile: its own descriptor high word)
+                            const uint32_t t_hi = (T64 && kc == NKC2 - 1) ? smem_desc_hi<32>() : smem_desc_hi<BK>();
 #pragma unroll
                             for (int ks = 0; ks < FULL; ++ks) {
                                 if (ks < nks) {
                                     if (kc == 0 && ks == 0) mma2_f16_ss(tmem_acc, t_lo, b_lo, smem_desc_hi<BK>(), IDESC2, 0u);
-                                    else mma2_f16_ss_acc(tmem_acc, t_lo + ks * 2, b_lo + ks * 2, smem_desc_hi<BK>(), IDESC2);
-                                    mma2_f16_ss_acc(tmem_acc + BN, t_lo + (A2_PLANE >> 4) + ks * 2,
-                                                    b_lo + (B_PLANE >> 4) + ks * 2, smem_desc_hi<BK>(), IDESC);
+                                    else mma2_f16_ss_acc_hh(tmem_acc, t_lo + ks * 2, t_hi, b_lo + ks * 2, smem_desc_hi<BK>(), IDESC2);
+                                    mma2_f16_ss_acc_hh(tmem_acc + BN, t_lo + (A2_PLANE >> 4) + ks * 2, t_hi,
+                                                       b_lo + (B_PLANE >> 4) + ks * 2, smem_desc_hi<BK>(), IDESC);
                                 }
                             }
                         } else {
@@ -345,7 +370,7 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             }
                         }
                         mma2_commit_both_a(b_empty0 + 8 * sb);
-                        if (kc == NKC2 - 1) mma2_commit_both_a(acc_full0 + 8 * as);
+                        if (kc == NKC2 - 1) { mma2_commit_both_a(acc_full0 + 8 * as); mma2_commit_both_a(t_free); }
                     }
                     __syncwarp();
                     b_lo += B_STAGE >> 4;
@@ -371,14 +396,16 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
 #endif
         }
-    } else {
-        // ================================ epilogue ====================================
+    } else if (warp >= 4) {
+        // ================================ epilogue groups =============================
+        const bool groupA = warp < 4 + EPI_WARPS;
+        const int gw = groupA ? warp - 4 : warp - 4 - EPI_WARPS;     // warp within its group
         const int q = warp & 3;                       // the TMEM lane quadrant this warp can read
-        const int h = (warp - 2) >> 2;                // which part of the channels
+        const int h = gw >> 2;                        // which part of the channels
         int nseg = 0;
         for (int rem = iters_per_tile; rem > 0; ++nseg) rem -= (nseg < a.seg_head ? 2 : 1) * a.seg_iters;
-        const int etid = threadIdx.x - 64;
-        for (int i = etid; i < BN; i += 32 * EPI_WARPS) {
+        const int etid = threadIdx.x - 128;
+        for (int i = etid; i < BN; i += 64 * EPI_WARPS) {
             epi_par[0][i] = __ldg(a.bias7 + i);
             epi_par[1][i] = __ldg(a.sn2_a + i);
             epi_par[2][i] = __ldg(a.sn2_invb + i);
@@ -386,233 +413,250 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             epi_par[4][i] = __ldg(a.snn_a + i);
             epi_par[5][i] = __ldg(a.snn_invb + i);
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(64 * EPI_WARPS) : "memory");
+        // The accumulator ring is used in the issuing warp's order: per step the conv7 segments, then one 1x1 chain.
+        // Each group waits for and hands back only its own buffers and steps over the other group's.
         int as = 0, pas = 0;
+        auto skip = [&](int n) { for (int i = 0; i < n; ++i) if (++as == NBUF) { as = 0; pas ^= 1; } };
         uint32_t acc_empty_leader[NBUF];
 #pragma unroll
         for (int i = 0; i < NBUF; ++i) acc_empty_leader[i] = mapa_u32(&bar_acc_empty[i], 0);
-        const uint32_t a2_full_leader = mapa_u32(&bar_a2_full, 0);
         const int n0 = h * HN;
         const uint32_t trow = (uint32_t)(q * 32 + lane);                        // row of the tile this thread owns
-        const uint32_t t_row_addr = smA2 + trow * ROWB;
-        const uint32_t sw = trow & 7u;                                          // 128B swizzle: 16-byte granule ^= row % 8
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)n0;
+        const int n_my = walker < a.total_tiles ? (a.total_tiles - walker + walkers - 1) / walkers : 0;
 
-        // one accumulator buffer of the ring -> registers (added in FP32, round-to-nearest), buffer handed back
-        PF_DECL(pf_w7); PF_DECL(pf_w1); PF_DECL(pf_emit); PF_DECL(pf_final); PF_T0(pf_t0);
-        bool pf_is1 = false; (void)pf_is1;
-        auto drain = [&](float (&acc)[HN], bool first) {
-            { PF_T0(tw); mbar_wait(&bar_acc_full[as], pas);
-#ifdef VOC_TC_PROF
-              if (pf_is1) pf_w1 += clock64() - tw; else pf_w7 += clock64() - tw;
-#endif
-            }
-            tc_fence_after();
-            const uint32_t taddr = tlane + (uint32_t)as * ACC_COLS;
-            if constexpr (CAT) {
+        if (groupA) {
+            // ---------------- group A: conv7 sums -> T tile ----------------
+            if constexpr (REBALANCE) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_A));
+            const uint32_t a2_full_leader = mapa_u32(&bar_a2_full, 0);
+            const uint32_t t_row_addr = smA2 + trow * ROWB;
+            const uint32_t sw = trow & 7u;                                      // 128B swizzle: 16-byte granule ^= row % 8
+            int p_tf = 0;
+            PF_DECL(pf_w7); PF_DECL(pf_wt); PF_DECL(pf_emit); PF_T0(pf_t0);
+            for (int s = 0; s < n_my; ++s) {
+                float acc[HN];
+                // conv7 accumulation segments of tile s, added in FP32 with round-to-nearest as in the unfused kernel
+                for (int seg = 0; seg < nseg; ++seg) {
+                    { PF_T0(tw); mbar_wait(&bar_acc_full[as], pas); PF_ACC(pf_w7, tw); }
+                    tc_fence_after();
+                    const uint32_t taddr = tlane + (uint32_t)as * ACC_COLS;
+                    const bool first = seg == 0;
+                    if constexpr (CAT) {
 #pragma unroll
-                for (int c0 = 0; c0 < HN / 8; c0 += 2) {
-                    uint32_t tm[2][8], tc[2][8];
+                        for (int c0 = 0; c0 < HN / 8; c0 += 2) {
+                            uint32_t tm[2][8], tc[2][8];
 #pragma unroll
-                    for (int c = 0; c < 2; ++c)
-                        if (c0 + c < HN / 8) { tmem_ld8(taddr + (c0 + c) * 8, tm[c]); tmem_ld8(taddr + BN + (c0 + c) * 8, tc[c]); }
-                    tmem_ld_wait();
+                            for (int c = 0; c < 2; ++c)
+                                if (c0 + c < HN / 8) { tmem_ld8(taddr + (c0 + c) * 8, tm[c]); tmem_ld8(taddr + BN + (c0 + c) * 8, tc[c]); }
+                            tmem_ld_wait();
 #pragma unroll
-                    for (int c = 0; c < 2; ++c)
-                        if (c0 + c < HN / 8) {
+                            for (int c = 0; c < 2; ++c)
+                                if (c0 + c < HN / 8) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float v = __uint_as_float(tm[c][j]) + __uint_as_float(tc[c][j]);
-                                acc[(c0 + c) * 8 + j] = first ? v : acc[(c0 + c) * 8 + j] + v;
-                            }
+                                    for (int j = 0; j < 8; ++j) {
+                                        const float v = __uint_as_float(tm[c][j]) + __uint_as_float(tc[c][j]);
+                                        acc[(c0 + c) * 8 + j] = first ? v : acc[(c0 + c) * 8 + j] + v;
+                                    }
+                                }
                         }
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(acc_empty_leader[as]);
-            } else {
-                constexpr int CH = 4;
-#pragma unroll
-                for (int c0 = 0; c0 < HN / 8; c0 += CH) {
-                    uint32_t tr[CH][8];
-#pragma unroll
-                    for (int c = 0; c < CH; ++c)
-                        if (c0 + c < HN / 8) tmem_ld8(taddr + (c0 + c) * 8, tr[c]);
-                    tmem_ld_wait();
-                    if (c0 + CH >= HN / 8) {
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(acc_empty_leader[as]);
-                    }
+                    } else {
+                        constexpr int CH = 4;
 #pragma unroll
-                    for (int c = 0; c < CH; ++c)
-                        if (c0 + c < HN / 8) {
+                        for (int c0 = 0; c0 < HN / 8; c0 += CH) {
+                            uint32_t tr[CH][8];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float v = __uint_as_float(tr[c][j]);
-                                acc[(c0 + c) * 8 + j] = first ? v : acc[(c0 + c) * 8 + j] + v;
+                            for (int c = 0; c < CH; ++c)
+                                if (c0 + c < HN / 8) tmem_ld8(taddr + (c0 + c) * 8, tr[c]);
+                            tmem_ld_wait();
+                            if (c0 + CH >= HN / 8) {
+                                tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive_cluster(acc_empty_leader[as]);
                             }
+#pragma unroll
+                            for (int c = 0; c < CH; ++c)
+                                if (c0 + c < HN / 8) {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) {
+                                        const float v = __uint_as_float(tr[c][j]);
+                                        acc[(c0 + c) * 8 + j] = first ? v : acc[(c0 + c) * 8 + j] + v;
+                                    }
+                                }
                         }
-                }
-            }
-            if (++as == NBUF) { as = 0; pas ^= 1; }
-        };
-
-        // T = Snake2(conv7 + b7) -> split fp16 -> this thread's row of the T tile in shared memory, then the hand-over
-        // to the issuing warp.  The previous 1x1 chain has finished reading the tile: this thread has drained that
-        // chain's accumulator (and, with ALIAS, every conv7 MMA that read the halo ring is in the segments just drained).
-        auto emit_t = [&](const float (&acc)[HN]) {
-#pragma unroll
-            for (int g16 = 0; g16 < HN; g16 += 16) {
-                uint32_t hi16[8], lo16[8];
-#pragma unroll
-                for (int g = g16; g < g16 + 16; g += 8) {
-                    const int pc = n0 + g;
-                    float v[8];
-                    const float4 b0 = *reinterpret_cast<const float4*>(&epi_par[0][pc]);
-                    const float4 b1 = *reinterpret_cast<const float4*>(&epi_par[0][pc + 4]);
-                    v[0] = acc[g + 0] * a.wscale7 + b0.x; v[1] = acc[g + 1] * a.wscale7 + b0.y;
-                    v[2] = acc[g + 2] * a.wscale7 + b0.z; v[3] = acc[g + 3] * a.wscale7 + b0.w;
-                    v[4] = acc[g + 4] * a.wscale7 + b1.x; v[5] = acc[g + 5] * a.wscale7 + b1.y;
-                    v[6] = acc[g + 6] * a.wscale7 + b1.z; v[7] = acc[g + 7] * a.wscale7 + b1.w;
-                    const float4 a0 = *reinterpret_cast<const float4*>(&epi_par[1][pc]);
-                    const float4 a1 = *reinterpret_cast<const float4*>(&epi_par[1][pc + 4]);
-                    const float4 i0 = *reinterpret_cast<const float4*>(&epi_par[2][pc]);
-                    const float4 i1 = *reinterpret_cast<const float4*>(&epi_par[2][pc + 4]);
-                    v[0] = voc_snake(v[0], a0.x, i0.x); v[1] = voc_snake(v[1], a0.y, i0.y);
-                    v[2] = voc_snake(v[2], a0.z, i0.z); v[3] = voc_snake(v[3], a0.w, i0.w);
-                    v[4] = voc_snake(v[4], a1.x, i1.x); v[5] = voc_snake(v[5], a1.y, i1.y);
-                    v[6] = voc_snake(v[6], a1.z, i1.z); v[7] = voc_snake(v[7], a1.w, i1.w);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        __half2 hh, ll;
-                        voc_split2(v[2 * j], v[2 * j + 1], hh, ll);
-                        hi16[(g - g16) / 2 + j] = *reinterpret_cast<uint32_t*>(&hh);
-                        lo16[(g - g16) / 2 + j] = *reinterpret_cast<uint32_t*>(&ll);
                     }
+                    skip(1);
                 }
-                // columns n0 + g16 .. + 15 of the tile: chunk (n0 + g16) / 64, 16-byte granules j0 and j0 + 1
-                const int col = n0 + g16;
-                const uint32_t base = t_row_addr + (uint32_t)(col >> 6) * A2_CHUNK;
-                const uint32_t j0 = (uint32_t)((col & 63) >> 3);
-                const uint32_t p0 = base + (((j0) ^ sw) << 4), p1 = base + (((j0 + 1) ^ sw) << 4);
-                sts128(p0, hi16[0], hi16[1], hi16[2], hi16[3]);
-                sts128(p1, hi16[4], hi16[5], hi16[6], hi16[7]);
-                sts128(p0 + A2_PLANE, lo16[0], lo16[1], lo16[2], lo16[3]);
-                sts128(p1 + A2_PLANE, lo16[4], lo16[5], lo16[6], lo16[7]);
-            }
-            fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core's reads
-            __syncwarp();
-            if (lane == 0) mbar_arrive_remote(a2_full_leader);
-        };
-
-        // 16 columns of the unit's output: x' = conv1 * 2^-e + b1 + x -> Y; Snake_next, split -> S
-        auto final16 = [&](const float* v16, int g16, const float (&res)[2][8], float* Yrow, long long soff) {
-            uint32_t hi16[8], lo16[8];
-#pragma unroll
-            for (int gg = 0; gg < 16; gg += 8) {
-                const int pc = n0 + g16 + gg;
-                float v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = v16[gg + j] * a.wscale1;
-                const float4 b0 = *reinterpret_cast<const float4*>(&epi_par[3][pc]);
-                const float4 b1 = *reinterpret_cast<const float4*>(&epi_par[3][pc + 4]);
-                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] += res[gg / 8][j];
-                if (Yrow) stg256(Yrow + g16 + gg, v);
-                const float4 a0 = *reinterpret_cast<const float4*>(&epi_par[4][pc]);
-                const float4 a1 = *reinterpret_cast<const float4*>(&epi_par[4][pc + 4]);
-                const float4 i0 = *reinterpret_cast<const float4*>(&epi_par[5][pc]);
-                const float4 i1 = *reinterpret_cast<const float4*>(&epi_par[5][pc + 4]);
-                v[0] = voc_snake(v[0], a0.x, i0.x); v[1] = voc_snake(v[1], a0.y, i0.y);
-                v[2] = voc_snake(v[2], a0.z, i0.z); v[3] = voc_snake(v[3], a0.w, i0.w);
-                v[4] = voc_snake(v[4], a1.x, i1.x); v[5] = voc_snake(v[5], a1.y, i1.y);
-                v[6] = voc_snake(v[6], a1.z, i1.z); v[7] = voc_snake(v[7], a1.w, i1.w);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    __half2 hh, ll;
-                    voc_split2(v[2 * j], v[2 * j + 1], hh, ll);
-                    hi16[gg / 2 + j] = *reinterpret_cast<uint32_t*>(&hh);
-                    lo16[gg / 2 + j] = *reinterpret_cast<uint32_t*>(&ll);
+                // the 1x1 chain of the previous tile must have finished reading T.  Simple order: it was issued before
+                // this tile's conv7, whose last segment has just been drained.  Pipelined order: it comes after.
+                if constexpr (PIPE) {
+                    if (s > 0) { PF_T0(tw); mbar_wait(&bar_t_free, (uint32_t)p_tf); p_tf ^= 1; PF_ACC(pf_wt, tw); }
                 }
+                PF_T0(te);
+                // T = Snake2(conv7 + b7) -> split fp16 -> this thread's row of the T tile
+#pragma unroll
+                for (int g16 = 0; g16 < HN; g16 += 16) {
+                    uint32_t hi16[8], lo16[8];
+#pragma unroll
+                    for (int g = g16; g < g16 + 16; g += 8) {
+                        const int pc = n0 + g;
+                        float v[8];
+                        const float4 b0 = *reinterpret_cast<const float4*>(&epi_par[0][pc]);
+                        const float4 b1 = *reinterpret_cast<const float4*>(&epi_par[0][pc + 4]);
+                        v[0] = acc[g + 0] * a.wscale7 + b0.x; v[1] = acc[g + 1] * a.wscale7 + b0.y;
+                        v[2] = acc[g + 2] * a.wscale7 + b0.z; v[3] = acc[g + 3] * a.wscale7 + b0.w;
+                        v[4] = acc[g + 4] * a.wscale7 + b1.x; v[5] = acc[g + 5] * a.wscale7 + b1.y;
+                        v[6] = acc[g + 6] * a.wscale7 + b1.z; v[7] = acc[g + 7] * a.wscale7 + b1.w;
+                        const float4 a0 = *reinterpret_cast<const float4*>(&epi_par[1][pc]);
+                        const float4 a1 = *reinterpret_cast<const float4*>(&epi_par[1][pc + 4]);
+                        const float4 i0 = *reinterpret_cast<const float4*>(&epi_par[2][pc]);
+                        const float4 i1 = *reinterpret_cast<const float4*>(&epi_par[2][pc + 4]);
+                        v[0] = voc_snake(v[0], a0.x, i0.x); v[1] = voc_snake(v[1], a0.y, i0.y);
+                        v[2] = voc_snake(v[2], a0.z, i0.z); v[3] = voc_snake(v[3], a0.w, i0.w);
+                        v[4] = voc_snake(v[4], a1.x, i1.x); v[5] = voc_snake(v[5], a1.y, i1.y);
+                        v[6] = voc_snake(v[6], a1.z, i1.z); v[7] = voc_snake(v[7], a1.w, i1.w);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            __half2 hh, ll;
+                            voc_split2(v[2 * j], v[2 * j + 1], hh, ll);
+                            hi16[(g - g16) / 2 + j] = *reinterpret_cast<uint32_t*>(&hh);
+                            lo16[(g - g16) / 2 + j] = *reinterpret_cast<uint32_t*>(&ll);
+                        }
+                    }
+                    // columns n0 + g16 .. + 15 of the tile: chunk (n0 + g16) / 64, 16-byte granules j0 and j0 + 1
+                    const int col = n0 + g16;
+                    const uint32_t j0 = (uint32_t)((col & 63) >> 3);
+                    uint32_t p0, p1;
+                    if (T64 && (col >> 6) == NKC2 - 1) {
+                        // 64-byte rows, SWIZZLE_64B: granule ^= (row / 2) % 4
+                        const uint32_t base = smA2 + (uint32_t)(NKC2 - 1) * A2_CHUNK + trow * 64u, sw64 = (trow >> 1) & 3u;
+                        p0 = base + ((j0 ^ sw64) << 4); p1 = base + (((j0 + 1) ^ sw64) << 4);
+                    } else {
+                        const uint32_t base = t_row_addr + (uint32_t)(col >> 6) * A2_CHUNK;
+                        p0 = base + (((j0) ^ sw) << 4); p1 = base + (((j0 + 1) ^ sw) << 4);
+                    }
+                    sts128(p0, hi16[0], hi16[1], hi16[2], hi16[3]);
+                    sts128(p1, hi16[4], hi16[5], hi16[6], hi16[7]);
+                    sts128(p0 + A2_PLANE, lo16[0], lo16[1], lo16[2], lo16[3]);
+                    sts128(p1 + A2_PLANE, lo16[4], lo16[5], lo16[6], lo16[7]);
+                }
+                fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core's reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(a2_full_leader);
+                PF_ACC(pf_emit, te);
+                // step over the 1x1 chain's buffer that follows this tile's segments in the ring
+                if (!PIPE || s > 0) skip(1);
             }
-            stg256u(a.S_hi + soff + g16, hi16);
-            stg256u(a.S_lo + soff + g16, lo16);
-        };
-
-        // the 1x1 accumulator of `tile` -> its output rows
-        auto finish_tile = [&](int tile, float (&acc)[HN]) {
-            const int m_tile = 2 * (tile % a.m_tiles) + (int)rank, b = tile / a.m_tiles;
-            const int m = m_tile * BM + (int)trow;
-            const bool valid = m < a.M;
-            // the residual row does not depend on the MMAs: its first loads fly while the 1x1 chain runs
-            const float* Rrow = a.R + (long long)b * a.r_bstride + (long long)(valid ? m : 0) * a.ldr + n0;
-            float* Yrow = (a.Y && valid) ? a.Y + (long long)b * a.y_bstride + (long long)m * a.ldy + n0 : nullptr;
-            const long long soff = (long long)b * a.s_bstride + (long long)m * a.lds + n0;
-            float res[2][2][8];                       // two 16-column windows of the residual row, alternating
-            if (valid) { ldg256(Rrow, res[0][0]); ldg256(Rrow + 8, res[0][1]); }
-            if constexpr (PIPE) {
-                // 16 columns at a time straight from TMEM (main + correction block): the conv7 sums of the next tile
-                // occupy the registers a whole-row drain would need
+#ifdef VOC_TC_PROF
+            if (warp == 4 && lane == 0) {
+                PF_FLUSH(RF_EPI_TOTAL, clock64() - pf_t0); PF_FLUSH(RF_EPI_W_ACC7, pf_w7 + pf_wt); PF_FLUSH(RF_EPI_EMIT, pf_emit);
+            }
+#endif
+        } else {
+            // ---------------- group B: 1x1 accumulator -> the unit's outputs ----------------
+            if constexpr (REBALANCE) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_B));
+            PF_DECL(pf_w1); PF_DECL(pf_final); PF_T0(pf_t0);
+            auto row_of = [&](int tile, int& m, int& b) { m = (2 * (tile % a.m_tiles) + (int)rank) * BM + (int)trow; b = tile / a.m_tiles; };
+            auto prefetch_res = [&](int tile) {
+                int m, b; row_of(tile, m, b);
+                if (m < a.M) {
+                    const float* r = a.R + (long long)b * a.r_bstride + (long long)m * a.ldr + n0;
+#pragma unroll
+                    for (int i = 0; i < HN; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(r + i));
+                }
+            };
+            if (n_my > 0) prefetch_res(walker);
+            if constexpr (PIPE) skip(nseg);                // step 0 holds only tile 0's conv7 segments
+            for (int s = 0; s < n_my; ++s) {
+                const int tile = walker + s * walkers;
+                // ring order: simple -- segs(s), chain(s);  pipelined -- segs(s+1) (if any), chain(s)
+                if (!PIPE || s + 1 < n_my) skip(nseg);
+                int m, b; row_of(tile, m, b);
+                const bool valid = m < a.M;
+                const float* Rrow = a.R + (long long)b * a.r_bstride + (long long)(valid ? m : 0) * a.ldr + n0;
+                float* Yrow = (a.Y && valid) ? a.Y + (long long)b * a.y_bstride + (long long)m * a.ldy + n0 : nullptr;
+                const long long soff = (long long)b * a.s_bstride + (long long)m * a.lds + n0;
+                float res[2][2][8];                       // two 16-column windows of the residual row, alternating
+                if (valid) { ldg256(Rrow, res[0][0]); ldg256(Rrow + 8, res[0][1]); }
+                if (s + 1 < n_my) prefetch_res(tile + walkers);   // the next tile's rows: HBM -> L2 while this one is finished
                 { PF_T0(tw); mbar_wait(&bar_acc_full[as], pas); PF_ACC(pf_w1, tw); }
+                PF_T0(tf);
                 tc_fence_after();
                 const uint32_t taddr = tlane + (uint32_t)as * ACC_COLS;
 #pragma unroll
                 for (int g16 = 0; g16 < HN; g16 += 16) {
-                    uint32_t tm[2][8], tc[2][8];
-                    tmem_ld8(taddr + g16, tm[0]); tmem_ld8(taddr + g16 + 8, tm[1]);
-                    tmem_ld8(taddr + BN + g16, tc[0]); tmem_ld8(taddr + BN + g16 + 8, tc[1]);
-                    if (valid && g16 + 16 < HN) { ldg256(Rrow + g16 + 16, res[((g16 >> 4) & 1) ^ 1][0]); ldg256(Rrow + g16 + 24, res[((g16 >> 4) & 1) ^ 1][1]); }
-                    tmem_ld_wait();
+                    float v16[16];
+                    if constexpr (CAT) {
+                        uint32_t tm[2][8], tc[2][8];
+                        tmem_ld8(taddr + g16, tm[0]); tmem_ld8(taddr + g16 + 8, tm[1]);
+                        tmem_ld8(taddr + BN + g16, tc[0]); tmem_ld8(taddr + BN + g16 + 8, tc[1]);
+                        if (valid && g16 + 16 < HN) { ldg256(Rrow + g16 + 16, res[((g16 >> 4) & 1) ^ 1][0]); ldg256(Rrow + g16 + 24, res[((g16 >> 4) & 1) ^ 1][1]); }
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            v16[j] = __uint_as_float(tm[0][j]) + __uint_as_float(tc[0][j]);
+                            v16[8 + j] = __uint_as_float(tm[1][j]) + __uint_as_float(tc[1][j]);
+                        }
+                    } else {
+                        uint32_t tm[2][8];
+                        tmem_ld8(taddr + g16, tm[0]); tmem_ld8(taddr + g16 + 8, tm[1]);
+                        if (valid && g16 + 16 < HN) { ldg256(Rrow + g16 + 16, res[((g16 >> 4) & 1) ^ 1][0]); ldg256(Rrow + g16 + 24, res[((g16 >> 4) & 1) ^ 1][1]); }
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { v16[j] = __uint_as_float(tm[0][j]); v16[8 + j] = __uint_as_float(tm[1][j]); }
+                    }
                     if (g16 + 16 >= HN) {
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(acc_empty_leader[as]);
                     }
-                    float v16[16];
+                    if (valid) {
+                        // 16 columns of the unit's output: x' = conv1 * 2^-e + b1 + x -> Y; Snake_next, split -> S
+                        const float (&rs)[2][8] = res[(g16 >> 4) & 1];
+                        uint32_t hi16[8], lo16[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        v16[j] = __uint_as_float(tm[0][j]) + __uint_as_float(tc[0][j]);
-                        v16[8 + j] = __uint_as_float(tm[1][j]) + __uint_as_float(tc[1][j]);
+                        for (int gg = 0; gg < 16; gg += 8) {
+                            const int pc = n0 + g16 + gg;
+                            float v[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = v16[gg + j] * a.wscale1;
+                            const float4 b0 = *reinterpret_cast<const float4*>(&epi_par[3][pc]);
+                            const float4 b1 = *reinterpret_cast<const float4*>(&epi_par[3][pc + 4]);
+                            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] += rs[gg / 8][j];
+                            if (Yrow) stg256(Yrow + g16 + gg, v);
+                            const float4 a0 = *reinterpret_cast<const float4*>(&epi_par[4][pc]);
+                            const float4 a1 = *reinterpret_cast<const float4*>(&epi_par[4][pc + 4]);
+                            const float4 i0 = *reinterpret_cast<const float4*>(&epi_par[5][pc]);
+                            const float4 i1 = *reinterpret_cast<const float4*>(&epi_par[5][pc + 4]);
+                            v[0] = voc_snake(v[0], a0.x, i0.x); v[1] = voc_snake(v[1], a0.y, i0.y);
+                            v[2] = voc_snake(v[2], a0.z, i0.z); v[3] = voc_snake(v[3], a0.w, i0.w);
+                            v[4] = voc_snake(v[4], a1.x, i1.x); v[5] = voc_snake(v[5], a1.y, i1.y);
+                            v[6] = voc_snake(v[6], a1.z, i1.z); v[7] = voc_snake(v[7], a1.w, i1.w);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                __half2 hh, ll;
+                                voc_split2(v[2 * j], v[2 * j + 1], hh, ll);
+                                hi16[gg / 2 + j] = *reinterpret_cast<uint32_t*>(&hh);
+                                lo16[gg / 2 + j] = *reinterpret_cast<uint32_t*>(&ll);
+                            }
+                        }
+                        stg256u(a.S_hi + soff + g16, hi16);
+                        stg256u(a.S_lo + soff + g16, lo16);
                     }
-                    if (valid) final16(v16, g16, res[(g16 >> 4) & 1], Yrow, soff);
                 }
-                if (++as == NBUF) { as = 0; pas ^= 1; }
-            } else {
-                pf_is1 = true;
-                drain(acc, true);                    // (the conv7 sums in these registers have been emitted)
-                pf_is1 = false;
-                if (!valid) return;
-#pragma unroll
-                for (int g16 = 0; g16 < HN; g16 += 16) {
-                    if (g16 + 16 < HN) { ldg256(Rrow + g16 + 16, res[((g16 >> 4) & 1) ^ 1][0]); ldg256(Rrow + g16 + 24, res[((g16 >> 4) & 1) ^ 1][1]); }
-                    final16(&acc[g16], g16, res[(g16 >> 4) & 1], Yrow, soff);
-                }
+                skip(1);
+                PF_ACC(pf_final, tf);
             }
-        };
-
-        const int n_my = walker < a.total_tiles ? (a.total_tiles - walker + walkers - 1) / walkers : 0;
-        float acc7[HN];
-        for (int s = 0; s < n_my + (PIPE ? 1 : 0); ++s) {
-            const bool do7 = !PIPE || s < n_my;
-            // ---- conv7 accumulation segments of tile s (added in FP32 with round-to-nearest, as in the unfused kernel)
-            if (do7) for (int seg = 0; seg < nseg; ++seg) drain(acc7, seg == 0);
-            if constexpr (!PIPE) {
-                { PF_T0(te); emit_t(acc7); PF_ACC(pf_emit, te); }
-                { PF_T0(tf); finish_tile(walker + s * walkers, acc7); PF_ACC(pf_final, tf); }
-            } else {
-                if (s > 0) { PF_T0(tf); finish_tile(walker + (s - 1) * walkers, acc7); PF_ACC(pf_final, tf); }
-                if (do7) { PF_T0(te); emit_t(acc7); PF_ACC(pf_emit, te); }
-            }
-        }
 #ifdef VOC_TC_PROF
-        if (warp == 2 && lane == 0) {
-            PF_FLUSH(RF_EPI_TOTAL, clock64() - pf_t0); PF_FLUSH(RF_EPI_W_ACC7, pf_w7); PF_FLUSH(RF_EPI_W_ACC1, pf_w1);
-            PF_FLUSH(RF_EPI_EMIT, pf_emit); PF_FLUSH(RF_EPI_FINAL, pf_final);
-        }
+            if (warp == 4 + EPI_WARPS && lane == 0) { PF_FLUSH(RF_EPI_W_ACC1, pf_w1); PF_FLUSH(RF_EPI_FINAL, pf_final); (void)pf_t0; }
 #endif
+        }
     }
     __syncwarp();
     tc_fence_before();
@@ -634,7 +678,7 @@ cudaError_t launch_fused(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
         attr_done[dev].store(true, std::memory_order_release);
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 + 128 * CP); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128 + 256 * CP); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -653,12 +697,12 @@ bool plan_fused(const RuFusedParams& p, FuPlan& pl) {
     const int a_stage = 2 * pl.box_rows * BK * 2;
     const int b_stage = cat ? (BN + BN / 2) * BK * 2 : 2 * (BN / 2) * BK * 2;
     const int nkc2 = (BN + 63) / 64;
-    const int a2 = 2 * nkc2 * BM * BK * 2;
+    const int a2 = (BN % 64) == 32 ? 2 * ((nkc2 - 1) * BM * BK * 2 + BM * 64) : 2 * nkc2 * BM * BK * 2;
     pl.SA = 2;
     // T next to the halo ring where that leaves at least two weight stages (a stage holds 450-1150 cycles of MMAs and
     // is refilled from L2; round 1 measured no difference between 2 and 8 stages), else overlaid on the ring
     int left = SMEM_BUDGET - pl.SA * a_stage - a2;
-    pl.alias = left < 2 * b_stage;
+    pl.alias = left < 3 * b_stage;
     if (pl.alias) left = SMEM_BUDGET - std::max(pl.SA * a_stage, a2);
     pl.SB = std::min(MAX_STAGES, left / b_stage);
     if (pl.SB < 2) return false;
@@ -745,25 +789,12 @@ cudaError_t voc_launch_ru_fused(const RuFusedParams& p, cudaStream_t st, int num
 
     const int sms = num_sms > 0 ? num_sms : 148;
     const int grid = 2 * std::min(a.total_tiles, sms / 2);
-    const bool pipe = !pl.alias && BN == 96 && !(flags & VOC_TC_NO_PIPE);
-    static const int cp_env = []() { const char* e = getenv("VOC_RU_CP"); return e ? atoi(e) : 0; }();   // experiment hook
+    const bool pipe = !pl.alias && !(flags & VOC_TC_NO_PIPE);
     if (BN == 96) {
-        if (pl.alias) return launch_fused<96, 3, true, false>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st);
-        if (cp_env == 6)
-            return pipe ? launch_fused<96, 6, false, true>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st)
-                        : launch_fused<96, 6, false, false>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st);
-        if (cp_env == 2)
-            return pipe ? launch_fused<96, 2, false, true>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st)
-                        : launch_fused<96, 2, false, false>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st);
-        return pipe ? launch_fused<96, 3, false, true>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st)
-                    : launch_fused<96, 3, false, false>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st);
+        if (pl.alias) return launch_fused<96, 2, true, false>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st);
+        return pipe ? launch_fused<96, 2, false, true>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st)
+                    : launch_fused<96, 2, false, false>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st);
     }
-    if (cp_env == 6 || cp_env == 4)
-        return pl.alias ? launch_fused<192, 4, true, false>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st)
-                        : launch_fused<192, 4, false, false>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st);
-    if (cp_env == 2)
-        return pl.alias ? launch_fused<192, 2, true, false>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st)
-                        : launch_fused<192, 2, false, false>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st);
-    return pl.alias ? launch_fused<192, 3, true, false>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st)
-                    : launch_fused<192, 3, false, false>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st);
+    return pl.alias ? launch_fused<192, 2, true, false>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st)
+                    : launch_fused<192, 2, false, false>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st);
 }

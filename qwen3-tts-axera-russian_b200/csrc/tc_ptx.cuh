@@ -177,6 +177,17 @@ __device__ __forceinline__ void mma2_f16_ss_acc(uint32_t tmem_d, uint32_t desc_a
         "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
         ::"r"(tmem_d), "r"(desc_a_lo), "r"(desc_b_lo), "r"(desc_hi), "r"(idesc) : "memory");
 }
+// the same with separate descriptor high words for A and B (operands staged with different swizzle modes)
+__device__ __forceinline__ void mma2_f16_ss_acc_hh(uint32_t tmem_d, uint32_t desc_a_lo, uint32_t desc_a_hi, uint32_t desc_b_lo,
+                                                   uint32_t desc_b_hi, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.eq.u32 p, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(desc_a_lo), "r"(desc_a_hi), "r"(desc_b_lo), "r"(desc_b_hi), "r"(idesc) : "memory");
+}
 // completion of the pair's MMAs arrives on the barrier at the same offset in both CTAs
 // 256-bit global accesses (sm_100): one full 32-byte sector per lane per instruction
 __device__ __forceinline__ void ldg256(const void* p, float (&r)[8]) {
