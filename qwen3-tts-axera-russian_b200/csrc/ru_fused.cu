@@ -140,7 +140,10 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_a_full[MAX_STAGES], bar_a_empty[MAX_STAGES];
     __shared__ __align__(8) uint64_t bar_b_full[MAX_STAGES], bar_b_empty[MAX_STAGES];
-    __shared__ __align__(8) uint64_t bar_acc_full[NBUF], bar_acc_empty[NBUF];
+    // accumulator ring: one "empty" barrier per buffer (the issuing warp sees every use), but two "full" barriers --
+    // conv7 segments complete on full7 (group A waits there), 1x1 chains on full1 (group B): a group that merely
+    // stepped over the other group's uses of a buffer could not tell the phases of a shared barrier apart (one parity bit)
+    __shared__ __align__(8) uint64_t bar_acc_full7[NBUF], bar_acc_full1[NBUF], bar_acc_empty[NBUF];
     __shared__ __align__(8) uint64_t bar_a2_full, bar_t_free;
     __shared__ uint32_t tmem_slot;
     // per-channel epilogue parameters: conv7 bias, Snake2 a / 1/b, conv1 bias, next Snake a / 1/b
@@ -162,7 +165,7 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW1b);
         for (int i = 0; i < a.SA; ++i) { mbar_init(&bar_a_full[i], 1); mbar_init(&bar_a_empty[i], 1); }
         for (int i = 0; i < a.SB; ++i) { mbar_init(&bar_b_full[i], 1); mbar_init(&bar_b_empty[i], 1); }
-        for (int i = 0; i < NBUF; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], 2 * EPI_WARPS); }
+        for (int i = 0; i < NBUF; ++i) { mbar_init(&bar_acc_full7[i], 1); mbar_init(&bar_acc_full1[i], 1); mbar_init(&bar_acc_empty[i], 2 * EPI_WARPS); }
         mbar_init(&bar_a2_full, 2 * EPI_WARPS);
         mbar_init(&bar_t_free, 1);
         fence_barrier_init();
@@ -241,7 +244,8 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (rank == 0) {
             const uint32_t a_full0 = opaque_u32(smem_u32(&bar_a_full[0])), a_empty0 = opaque_u32(smem_u32(&bar_a_empty[0]));
             const uint32_t b_full0 = opaque_u32(smem_u32(&bar_b_full[0])), b_empty0 = opaque_u32(smem_u32(&bar_b_empty[0]));
-            const uint32_t acc_full0 = opaque_u32(smem_u32(&bar_acc_full[0])), acc_empty0 = opaque_u32(smem_u32(&bar_acc_empty[0]));
+            const uint32_t acc_full0 = opaque_u32(smem_u32(&bar_acc_full7[0])), acc_empty0 = opaque_u32(smem_u32(&bar_acc_empty[0]));
+            const uint32_t acc_full1_0 = opaque_u32(smem_u32(&bar_acc_full1[0]));
             const uint32_t a2_full = opaque_u32(smem_u32(&bar_a2_full)), t_free = opaque_u32(smem_u32(&bar_t_free));
             const uint32_t rt0 = tmem_base >> 24;
             auto reg = [&](uint32_t x) { return opaque_u32(x + rt0); };
@@ -370,7 +374,7 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             }
                         }
                         mma2_commit_both_a(b_empty0 + 8 * sb);
-                        if (kc == NKC2 - 1) { mma2_commit_both_a(acc_full0 + 8 * as); mma2_commit_both_a(t_free); }
+                        if (kc == NKC2 - 1) { mma2_commit_both_a(acc_full1_0 + 8 * as); mma2_commit_both_a(t_free); }
                     }
                     __syncwarp();
                     b_lo += B_STAGE >> 4;
@@ -416,8 +420,9 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         asm volatile("bar.sync 1, %0;" ::"n"(64 * EPI_WARPS) : "memory");
         // The accumulator ring is used in the issuing warp's order: per step the conv7 segments, then one 1x1 chain.
         // Each group waits for and hands back only its own buffers and steps over the other group's.
-        int as = 0, pas = 0;
-        auto skip = [&](int n) { for (int i = 0; i < n; ++i) if (++as == NBUF) { as = 0; pas ^= 1; } };
+        int as = 0;                                   // position in the ring (all uses, both groups')
+        uint32_t par = 0;                             // bit b: parity of this group's next wait on its full barrier of buffer b
+        auto skip = [&](int n) { for (int i = 0; i < n; ++i) if (++as == NBUF) as = 0; };
         uint32_t acc_empty_leader[NBUF];
 #pragma unroll
         for (int i = 0; i < NBUF; ++i) acc_empty_leader[i] = mapa_u32(&bar_acc_empty[i], 0);
@@ -438,7 +443,8 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 float acc[HN];
                 // conv7 accumulation segments of tile s, added in FP32 with round-to-nearest as in the unfused kernel
                 for (int seg = 0; seg < nseg; ++seg) {
-                    { PF_T0(tw); mbar_wait(&bar_acc_full[as], pas); PF_ACC(pf_w7, tw); }
+                    { PF_T0(tw); mbar_wait(&bar_acc_full7[as], (par >> as) & 1u); PF_ACC(pf_w7, tw); }
+                    par ^= 1u << as;
                     tc_fence_after();
                     const uint32_t taddr = tlane + (uint32_t)as * ACC_COLS;
                     const bool first = seg == 0;
@@ -582,7 +588,8 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 float res[2][2][8];                       // two 16-column windows of the residual row, alternating
                 if (valid) { ldg256(Rrow, res[0][0]); ldg256(Rrow + 8, res[0][1]); }
                 if (s + 1 < n_my) prefetch_res(tile + walkers);   // the next tile's rows: HBM -> L2 while this one is finished
-                { PF_T0(tw); mbar_wait(&bar_acc_full[as], pas); PF_ACC(pf_w1, tw); }
+                { PF_T0(tw); mbar_wait(&bar_acc_full1[as], (par >> as) & 1u); PF_ACC(pf_w1, tw); }
+                par ^= 1u << as;
                 PF_T0(tf);
                 tc_fence_after();
                 const uint32_t taddr = tlane + (uint32_t)as * ACC_COLS;
