@@ -95,6 +95,24 @@ int voc_synthesize_dev(void* h, const long long* d_codes, int n_tokens, float* d
 int voc_synthesize_batch_pcm16(void* h, const long long* codes, const int* n_tokens, int n_requests,
                                short* out, long long cap, long long* out_offsets);
 
+/* ---- carried-state decode (OPT-IN: the output differs from the reference's) --------
+ * The reference decodes a long request as 64-frame windows with a stride of 48 and crossfades the 16
+ * recomputed frames (dual_npu/vocoder_server.py:83-119): 25 % of the frames are computed twice and the
+ * window edges differ from an un-chunked decode.  These entry points decode ONE sequence incrementally
+ * instead: every causal layer keeps the rows of left context it needs ((k-1)*dilation input rows per
+ * convolution, one per transposed convolution, sliding_window-1 rows of K/V for the attention) from one
+ * call to the next, so that the concatenated output of successive calls equals the decoder run once on
+ * the whole sequence -- each call emits exactly n_tokens * 1920 samples, nothing is recomputed, there is
+ * no crossfade and no short-last-window duplication.  Needs transconv_trim = "right" (the
+ * causal, length-preserving trim); VOC_E_STATE otherwise.  voc_stream_reset starts a new sequence.
+ * Host pointers; any n_tokens >= 1 per call, at most 10240 frames per sequence.                   */
+int       voc_stream_reset(void* h);
+long long voc_stream_position(void* h);      /* frames decoded since the last reset */
+int       voc_stream_decode_f32(void* h, const long long* codes, int n_tokens, float* out, long long cap,
+                                long long* n_out);
+int       voc_stream_decode_pcm16(void* h, const long long* codes, int n_tokens, short* out, long long cap,
+                                  long long* n_out);
+
 /* The _dev twins do not synchronise, so an out-of-range code cannot be reported by their
  * return value.  voc_check_dev synchronises `stream` and returns VOC_E_INVALID if any launch
  * since the last check met a code outside [0, codebook_size) (and clears the flag).        */

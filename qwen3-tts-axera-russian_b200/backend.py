@@ -49,6 +49,10 @@ SIGNATURES = {
     "voc_synthesize_batch_pcm16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong,
                                              C.c_void_p]),
     "voc_check_dev": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "voc_stream_reset": (C.c_int, [C.c_void_p]),
+    "voc_stream_position": (C.c_longlong, [C.c_void_p]),
+    "voc_stream_decode_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.POINTER(C.c_longlong)]),
+    "voc_stream_decode_pcm16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.POINTER(C.c_longlong)]),
     "voc_plan": (C.c_int, [C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_void_p,
                            C.POINTER(C.c_longlong), C.POINTER(C.c_int)]),
     "voc_fade_tables": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
@@ -286,6 +290,21 @@ class Vocoder:
         self._ck(self.lib.voc_synthesize_batch_pcm16(self._h, codes.ctypes.data, lens.ctypes.data, len(reqs),
                                                      out.ctypes.data, cap, offs.ctypes.data))
         return [out[offs[i]:offs[i + 1]] for i in range(len(reqs))]
+
+    # ---- carried-state decode (opt-in) ----
+    def stream_reset(self):
+        self._ck(self.lib.voc_stream_reset(self._h))
+
+    def stream_decode(self, codes: np.ndarray, pcm16: bool = False) -> np.ndarray:
+        """The next `len(codes)` frames of the current sequence -> their len(codes) * 1920 samples (float32, or int16
+        with the reference's truncating conversion).  Successive calls concatenate to the un-chunked decode."""
+        codes = self._codes2d(codes)
+        n = len(codes)
+        out = np.empty(n * self.cfg.samples_per_frame, dtype=np.int16 if pcm16 else np.float32)
+        cnt = C.c_longlong(0)
+        fn = self.lib.voc_stream_decode_pcm16 if pcm16 else self.lib.voc_stream_decode_f32
+        self._ck(fn(self._h, codes.ctypes.data, n, out.ctypes.data, out.size, C.byref(cnt)))
+        return out[: cnt.value]
 
     def synthesize_dev(self, d_codes, n_tokens: int, d_out_f32=None, d_out_i16=None, cap: int = 0,
                        stream: int = 0) -> int:

@@ -734,6 +734,7 @@ bool voc_ru_fused_eligible(const RuFusedParams& p) {
     if (p.C != 96 && p.C != 192) return false;
     if (p.ksz < 2 || p.ksz > VOC_MAX_TAPS || p.dil < 1) return false;
     if (p.L <= BM || p.B < 1) return false;                  // the pair form wants at least two M tiles per window
+    if (p.a_halo < 0 || (p.a_halo && p.B != 1)) return false;
     if (!p.A_hi || !p.A_lo || !p.W7tc || !p.W1tc || !p.R || !p.S_hi || !p.S_lo) return false;
     if (!p.bias7 || !p.bias1 || !p.sn2_a || !p.sn2_invb || !p.snn_a || !p.snn_invb) return false;
     auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
@@ -752,7 +753,7 @@ cudaError_t voc_launch_ru_fused(const RuFusedParams& p, cudaStream_t st, int num
     FuArgs a;
     memset(&a, 0, sizeof(a));
     a.M = p.L; a.B = p.B; a.ntaps = p.ksz;
-    a.a_min_off = -(p.ksz - 1) * p.dil;
+    a.a_min_off = p.a_halo - (p.ksz - 1) * p.dil;       // row 0 of the unit is row a_halo of the A tensor
     a.tap_row0 = 0; a.tap_step = p.dil;
     a.a_box_rows = pl.box_rows;
     // the same K chunking and segment schedule as voc_launch_tapgemm_tc gives these two layers (bit-identical results)
@@ -780,7 +781,8 @@ cudaError_t voc_launch_ru_fused(const RuFusedParams& p, cudaStream_t st, int num
 
     CUtensorMap tmA, tmB, tmB2, tmW1, tmW1b;
     const long long a_pl = (long long)(p.A_lo - p.A_hi);
-    if (!voc_tc_get_map(p.A_hi, p.C, p.L, p.B, (long long)p.C * 2, bs * 2, a_pl * 2, BK, a.a_box_rows, 2, &tmA))
+    if (!voc_tc_get_map(p.A_hi, p.C, p.L + p.a_halo, p.B, (long long)p.C * 2, ((long long)(p.L + p.a_halo) * p.C) * 2, a_pl * 2, BK,
+                        a.a_box_rows, 2, &tmA))
         return cudaErrorInvalidValue;
     const long long wrow = (long long)p.C * 2, wtap = (long long)p.C * p.C * 2;
     if (!voc_tc_get_map(p.W7tc, p.C, p.C, p.ksz, wrow, wtap, p.w7_plane * 2, BK, cat ? BN : BN / 2, cat ? 1 : 2, &tmB))

@@ -317,7 +317,8 @@ cudaError_t voc_launch_rmsnorm(const float* x, const float* w, VocAct y, int row
 __global__ void dwconv_ln_kernel(const float* __restrict__ x, const float* __restrict__ dw_w,
                                  const float* __restrict__ dw_b, const float* __restrict__ ln_w,
                                  const float* __restrict__ ln_b, VocAct y, int L, int C,
-                                 int ksz, float eps) {
+                                 int ksz, float eps, int halo) {
+    // halo: rows of carried history that precede row 0 in memory (streaming decode); 0 = causal zero padding
     extern __shared__ float sh[];          // C floats + 32 reduction slots
     float* h = sh;
     float* red = sh + C;
@@ -328,7 +329,7 @@ __global__ void dwconv_ln_kernel(const float* __restrict__ x, const float* __res
         float a = dw_b[c];
         for (int j = 0; j < ksz; ++j) {
             const int tt = t - (ksz - 1 - j);
-            if (tt >= 0) a = fmaf(dw_w[j * C + c], xb[(long long)tt * C + c], a);
+            if (tt >= -halo) a = fmaf(dw_w[j * C + c], xb[(long long)tt * C + c], a);
         }
         h[c] = a;
         lsum += a;
@@ -354,10 +355,11 @@ __global__ void dwconv_ln_kernel(const float* __restrict__ x, const float* __res
 
 cudaError_t voc_launch_dwconv_ln(const float* x, const float* dw_w, const float* dw_b, const float* ln_w,
                                  const float* ln_b, VocAct y, int B, int L, int C, int ksz, float eps,
-                                 cudaStream_t st) {
+                                 cudaStream_t st, int halo) {
     if (B <= 0 || L <= 0) return cudaSuccess;
+    if (halo && B != 1) return cudaErrorInvalidValue;
     dim3 grid(L, B);
-    dwconv_ln_kernel<<<grid, 256, (C + 32) * sizeof(float), st>>>(x, dw_w, dw_b, ln_w, ln_b, y, L, C, ksz, eps);
+    dwconv_ln_kernel<<<grid, 256, (C + 32) * sizeof(float), st>>>(x, dw_w, dw_b, ln_w, ln_b, y, L, C, ksz, eps, halo);
     return cudaGetLastError();
 }
 
@@ -461,6 +463,117 @@ attention_kernel(const float* __restrict__ qkv, VocAct out, int T, int heads,
     }
 }
 
+// Streaming form (carried-state decode): one sequence; the qkv buffer holds `kv_halo` rows of history
+// (the previous segments' last rows, K and V parts used) before the T new rows, whose absolute positions start at pos0.
+template <int HD>
+__global__ void __launch_bounds__(64)
+attention_stream_kernel(const float* __restrict__ qkv, VocAct out, int T, int heads,
+                        const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, int window,
+                        int kv_halo, int pos0) {
+    constexpr int H2 = HD / 2;
+    __shared__ __align__(16) float Ks[64][HD];
+    __shared__ __align__(16) float Vs[64][HD];
+    const int hh = blockIdx.y, q0 = blockIdx.x * 64;
+    const int tid = threadIdx.x;
+    const int A = heads * HD;
+    const int ld = 3 * A;
+    const int R = kv_halo + T;                               // rows in the buffer
+    const int qi = q0 + tid;
+    const bool qvalid = qi < T;
+    const int qpos = pos0 + qi;
+    float q[HD], o[HD];
+    if (qvalid) {
+        const float* qr = qkv + (long long)(kv_halo + qi) * ld + hh * HD;
+#pragma unroll
+        for (int d = 0; d < H2; ++d) {
+            const float c = rope_cos[(long long)qpos * H2 + d], s = rope_sin[(long long)qpos * H2 + d];
+            const float x1 = qr[d], x2 = qr[d + H2];
+            q[d] = x1 * c - x2 * s;
+            q[d + H2] = x2 * c + x1 * s;
+        }
+    } else {
+#pragma unroll
+        for (int d = 0; d < HD; ++d) q[d] = 0.f;
+    }
+#pragma unroll
+    for (int d = 0; d < HD; ++d) o[d] = 0.f;
+    float mx = -INFINITY, l = 0.f;
+    const float scaling = rsqrtf((float)HD);
+    int rstart = kv_halo + q0 - window + 1; if (rstart < 0) rstart = 0;      // first buffer row any query of this block sees
+    rstart = (rstart / 64) * 64;
+    const int rend = min(R, kv_halo + q0 + 64);
+    for (int r0 = rstart; r0 < rend; r0 += 64) {
+        __syncthreads();
+        for (int idx = tid; idx < 64 * H2; idx += 64) {
+            const int j = idx / H2, d = idx - j * H2;
+            const int rj = r0 + j;
+            float k1 = 0.f, k2 = 0.f, v1 = 0.f, v2 = 0.f, c = 1.f, s = 0.f;
+            if (rj < R) {
+                const float* kr = qkv + (long long)rj * ld + A + hh * HD;
+                const float* vr = qkv + (long long)rj * ld + 2 * A + hh * HD;
+                k1 = kr[d]; k2 = kr[d + H2]; v1 = vr[d]; v2 = vr[d + H2];
+                const int kp = pos0 - kv_halo + rj;              // absolute position (>= 0: the halo never predates frame 0)
+                c = rope_cos[(long long)kp * H2 + d]; s = rope_sin[(long long)kp * H2 + d];
+            }
+            Ks[j][d] = k1 * c - k2 * s;
+            Ks[j][d + H2] = k2 * c + k1 * s;
+            Vs[j][d] = v1;
+            Vs[j][d + H2] = v2;
+        }
+        __syncthreads();
+        if (!qvalid) continue;
+        const int jmax = min(64, rend - r0);
+        for (int j = 0; j < jmax; ++j) {
+            const int kp = pos0 - kv_halo + r0 + j;
+            if (kp > qpos || kp <= qpos - window) continue;
+            float s = 0.f;
+#pragma unroll
+            for (int d = 0; d < HD; d += 4) {
+                const float4 k4 = *reinterpret_cast<const float4*>(&Ks[j][d]);
+                s = fmaf(q[d], k4.x, s); s = fmaf(q[d + 1], k4.y, s);
+                s = fmaf(q[d + 2], k4.z, s); s = fmaf(q[d + 3], k4.w, s);
+            }
+            s *= scaling;
+            if (s > mx) {
+                const float corr = expf(mx - s);
+                l *= corr;
+#pragma unroll
+                for (int d = 0; d < HD; ++d) o[d] *= corr;
+                mx = s;
+            }
+            const float pexp = expf(s - mx);
+            l += pexp;
+#pragma unroll
+            for (int d = 0; d < HD; d += 4) {
+                const float4 v4 = *reinterpret_cast<const float4*>(&Vs[j][d]);
+                o[d] = fmaf(pexp, v4.x, o[d]); o[d + 1] = fmaf(pexp, v4.y, o[d + 1]);
+                o[d + 2] = fmaf(pexp, v4.z, o[d + 2]); o[d + 3] = fmaf(pexp, v4.w, o[d + 3]);
+            }
+        }
+    }
+    if (qvalid) {
+        const float inv = 1.f / l;
+        const long long oo = (long long)qi * A + hh * HD;
+#pragma unroll
+        for (int d = 0; d < HD; d += 4)
+            act_store4(out, oo + d, make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv));
+    }
+}
+
+cudaError_t voc_launch_attention_stream(const float* qkv, VocAct out, int T, int heads, int head_dim,
+                                        const float* rope_cos, const float* rope_sin, int window, int kv_halo,
+                                        int pos0, cudaStream_t st) {
+    if (T <= 0) return cudaSuccess;
+    dim3 grid((T + 63) / 64, heads, 1);
+    switch (head_dim) {
+        case 64: attention_stream_kernel<64><<<grid, 64, 0, st>>>(qkv, out, T, heads, rope_cos, rope_sin, window, kv_halo, pos0); break;
+        case 32: attention_stream_kernel<32><<<grid, 64, 0, st>>>(qkv, out, T, heads, rope_cos, rope_sin, window, kv_halo, pos0); break;
+        case 16: attention_stream_kernel<16><<<grid, 64, 0, st>>>(qkv, out, T, heads, rope_cos, rope_sin, window, kv_halo, pos0); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t voc_launch_attention(const float* qkv, VocAct out, int B, int T, int heads, int head_dim,
                                  const float* rope_cos, const float* rope_sin, int window,
                                  cudaStream_t st) {
@@ -504,7 +617,7 @@ cudaError_t voc_launch_swiglu(const float* gu, VocAct out, long long rows, int i
 template <int KS>
 __global__ void __launch_bounds__(256)
 head_kernel(VocAct S, long long s_bstride, int L, int C, const float* __restrict__ w /*[k][C]*/, float bias,
-            float* __restrict__ out, long long o_bstride) {
+            float* __restrict__ out, long long o_bstride, int halo) {
     extern __shared__ float ws[];           // KS x C
     for (int idx = threadIdx.x; idx < KS * C; idx += blockDim.x) ws[idx] = w[idx];
     __syncthreads();
@@ -514,7 +627,7 @@ head_kernel(VocAct S, long long s_bstride, int L, int C, const float* __restrict
     const int t0 = (blockIdx.x * (blockDim.x >> 5) + warp) * OUT_PER_WARP;   // first output of this warp
     if (t0 >= L) return;
     const int t = t0 - (KS - 1) + lane;                                      // the row this lane reads
-    const bool have = t >= 0 && t < L;
+    const bool have = t >= -halo && t < L;       // halo rows of carried history precede row 0 (streaming decode)
     float p[KS];
 #pragma unroll
     for (int j = 0; j < KS; ++j) p[j] = 0.f;
@@ -591,15 +704,16 @@ head_kernel_generic(VocAct S, long long s_bstride, int L, int C, int ksz,
 }
 
 cudaError_t voc_launch_head(VocAct S, long long s_bstride, int L, int C, int ksz, const float* w,
-                            float bias, float* out, long long o_bstride, int B, cudaStream_t st) {
+                            float bias, float* out, long long o_bstride, int B, cudaStream_t st, int halo) {
     if (C % 4) return cudaErrorInvalidValue;
     if (B <= 0 || L <= 0) return cudaSuccess;
     if (ksz == 7 && C % 8 == 0 && s_bstride % 8 == 0) {
         const int out_per_block = 8 * (32 - 6);
         dim3 grid((L + out_per_block - 1) / out_per_block, B);
-        head_kernel<7><<<grid, 256, (size_t)7 * C * sizeof(float), st>>>(S, s_bstride, L, C, w, bias, out, o_bstride);
+        head_kernel<7><<<grid, 256, (size_t)7 * C * sizeof(float), st>>>(S, s_bstride, L, C, w, bias, out, o_bstride, halo);
         return cudaGetLastError();
     }
+    if (halo) return cudaErrorNotSupported;
     const size_t smem = ((size_t)(64 + ksz - 1) * (C + 1) + (size_t)ksz * C) * sizeof(float);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(head_kernel_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

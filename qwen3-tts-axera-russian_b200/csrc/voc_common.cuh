@@ -125,6 +125,7 @@ void voc_tc_clear_cache();
 // ------------------------------------------------------------------------------------
 struct RuFusedParams {
     const __half* A_hi;  const __half* A_lo;  int L;  int C;  int B;  int dil;  int ksz;
+    int a_halo;          // rows of carried history stored before row 0 of A (streaming decode, B = 1); 0 = causal zeros
     const __half* W7tc;  long long w7_plane;  float w7scale;  const float* bias7;
     const float* sn2_a;  const float* sn2_invb;
     const __half* W1tc;  long long w1_plane;  float w1scale;  const float* bias1;
@@ -149,13 +150,16 @@ cudaError_t voc_launch_rmsnorm(const float* x, const float* w, VocAct y, int row
                                cudaStream_t st);
 cudaError_t voc_launch_dwconv_ln(const float* x, const float* dw_w, const float* dw_b, const float* ln_w,
                                  const float* ln_b, VocAct y, int B, int L, int C, int ksz, float eps,
-                                 cudaStream_t st);
+                                 cudaStream_t st, int halo = 0);
 cudaError_t voc_launch_attention(const float* qkv, VocAct out, int B, int T, int heads, int head_dim,
                                  const float* rope_cos, const float* rope_sin, int window,
                                  cudaStream_t st);
+cudaError_t voc_launch_attention_stream(const float* qkv, VocAct out, int T, int heads, int head_dim,
+                                        const float* rope_cos, const float* rope_sin, int window, int kv_halo,
+                                        int pos0, cudaStream_t st);
 cudaError_t voc_launch_swiglu(const float* gu, VocAct out, long long rows, int inter, cudaStream_t st);
 cudaError_t voc_launch_head(VocAct S, long long s_bstride, int L, int C, int ksz, const float* w,
-                            float bias, float* out, long long o_bstride, int B, cudaStream_t st);
+                            float bias, float* out, long long o_bstride, int B, cudaStream_t st, int halo = 0);
 cudaError_t voc_launch_stitch(const float* chunks, long long chunk_stride, const int* win_meta,
                               int n_windows, int ov, const float* fade_out, const float* fade_in,
                               float* out_f32, short* out_i16, int max_a_len, cudaStream_t st);

@@ -221,6 +221,11 @@ struct Engine {
     short* d_pcm = nullptr; size_t pcm_cap = 0;
     std::map<std::string, std::pair<std::shared_ptr<DevBuf>, size_t>> dbg;
 
+    // carried-state decode: frames decoded so far and, per convolution / attention layer, the rows of
+    // its input that the next segment's left context needs (created on first use, in the order stream_segment walks)
+    struct Stream { long long pos = 0; std::vector<std::pair<float*, size_t>> halos; } strm;
+    int rope_positions = 0;
+
     // per-launch CUDA-event profile (option "profile" = "1"), read by voc_profile_report
     bool profile = false;
     struct ProfRec { const char* tag; double flops, bytes; cudaEvent_t e0, e1; };
@@ -235,6 +240,7 @@ struct Engine {
     ~Engine() {
         for (auto& g : graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
         for (void* p : owned) cudaFree(p);
+        for (auto& hl : strm.halos) cudaFree(hl.first);
         if (d_err) cudaFree(d_err);
         if (d_meta) cudaFree(d_meta);
         if (d_fade_out) cudaFree(d_fade_out);
@@ -514,7 +520,10 @@ static int engine_finalize(Engine* E) {
         }
         REQ(E->xf_norm = upload_named(E, "xf.norm.w", c.xf_hidden));
         // rotary table evaluated in float64 then cast to float32 (angles t * theta^(-2d/hd))
-        const int T = c.chunk_frames, H2 = c.xf_head_dim / 2;
+        // positions 0 .. 10 239: a window's frames, or the absolute frame index of a carried-state decode (the
+        // protocol's longest request is 10 000 frames, vocoder_server.py:149)
+        const int T = std::max(c.chunk_frames, 10240), H2 = c.xf_head_dim / 2;
+        E->rope_positions = T;
         std::vector<float> cs((size_t)T * H2), sn((size_t)T * H2);
         for (int t = 0; t < T; ++t) for (int d = 0; d < H2; ++d) {
             const double inv = 1.0 / std::pow(c.rope_theta, (2.0 * d) / c.xf_head_dim);
@@ -821,6 +830,211 @@ static int run_wave(Engine* E, const long long* d_codes, int n_frames, int win_s
     for (int s = 0; s < nw; s += bw) {
         if (int r = run_back(E, x, s, L, std::min(bw, nw - s), chunk_out + (long long)s * Lc, Lc, st)) return r;
     }
+    return VOC_OK;
+}
+
+// --------------------------------------------------------------------------------------
+// Carried-state decode (opt-in, needs transconv_trim = "right"): ONE sequence is decoded segment by
+// segment; instead of the reference's 64-frame windows with 16 frames recomputed and crossfaded
+// (vocoder_server.py:83-119), every causal layer finds its left context -- (k-1)*dilation rows of its input, one row
+// for a transposed convolution, sliding_window-1 rows of K/V for the attention -- in a halo that precedes row 0 of its
+// input buffer and was saved from the previous segment.  Output = the un-chunked decoder on the whole sequence.
+// --------------------------------------------------------------------------------------
+static int stream_segment(Engine* E, const long long* d_codes, int n, float* out, cudaStream_t st) {
+    const Cfg& c = E->cfg;
+    const long long pos0 = E->strm.pos;
+    size_t hidx = 0;
+    // the state buffer of the next layer in walking order (zeros = the causal zero padding of frame 0)
+    auto halo_state = [&](size_t elems, float** ptr) -> int {
+        if (hidx == E->strm.halos.size()) {
+            float* d = nullptr;
+            CK(cudaMalloc(&d, std::max<size_t>(elems, 1) * sizeof(float)));
+            E->strm.halos.push_back({d, elems});
+            CK(cudaMemsetAsync(d, 0, std::max<size_t>(elems, 1) * sizeof(float), st));
+        }
+        if (E->strm.halos[hidx].second != elems) return fail(E, VOC_E_STATE, "stream state does not match the architecture");
+        *ptr = E->strm.halos[hidx++].first;
+        return VOC_OK;
+    };
+    auto cpy = [&](void* d, const void* sr, size_t bytes) -> int {
+        if (bytes) CK(cudaMemcpyAsync(d, sr, bytes, cudaMemcpyDeviceToDevice, st));
+        E->launches++;
+        return VOC_OK;
+    };
+    // operand tensors (two fp16 planes, or float32 on the CUDA-core path): rows [0, H) <- state; state <- rows [L, L + H)
+    auto restore_op = [&](float* buf, const float* stt, int H, int C) -> int {
+        const VocAct a = act(E, buf);
+        const size_t n_el = (size_t)H * C;
+        if (a.f) return cpy(a.f, stt, n_el * 4);
+        if (int r = cpy(a.hi, stt, n_el * 2)) return r;
+        return cpy(a.lo, reinterpret_cast<const __half*>(stt) + n_el, n_el * 2);
+    };
+    auto save_op = [&](float* buf, float* stt, int H, int C, int L) -> int {
+        const VocAct a = act(E, buf);
+        const size_t n_el = (size_t)H * C, off = (size_t)L * C;
+        if (a.f) return cpy(stt, a.f + off, n_el * 4);
+        if (int r = cpy(stt, a.hi + off, n_el * 2)) return r;
+        return cpy(reinterpret_cast<__half*>(stt) + n_el, a.lo + off, n_el * 2);
+    };
+#define KLAUNCH(tag, flops, bytes, call) do { ProfScope _ps(E, st, tag, flops, bytes); CK(call); } while (0)
+#define GEMM(tag, p) do { if (int _r = gemm_ck(E, p, st, tag)) return _r; } while (0)
+    const int T = n;
+    // ---- codebook sum -> pre-conv (k taps: k - 1 frames of history)
+    const int Hpc = c.pre_conv_kernel - 1;
+    KLAUNCH("rvq_gather", 0.0, 4.0 * T * c.rvq_dim * (c.num_quantizers + 1.0),
+            voc_launch_rvq_gather(d_codes, n, T, T, 1, c.num_quantizers, c.codebook_size, E->rvq_tables, c.rvq_dim,
+                                  act_at(E, E->f_rvq, (size_t)Hpc * c.rvq_dim), E->d_err, st, nullptr));
+    {
+        float* stt; if (int r = halo_state((size_t)Hpc * c.rvq_dim, &stt)) return r;
+        if (int r = restore_op(E->f_rvq, stt, Hpc, c.rvq_dim)) return r;
+        TapGemmParams p = gp(E->pre_conv, act(E, E->f_rvq), 0, Hpc + T, Hpc, T, 1);
+        setS(p, act(E, E->f_pre), nullptr);
+        GEMM("pre_conv", p);
+        if (int r = save_op(E->f_rvq, stt, Hpc, c.rvq_dim, T)) return r;
+    }
+    float* x = E->f_pre;
+    if (c.pre_transformer) {
+        const int rows = T, H = c.xf_hidden, A = c.attn_dim();
+        const int Hq = std::max(c.sliding_window - 1, 0);
+        const int kvh = (int)std::min<long long>(Hq, pos0);            // rows of history that exist
+        const double nb = 8.0 * rows * H;
+        { TapGemmParams p = gp(E->xf_in, act(E, x), 0, rows, 0, rows, 1); setY(p, E->f_h); GEMM("xf.gemm", p); }
+        for (int l = 0; l < c.xf_layers; ++l) {
+            auto& Ly = E->xf[l];
+            float* stt; if (int r = halo_state((size_t)Hq * 3 * A, &stt)) return r;
+            KLAUNCH("xf.norm", 0.0, nb, voc_launch_rmsnorm(E->f_h, Ly.ln1, act(E, E->f_hn), rows, H, (float)c.rms_eps, st));
+            float* qkv_new = E->f_qkv + (size_t)Hq * 3 * A;          // this segment's rows follow the history rows
+            { TapGemmParams p = gp(Ly.qkv, act(E, E->f_hn), 0, rows, 0, rows, 1); setY(p, qkv_new); GEMM("xf.gemm", p); }
+            if (int r = cpy(E->f_qkv, stt, (size_t)Hq * 3 * A * 4)) return r;
+            KLAUNCH("xf.attn", 4.0 * c.xf_heads * (double)T * std::min(T + kvh, c.sliding_window) * c.xf_head_dim, 16.0 * rows * A,
+                    voc_launch_attention_stream(E->f_qkv + (size_t)(Hq - kvh) * 3 * A, act(E, E->f_att), T, c.xf_heads, c.xf_head_dim,
+                                                E->rope_cos, E->rope_sin, c.sliding_window, kvh, (int)pos0, st));
+            if (int r = cpy(stt, E->f_qkv + (size_t)T * 3 * A, (size_t)Hq * 3 * A * 4)) return r;
+            { TapGemmParams p = gp(Ly.o, act(E, E->f_att), 0, rows, 0, rows, 1); p.scale = Ly.ls_attn; setR(p, E->f_h); setY(p, E->f_h); GEMM("xf.gemm", p); }
+            KLAUNCH("xf.norm", 0.0, nb, voc_launch_rmsnorm(E->f_h, Ly.ln2, act(E, E->f_hn), rows, H, (float)c.rms_eps, st));
+            { TapGemmParams p = gp(Ly.gu, act(E, E->f_hn), 0, rows, 0, rows, 1); setY(p, E->f_gu); GEMM("xf.gemm", p); }
+            KLAUNCH("xf.swiglu", 0.0, 12.0 * rows * c.xf_inter, voc_launch_swiglu(E->f_gu, act(E, E->f_act), rows, c.xf_inter, st));
+            { TapGemmParams p = gp(Ly.down, act(E, E->f_act), 0, rows, 0, rows, 1); p.scale = Ly.ls_mlp; setR(p, E->f_h); setY(p, E->f_h); GEMM("xf.gemm", p); }
+        }
+        KLAUNCH("xf.norm", 0.0, nb, voc_launch_rmsnorm(E->f_h, E->xf_norm, act(E, E->f_hn), rows, H, (float)c.rms_eps, st));
+        { TapGemmParams p = gp(E->xf_out, act(E, E->f_hn), 0, rows, 0, rows, 1); setS(p, act(E, E->f_x), nullptr); GEMM("xf.gemm", p); }
+        x = E->f_x;
+    }
+    // ---- up-sampling stages: k = s transposed conv (no context), ConvNeXt (depth-wise conv: k - 1 rows)
+    const int Hk = c.conv_kernel - 1;
+    int L = T;
+    for (size_t u = 0; u < E->ups.size(); ++u) {
+        auto& U = E->ups[u];
+        const int C = c.latent_dim, r = c.upsampling_ratios[u];
+        float* d1 = (x == E->f_x) ? E->f_x2 : E->f_x;
+        float* d2 = (d1 == E->f_x) ? E->f_x2 : E->f_x;
+        const bool last_up = (u + 1 == E->ups.size());
+        const size_t out_off = last_up ? (size_t)Hk * C : 0;            // conv-in wants Hk rows of history before its input
+        if (!c.convnext) {
+            TapGemmParams p = gp(U.convt, act(E, x), (long long)L * C, L, 0, L, 1);
+            setS(p, act_at(E, d1, out_off), nullptr);
+            GEMM("up.convt", p);
+            L *= r; x = d1;
+            continue;
+        }
+        float* d1n = d1 + (size_t)Hk * C;                               // float32, Hk history rows in front
+        { TapGemmParams p = gp(U.convt, act(E, x), (long long)L * C, L, 0, L, 1); setY(p, d1n); GEMM("up.convt", p); }
+        L *= r;
+        float* stt; if (int rr = halo_state((size_t)Hk * C, &stt)) return rr;
+        if (int rr = cpy(d1, stt, (size_t)Hk * C * 4)) return rr;
+        KLAUNCH("up.dwconv_ln", 2.0 * L * C * c.conv_kernel, 8.0 * L * C,
+                voc_launch_dwconv_ln(d1n, U.dw_w, U.dw_b, U.ln_w, U.ln_b, act(E, E->f_ln), 1, L, C, c.conv_kernel, (float)c.ln_eps, st, Hk));
+        if (int rr = cpy(stt, d1 + (size_t)L * C, (size_t)Hk * C * 4)) return rr;
+        { TapGemmParams p = gp(U.pw1, act(E, E->f_ln), 0, L, 0, L, 1); p.act = VOC_ACT_GELU; setS(p, act(E, E->f_mid), nullptr); GEMM("up.pw1", p); }
+        { TapGemmParams p = gp(U.pw2, act(E, E->f_mid), 0, L, 0, L, 1); p.scale = U.gamma; setR(p, d1n); setS(p, act_at(E, d2, out_off), nullptr); GEMM("up.pw2", p); }
+        x = d2;
+    }
+    // ---- decoder conv-in (k taps) -> Snake of block 0 -> the operand of block 0's transposed conv (1 row of history)
+    float* bX = E->big[0].p; float* bS = E->big[1].p; float* bT = E->big[2].p; float* bX2 = E->big[3].p;
+    {
+        float* stt; if (int r = halo_state((size_t)Hk * c.latent_dim, &stt)) return r;
+        if (int r = restore_op(x, stt, Hk, c.latent_dim)) return r;
+        TapGemmParams p = gp(E->conv_in, act(E, x), 0, Hk + L, Hk, L, 1);
+        setS(p, act_at(E, bS, (size_t)1 * c.decoder_dim), &E->blocks[0].s_in);
+        GEMM("conv_in", p);
+        if (int r = save_op(x, stt, Hk, c.latent_dim, L)) return r;
+    }
+    static const char* const T_CONVT[] = {"dec0.convt", "dec1.convt", "dec2.convt", "dec3.convt", "decN.convt"};
+    static const char* const T_C7[] = {"dec0.ru.conv7", "dec1.ru.conv7", "dec2.ru.conv7", "dec3.ru.conv7", "decN.ru.conv7"};
+    static const char* const T_C1[] = {"dec0.ru.conv1", "dec1.ru.conv1", "dec2.ru.conv1", "dec3.ru.conv1", "decN.ru.conv1"};
+    static const char* const T_FU[] = {"dec0.ru.fused", "dec1.ru.fused", "dec2.ru.fused", "dec3.ru.fused", "decN.ru.fused"};
+    for (size_t b = 0; b < E->blocks.size(); ++b) {
+        auto& Bk = E->blocks[b];
+        const size_t ti = std::min<size_t>(b, 4);
+        const int C = Bk.cout;
+        const int H0 = Hk * c.dilations[0];
+        {   // transposed conv: out[t s + j] = x[t] W[j] + x[t - 1] W[j + s]
+            float* stt; if (int r = halo_state((size_t)Bk.cin, &stt)) return r;
+            if (int r = restore_op(bS, stt, 1, Bk.cin)) return r;
+            TapGemmParams p = gp(Bk.convt, act(E, bS), 0, 1 + L, 1, L, 1);
+            setY(p, bX); setS(p, act_at(E, bT, (size_t)H0 * C), &Bk.s_ru0_tiled);
+            GEMM(T_CONVT[ti], p);
+            if (int r = save_op(bS, stt, 1, Bk.cin, L)) return r;
+        }
+        L *= Bk.stride;
+        std::swap(bS, bT);
+        for (size_t j = 0; j < Bk.ru.size(); ++j) {
+            auto& R = Bk.ru[j];
+            const int H = Hk * c.dilations[j];
+            const bool last_ru = (j + 1 == Bk.ru.size());
+            const SnakeP& nxt = !last_ru ? Bk.ru[j + 1].s1 : (b + 1 < E->blocks.size() ? E->blocks[b + 1].s_in : E->head_snake);
+            const int Hn = !last_ru ? Hk * c.dilations[j + 1] : (b + 1 < E->blocks.size() ? 1 : Hk);   // history the next consumer wants
+            float* stt; if (int r = halo_state((size_t)H * C, &stt)) return r;
+            if (int r = restore_op(bS, stt, H, C)) return r;
+            bool done = false;
+            if (E->tc() && E->fuse_ru) {
+                RuFusedParams f;
+                memset(&f, 0, sizeof f);
+                const VocAct Ain = act(E, bS), Sout = act_at(E, bT, (size_t)Hn * C);
+                f.A_hi = Ain.hi; f.A_lo = Ain.lo; f.L = L; f.C = C; f.B = 1; f.dil = c.dilations[j]; f.ksz = c.conv_kernel; f.a_halo = H;
+                f.W7tc = R.c1.Wtc; f.w7_plane = R.c1.wtc_plane; f.w7scale = R.c1.wscale; f.bias7 = R.c1.bias;
+                f.sn2_a = R.s2.a; f.sn2_invb = R.s2.invb;
+                f.W1tc = R.c2.Wtc; f.w1_plane = R.c2.wtc_plane; f.w1scale = R.c2.wscale; f.bias1 = R.c2.bias;
+                f.R = bX; f.Y = !last_ru ? bX2 : nullptr;
+                f.S_hi = Sout.hi; f.S_lo = Sout.lo; f.snn_a = nxt.a; f.snn_invb = nxt.invb;
+                if (voc_ru_fused_eligible(f)) {
+                    const double el = (double)L * C;
+                    ProfScope ps(E, st, T_FU[ti], 2.0 * el * C * (c.conv_kernel + 1), 4.0 * el * (f.Y ? 4.0 : 3.0));
+                    CK(voc_launch_ru_fused(f, st, E->num_sms, E->tc_flags));
+                    done = true;
+                }
+            }
+            if (!done) {
+                // two launches (small test architectures): conv7 -> Snake2 -> bT (the 1x1 conv needs no history); the
+                // unit's output operand then overwrites bS, whose tail is saved first
+                TapGemmParams p = gp(R.c1, act(E, bS), 0, H + L, H, L, 1);
+                setS(p, act(E, bT), &R.s2);
+                GEMM(T_C7[ti], p);
+                if (int r = save_op(bS, stt, H, C, L)) return r;
+                TapGemmParams p2 = gp(R.c2, act(E, bT), 0, L, 0, L, 1);
+                setR(p2, bX);
+                if (!last_ru) setY(p2, bX2);
+                setS(p2, act_at(E, bS, (size_t)Hn * C), &nxt);
+                GEMM(T_C1[ti], p2);
+            } else {
+                if (int r = save_op(bS, stt, H, C, L)) return r;
+                std::swap(bS, bT);
+            }
+            if (!last_ru) std::swap(bX, bX2);
+        }
+    }
+    // ---- head: conv k taps on the Snake'd signal + clamp
+    const int ch = c.decoder_dim >> c.upsample_rates.size();
+    {
+        float* stt; if (int r = halo_state((size_t)Hk * ch, &stt)) return r;
+        if (int r = restore_op(bS, stt, Hk, ch)) return r;
+        KLAUNCH("head", 2.0 * L * ch * c.conv_kernel, 4.0 * L * (ch + 1.0),
+                voc_launch_head(act_at(E, bS, (size_t)Hk * ch), (long long)L * ch, L, ch, c.conv_kernel, E->head_w, E->head_b, out, L, 1, st, Hk));
+        if (int r = save_op(bS, stt, Hk, ch, L)) return r;
+    }
+#undef KLAUNCH
+#undef GEMM
+    E->strm.pos += n;
     return VOC_OK;
 }
 
@@ -1499,6 +1713,65 @@ int voc_synthesize_batch_pcm16(void* h, const long long* codes, const int* n_tok
     return VOC_OK;
 }
 
+// ---- carried-state decode (opt-in; changes the output: no windows, no crossfade) --------------------------------
+int voc_stream_reset(void* h) {
+    Engine* E = (Engine*)h;
+    if (!E) return VOC_E_INVALID;
+    if (!E->finalized) return fail(E, VOC_E_STATE, "voc_finalize has not been called");
+    CK(cudaSetDevice(E->device));
+    for (auto& hl : E->strm.halos) CK(cudaMemsetAsync(hl.first, 0, std::max<size_t>(hl.second, 1) * sizeof(float), E->stream));
+    CK(cudaStreamSynchronize(E->stream));
+    E->strm.pos = 0;
+    return VOC_OK;
+}
+
+long long voc_stream_position(void* h) { return h ? ((Engine*)h)->strm.pos : VOC_E_INVALID; }
+
+static int stream_host(void* h, const long long* codes, int n, float* of, short* oi, long long cap, long long* n_out) {
+    Engine* E = (Engine*)h;
+    if (!E) return VOC_E_INVALID;
+    if (!E->finalized) return fail(E, VOC_E_STATE, "voc_finalize has not been called");
+    if (!codes || (!of && !oi) || !n_out || n <= 0) return fail(E, VOC_E_INVALID, "bad argument");
+    const Cfg& c = E->cfg;
+    if (c.trim_both) return fail(E, VOC_E_STATE, "carried-state decode needs transconv_trim = \"right\" (a causal, length-preserving decoder)");
+    if (E->strm.pos + n > E->rope_positions) return fail(E, VOC_E_INVALID, "stream longer than the rotary table (10240 frames): call voc_stream_reset");
+    const long long spf = c.samples_per_frame();
+    if ((long long)n * spf > cap) return fail(E, VOC_E_INVALID, "output buffer too small");
+    CK(cudaSetDevice(E->device));
+    // segment length: what the activation pools hold for one sequence (the decoder wave, the front pool's qkv rows)
+    const int seg_max = std::max(1, std::min(E->wave * c.chunk_frames - 1, E->front_wave * c.chunk_frames - c.sliding_window - 8));
+    if (int r = ensure_codes(E, (size_t)n * 16)) return r;
+    CK(cudaMemsetAsync(E->d_err, 0, sizeof(int), E->stream));
+    CK(cudaMemcpyAsync(E->d_codes, codes, (size_t)n * 16 * sizeof(long long), cudaMemcpyHostToDevice, E->stream));
+    if (int r = ensure_buf(E, E->chunks, (size_t)std::min(n, seg_max) * spf)) return r;
+    if (oi && E->pcm_cap < (size_t)std::min(n, seg_max) * spf) {
+        if (E->d_pcm) cudaFree(E->d_pcm);
+        E->d_pcm = nullptr; E->pcm_cap = 0;
+        CK(cudaMalloc(&E->d_pcm, (size_t)std::min(n, seg_max) * spf * sizeof(short))); E->pcm_cap = (size_t)std::min(n, seg_max) * spf;
+    }
+    for (int f0 = 0; f0 < n; f0 += seg_max) {
+        const int m = std::min(seg_max, n - f0);
+        if (int r = guarded(h, [&]() -> int { return stream_segment(E, E->d_codes + (size_t)f0 * 16, m, E->chunks.p, E->stream); })) return r;
+        const size_t cnt = (size_t)m * spf;
+        if (of) CK(cudaMemcpyAsync(of + (size_t)f0 * spf, E->chunks.p, cnt * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
+        if (oi) {
+            E->launches++;
+            CK(voc_launch_pcm16(E->chunks.p, E->d_pcm, (long long)cnt, E->stream));
+            CK(cudaMemcpyAsync(oi + (size_t)f0 * spf, E->d_pcm, cnt * sizeof(short), cudaMemcpyDeviceToHost, E->stream));
+        }
+    }
+    if (int r = check_codes_flag(E, E->stream)) return r;
+    CK(cudaStreamSynchronize(E->stream));
+    *n_out = (long long)n * spf;
+    return VOC_OK;
+}
+int voc_stream_decode_f32(void* h, const long long* codes, int n_tokens, float* out, long long cap, long long* n_out) {
+    return stream_host(h, codes, n_tokens, out, nullptr, cap, n_out);
+}
+int voc_stream_decode_pcm16(void* h, const long long* codes, int n_tokens, short* out, long long cap, long long* n_out) {
+    return stream_host(h, codes, n_tokens, nullptr, out, cap, n_out);
+}
+
 int voc_check_dev(void* h, void* stream) {
     Engine* E = (Engine*)h;
     if (!E) return VOC_E_INVALID;
@@ -1738,13 +2011,34 @@ int voc_test_ru(int device, int fused, int tc_flags, int B, int L, int C, int ks
     SnakeP s2, sn; s2.a = up_doubled(sn2_a, C); s2.invb = up(sn2_invb, C); sn.a = up_doubled(snn_a, C); sn.invb = up(snn_invb, C);
     const size_t ne = (size_t)B * L * C, na = (ne + 63) / 64 * 64;
     float* dR = up(R, ne);
+    // Every output buffer sits between guard bands of a known byte pattern that are checked after the launches: an
+    // out-of-bounds store of the kernels under test fails the call (compute-sanitizer is not available on the GPU
+    // pool this library is developed on; profiles/r2_compute_sanitizer_refused.txt).
+    const size_t G = 16384;                                  // guard floats on each side
+    auto guarded_alloc = [&](float** p, size_t n) -> int {
+        float* raw = nullptr;
+        CK(cudaMalloc(&raw, (n + 2 * G) * 4)); E->owned.push_back(raw);
+        CK(cudaMemsetAsync(raw, 0xA5, (n + 2 * G) * 4, E->stream));
+        *p = raw + G;
+        return VOC_OK;
+    };
+    auto guards_intact = [&](const float* p, size_t n, const char* what) -> int {
+        std::vector<unsigned char> g(2 * G * 4);
+        CK(cudaMemcpy(g.data(), p - G, G * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(g.data() + G * 4, p + n, G * 4, cudaMemcpyDeviceToHost));
+        for (unsigned char c : g) if (c != 0xA5) return fail(E, VOC_E_CUDA, std::string("guard band of ") + what + " overwritten: out-of-bounds store");
+        return VOC_OK;
+    };
     float *dA = nullptr, *dT = nullptr, *dY = nullptr, *dS = nullptr, *tmp = nullptr;
     CK(cudaMalloc(&dA, na * 4)); E->owned.push_back(dA); E->cap[dA] = na;
-    CK(cudaMalloc(&dT, na * 4)); E->owned.push_back(dT); E->cap[dT] = na;
-    CK(cudaMalloc(&dS, na * 4)); E->owned.push_back(dS); E->cap[dS] = na;
-    CK(cudaMalloc(&dY, na * 4)); E->owned.push_back(dY);
+    if (int r = guarded_alloc(&dT, na)) return r;            // operand tensors: two fp16 planes in the bytes of na floats
+    E->cap[dT] = na;
+    if (int r = guarded_alloc(&dS, na)) return r;
+    E->cap[dS] = na;
+    if (int r = guarded_alloc(&dY, na)) return r;
     CK(cudaMalloc(&tmp, na * 4)); E->owned.push_back(tmp);
     CK(cudaMemsetAsync(dY, 0, na * 4, E->stream)); CK(cudaMemsetAsync(dS, 0, na * 4, E->stream));
+    CK(cudaMemsetAsync(dT, 0, na * 4, E->stream));
     {
         std::vector<__half> h(2 * na);
         for (size_t i = 0; i < ne; ++i) {
@@ -1786,6 +2080,9 @@ int voc_test_ru(int device, int fused, int tc_flags, int B, int L, int C, int ks
         *ms = t / iters;
         cudaEventDestroy(e0); cudaEventDestroy(e1);
     }
+    if (int r = guards_intact(dY, na, "Y")) return r;
+    if (int r = guards_intact(dS, na, "S")) return r;
+    if (int r = guards_intact(dT, na, "T")) return r;
     if (Y) CK(cudaMemcpy(Y, dY, ne * 4, cudaMemcpyDeviceToHost));
     if (S) {
         CK(voc_launch_unsplit(Sout.hi, Sout.lo, tmp, (long long)ne, E->stream));

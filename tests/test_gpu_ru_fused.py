@@ -82,3 +82,20 @@ def test_shapes_the_fused_kernel_does_not_take(backend):
     k = make_case(96, 100, 1, 1, seed=1)              # a single M tile: the pair form does not apply
     rc, *_ = backend.test_ru(1, **k)
     assert rc == 1
+
+
+def test_fused_unit_is_deterministic_and_stays_inside_its_buffers(backend):
+    """compute-sanitizer is not offered on the GPU pool (profiles/r2_compute_sanitizer_refused.txt), so the two things it
+    would have shown are checked directly: (1) voc_test_ru places every output between guard bands and fails if one byte
+    of them changes -- ragged sizes whose last tile pair is mostly out of range; (2) a race between the epilogue groups,
+    the tensor core and TMA (T tile hand-over, accumulator ring, halo ring overlay) would make results depend on timing:
+    the same launch repeated must give the same bits, in both orders of work."""
+    for C, L, B, dil in [(96, 131, 1, 9), (96, 1153, 2, 3), (192, 257, 1, 9), (192, 2049, 1, 1)]:
+        k = make_case(C, L, B, dil, seed=7 * C + L)
+        first = None
+        for rep in range(4):
+            rc, Y, S, _ = backend.test_ru(1, tc_flags=32 if rep == 3 else 0, **k)
+            assert rc == 0, (C, L, dil, rc)                   # rc -2 = a guard band was overwritten
+            if first is None:
+                first = (Y, S)
+            assert np.array_equal(first[0], Y) and np.array_equal(first[1], S), (C, L, dil, rep)
