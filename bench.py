@@ -18,6 +18,7 @@ Prints ONE JSON line (see the keys below).  audio seconds are nominal: 64 frames
 from __future__ import annotations
 
 import argparse
+import ctypes
 import importlib
 import json
 import os
@@ -373,6 +374,56 @@ def run_b200(args, rank: int, local_rank: int, world: int):
                   "timed": "host int64 codes -> host int16 PCM through voc_synthesize_batch_pcm16, CUDA events on the "
                            "handle's stream, max over ranks"}
 
+    # ---- (7) the same 10-minute utterance through the opt-in carried-state decode: no windows, no
+    # recomputed overlap, no crossfade -- the output is the un-chunked decoder's, NOT the reference's stitched one, so
+    # this is reported beside the windowed figure, never instead of it.  Needs the causal trim; rank 0 only.
+    stream = None
+    if not args.no_legs and rank == 0:
+        import dataclasses
+        cfg_r = dataclasses.replace(cfg, transconv_trim="right")
+        voc.close()                                   # one set of activation pools at a time
+        voc_r = backend.Vocoder(cfg_r, weights, device=local_rank, wave=args.wave)
+        voc_r.set_option("gemm", args.gemm)
+        own_r = torch.cuda.ExternalStream(voc_r.stream, device=dev)
+        n_u = 7500
+        s_codes = torch.from_numpy(np.random.default_rng(7).integers(0, cfg.codebook_size, (n_u, 16), dtype=np.int64)).pin_memory()
+        s_out = torch.empty(n_u * 1920, dtype=torch.int16).pin_memory()
+        cnt = ctypes.c_longlong(0)
+
+        def stream_step():
+            voc_r.stream_reset()
+            rc = voc_r.lib.voc_stream_decode_pcm16(voc_r._h, s_codes.data_ptr(), n_u, s_out.data_ptr(), s_out.numel(), ctypes.byref(cnt))
+            if rc:
+                raise RuntimeError(voc_r.lib.voc_last_error(voc_r._h))
+
+        stream_step()
+        torch.cuda.synchronize(dev)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(own_r)
+        for _ in range(3):
+            stream_step()
+        s1.record(own_r)
+        torch.cuda.synchronize(dev)
+        ms_s = s0.elapsed_time(s1) / 3
+        # windowed decode of the same codes on the same (right-trim) handle, for the ratio
+        w_out = torch.empty(voc_r.out_samples(n_u), dtype=torch.int16).pin_memory()
+        wn = ctypes.c_longlong(0)
+        voc_r.lib.voc_synthesize_pcm16(voc_r._h, s_codes.data_ptr(), n_u, w_out.data_ptr(), w_out.numel(), ctypes.byref(wn))
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record(own_r)
+        for _ in range(3):
+            voc_r.lib.voc_synthesize_pcm16(voc_r._h, s_codes.data_ptr(), n_u, w_out.data_ptr(), w_out.numel(), ctypes.byref(wn))
+        w1.record(own_r)
+        torch.cuda.synchronize(dev)
+        ms_w = w0.elapsed_time(w1) / 3
+        stream = {"workload": "the 10-minute utterance (7500 frames) through voc_stream_decode_pcm16: carried per-layer state, "
+                              "segments of wave*64-1 frames, transconv_trim=right; host codes -> host PCM",
+                  "value": n_u * 0.08 / (ms_s / 1e3), "unit": "audio-s/s", "ms": ms_s, "out_samples": int(cnt.value),
+                  "windowed_same_handle": {"value": n_u * 0.08 / (ms_w / 1e3), "ms": ms_w, "out_samples": int(wn.value)},
+                  "speedup_over_windowed": ms_w / ms_s,
+                  "note": "opt-in mode: output = un-chunked decode (tests/test_gpu_stream.py), not the reference's 64/48/16 stitching"}
+        voc_r.close()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -464,7 +515,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
                 "latency_ms": {"workload": "1 chunk, batch 1, host to host incl. H2D of 8 KB codes and D2H of the "
                                            "window (BASELINE configs[1]); 200 calls after 20 warm-ups",
                                "p50": lat[len(lat) // 2], "p95": lat[int(0.95 * len(lat)) - 1]},
-                "utterance_10min": utt, "corpus_1k": corpus},
+                "utterance_10min": utt, "corpus_1k": corpus, "stream_10min": stream},
         "gpu_launches": int(launches),
         "simt_launches": simt_launches,
         "clocks": clocks,
