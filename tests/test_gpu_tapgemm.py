@@ -54,7 +54,7 @@ CASES = [
     ("linear_k72",       1, 130,   72,  64, 130, 0, [0]),
     ("conv3_k40",        2, 140,   40,  96, 140, 0, [-4, -2, 0]),
     ("conv7_k160",       1, 300,  160, 192, 300, 0, [-6, -5, -4, -3, -2, -1, 0]),
-    # cta_group::2 pair mode (BN = 192 with taps*K >= 1024; BN = 96 with taps*K >= 512): odd numbers of M tiles
+    # cta_group::2 pair mode (BN = 192 with taps*K >= 768; BN = 96 with taps*K >= 384, tc_gemm.cu): odd numbers of M tiles
     # (the pair's second CTA gets an all-padding tile), several windows, K tail (K = 96 in 64-wide chunks)
     ("pair_conv7_c192",  3, 650,  192, 192, 650, 0, [-54, -45, -36, -27, -18, -9, 0]),
     ("pair_conv7_c96",   2, 900,   96,  96, 900, 0, [-6, -5, -4, -3, -2, -1, 0]),
