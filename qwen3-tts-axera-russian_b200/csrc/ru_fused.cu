@@ -67,6 +67,7 @@ struct FuArgs {
     const float* R;  long long r_bstride;  int ldr;
     float* Y;        long long y_bstride;  int ldy;
     __half* S_hi;  __half* S_lo;  long long s_bstride;  int lds;
+    const float* head_w;  float* head_part;   // HEAD: the output head's weights [taps][C]; per-tap partial sums out
 };
 
 // Bring-up profiling (-DVOC_TC_PROF, tools/ab_build.sh): cycles each role spends waiting, summed over CTAs
@@ -98,7 +99,7 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-template <int BN, int CP, bool ALIAS, bool PIPE>
+template <int BN, int CP, bool ALIAS, bool PIPE, bool HEAD = false>
 __global__ void __launch_bounds__(128 + 256 * CP, 1)
 ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmW1,
@@ -148,6 +149,11 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     __shared__ uint32_t tmem_slot;
     // per-channel epilogue parameters: conv7 bias, Snake2 a / 1/b, conv1 bias, next Snake a / 1/b
     __shared__ __align__(16) float epi_par[6][BN];
+    // HEAD (the last unit of the last block): instead of storing S = Snake_head(x') for the head kernel to read back
+    // (4 B per element out, 4 B in), group B multiplies its columns of S with the head's 7 weight rows on the spot and
+    // stores 7 partial sums per (row, column part): the output sample is their shifted sum (head_finish_kernel)
+    constexpr int HEAD_TAPS = 7;
+    __shared__ __align__(16) float head_par[HEAD ? HEAD_TAPS : 1][HEAD ? BN : 4];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -416,6 +422,10 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             epi_par[3][i] = __ldg(a.bias1 + i);
             epi_par[4][i] = __ldg(a.snn_a + i);
             epi_par[5][i] = __ldg(a.snn_invb + i);
+            if constexpr (HEAD) {
+#pragma unroll
+                for (int t = 0; t < HEAD_TAPS; ++t) head_par[t][i] = __ldg(a.head_w + t * BN + i);
+            }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(64 * EPI_WARPS) : "memory");
         // The accumulator ring is used in the issuing warp's order: per step the conv7 segments, then one 1x1 chain.
@@ -585,6 +595,9 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const float* Rrow = a.R + (long long)b * a.r_bstride + (long long)(valid ? m : 0) * a.ldr + n0;
                 float* Yrow = (a.Y && valid) ? a.Y + (long long)b * a.y_bstride + (long long)m * a.ldy + n0 : nullptr;
                 const long long soff = (long long)b * a.s_bstride + (long long)m * a.lds + n0;
+                float hp[HEAD ? HEAD_TAPS : 1];
+#pragma unroll
+                for (int t = 0; t < (HEAD ? HEAD_TAPS : 1); ++t) hp[t] = 0.f;
                 float res[2][2][8];                       // two 16-column windows of the residual row, alternating
                 if (valid) { ldg256(Rrow, res[0][0]); ldg256(Rrow + 8, res[0][1]); }
                 if (s + 1 < n_my) prefetch_res(tile + walkers);   // the next tile's rows: HBM -> L2 while this one is finished
@@ -645,16 +658,38 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             v[2] = voc_snake(v[2], a0.z, i0.z); v[3] = voc_snake(v[3], a0.w, i0.w);
                             v[4] = voc_snake(v[4], a1.x, i1.x); v[5] = voc_snake(v[5], a1.y, i1.y);
                             v[6] = voc_snake(v[6], a1.z, i1.z); v[7] = voc_snake(v[7], a1.w, i1.w);
+                            if constexpr (HEAD) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                __half2 hh, ll;
-                                voc_split2(v[2 * j], v[2 * j + 1], hh, ll);
-                                hi16[gg / 2 + j] = *reinterpret_cast<uint32_t*>(&hh);
-                                lo16[gg / 2 + j] = *reinterpret_cast<uint32_t*>(&ll);
+                                for (int t = 0; t < HEAD_TAPS; ++t) {
+                                    const float4 w0 = *reinterpret_cast<const float4*>(&head_par[t][pc]);
+                                    const float4 w1 = *reinterpret_cast<const float4*>(&head_par[t][pc + 4]);
+                                    float acc = hp[t];
+                                    acc = fmaf(w0.x, v[0], acc); acc = fmaf(w0.y, v[1], acc); acc = fmaf(w0.z, v[2], acc); acc = fmaf(w0.w, v[3], acc);
+                                    acc = fmaf(w1.x, v[4], acc); acc = fmaf(w1.y, v[5], acc); acc = fmaf(w1.z, v[6], acc); acc = fmaf(w1.w, v[7], acc);
+                                    hp[t] = acc;
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    __half2 hh, ll;
+                                    voc_split2(v[2 * j], v[2 * j + 1], hh, ll);
+                                    hi16[gg / 2 + j] = *reinterpret_cast<uint32_t*>(&hh);
+                                    lo16[gg / 2 + j] = *reinterpret_cast<uint32_t*>(&ll);
+                                }
                             }
                         }
-                        stg256u(a.S_hi + soff + g16, hi16);
-                        stg256u(a.S_lo + soff + g16, lo16);
+                        if constexpr (!HEAD) {
+                            stg256u(a.S_hi + soff + g16, hi16);
+                            stg256u(a.S_lo + soff + g16, lo16);
+                        }
+                    }
+                }
+                if constexpr (HEAD) {
+                    // planes [window][column part][tap][row]: consecutive lanes = consecutive rows, coalesced 4-byte stores
+                    if (valid) {
+                        float* pp = a.head_part + (((long long)b * CP + h) * HEAD_TAPS) * a.M + m;
+#pragma unroll
+                        for (int t = 0; t < HEAD_TAPS; ++t) pp[(long long)t * a.M] = hp[t];
                     }
                 }
                 skip(1);
@@ -672,14 +707,14 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == 1) tmem_dealloc2(tmem_base, TMEM_COLS);
 }
 
-template <int BN, int CP, bool ALIAS, bool PIPE>
+template <int BN, int CP, bool ALIAS, bool PIPE, bool HEAD = false>
 cudaError_t launch_fused(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB2, const CUtensorMap& tmW1,
                          const CUtensorMap& tmW1b, const FuArgs& a, int grid, size_t smem, cudaStream_t st) {
     static std::atomic<bool> attr_done[FU_MAX_DEVICES];
     int dev = -1;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= FU_MAX_DEVICES) return cudaErrorInvalidDevice;
     if (!attr_done[dev].load(std::memory_order_acquire)) {
-        cudaError_t e = cudaFuncSetAttribute(ru_fused_kernel<BN, CP, ALIAS, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(ru_fused_kernel<BN, CP, ALIAS, PIPE, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              SMEM_BUDGET + 1024);
         if (e != cudaSuccess) return e;
         attr_done[dev].store(true, std::memory_order_release);
@@ -690,7 +725,7 @@ cudaError_t launch_fused(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, ru_fused_kernel<BN, CP, ALIAS, PIPE>, tmA, tmB, tmB2, tmW1, tmW1b, a);
+    return cudaLaunchKernelEx(&cfg, ru_fused_kernel<BN, CP, ALIAS, PIPE, HEAD>, tmA, tmB, tmB2, tmW1, tmW1b, a);
 }
 
 struct FuPlan { int box_rows, SA, SB; bool alias; size_t smem; };
@@ -735,13 +770,17 @@ bool voc_ru_fused_eligible(const RuFusedParams& p) {
     if (p.ksz < 2 || p.ksz > VOC_MAX_TAPS || p.dil < 1) return false;
     if (p.L <= BM || p.B < 1) return false;                  // the pair form wants at least two M tiles per window
     if (p.a_halo < 0 || (p.a_halo && p.B != 1)) return false;
-    if (!p.A_hi || !p.A_lo || !p.W7tc || !p.W1tc || !p.R || !p.S_hi || !p.S_lo) return false;
+    if (!p.A_hi || !p.A_lo || !p.W7tc || !p.W1tc || !p.R) return false;
+    if (p.head_w) {                                          // head folded into the unit: per-tap partial sums instead of S
+        if (!p.head_part || p.head_taps != 7 || p.C != 96 || p.Y) return false;
+    } else if (!p.S_hi || !p.S_lo) return false;
     if (!p.bias7 || !p.bias1 || !p.sn2_a || !p.sn2_invb || !p.snn_a || !p.snn_invb) return false;
     auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
-    if (!al32(p.A_hi) || !al32(p.A_lo) || !al32(p.R) || !al32(p.S_hi) || !al32(p.S_lo) || (p.Y && !al32(p.Y))) return false;
+    if (!al32(p.A_hi) || !al32(p.A_lo) || !al32(p.R) || (p.S_hi && (!al32(p.S_hi) || !al32(p.S_lo))) || (p.Y && !al32(p.Y))) return false;
     if ((p.A_lo - p.A_hi) % 8 || p.A_lo <= p.A_hi || p.w7_plane % 8 || p.w1_plane % 8) return false;
     FuPlan pl;
-    return plan_fused(p, pl);
+    if (!plan_fused(p, pl)) return false;
+    return !(p.head_w && pl.alias);
 }
 
 cudaError_t voc_launch_ru_fused(const RuFusedParams& p, cudaStream_t st, int num_sms, int flags) {
@@ -778,6 +817,7 @@ cudaError_t voc_launch_ru_fused(const RuFusedParams& p, cudaStream_t st, int num
     a.R = p.R; a.r_bstride = bs; a.ldr = p.C;
     a.Y = p.Y; a.y_bstride = bs; a.ldy = p.C;
     a.S_hi = p.S_hi; a.S_lo = p.S_lo; a.s_bstride = bs; a.lds = p.C;
+    a.head_w = p.head_w; a.head_part = p.head_part;
 
     CUtensorMap tmA, tmB, tmB2, tmW1, tmW1b;
     const long long a_pl = (long long)(p.A_lo - p.A_hi);
@@ -799,6 +839,11 @@ cudaError_t voc_launch_ru_fused(const RuFusedParams& p, cudaStream_t st, int num
     const int sms = num_sms > 0 ? num_sms : 148;
     const int grid = 2 * std::min(a.total_tiles, sms / 2);
     const bool pipe = !pl.alias && !(flags & VOC_TC_NO_PIPE);
+    if (p.head_w) {
+        if (BN != 96 || pl.alias) return cudaErrorNotSupported;
+        return pipe ? launch_fused<96, 2, false, true, true>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st)
+                    : launch_fused<96, 2, false, false, true>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st);
+    }
     if (BN == 96) {
         if (pl.alias) return launch_fused<96, 2, true, false>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st);
         return pipe ? launch_fused<96, 2, false, true>(tmA, tmB, tmB2, tmW1, tmW1b, a, grid, pl.smem, st)

@@ -131,6 +131,9 @@ struct RuFusedParams {
     const __half* W1tc;  long long w1_plane;  float w1scale;  const float* bias1;
     const float* R;  float* Y;
     __half* S_hi;  __half* S_lo;  const float* snn_a;  const float* snn_invb;
+    // the output head folded into the last unit (C = 96): head_w [head_taps][C]; head_part [B][2 column parts][head_taps][L]
+    // receives per-tap partial sums of w * Snake_next(x') instead of S (S_hi / S_lo / Y null)
+    const float* head_w;  float* head_part;  int head_taps;
 };
 bool voc_ru_fused_eligible(const RuFusedParams& p);
 cudaError_t voc_launch_ru_fused(const RuFusedParams& p, cudaStream_t st, int num_sms, int flags);
@@ -160,6 +163,8 @@ cudaError_t voc_launch_attention_stream(const float* qkv, VocAct out, int T, int
 cudaError_t voc_launch_swiglu(const float* gu, VocAct out, long long rows, int inter, cudaStream_t st);
 cudaError_t voc_launch_head(VocAct S, long long s_bstride, int L, int C, int ksz, const float* w,
                             float bias, float* out, long long o_bstride, int B, cudaStream_t st, int halo = 0);
+cudaError_t voc_launch_head_finish(const float* part, int parts, int taps, int L, float bias, float* out,
+                                   long long o_bstride, int B, cudaStream_t st);
 cudaError_t voc_launch_stitch(const float* chunks, long long chunk_stride, const int* win_meta,
                               int n_windows, int ov, const float* fade_out, const float* fade_in,
                               float* out_f32, short* out_i16, int max_a_len, cudaStream_t st);

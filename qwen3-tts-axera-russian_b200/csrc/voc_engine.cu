@@ -189,6 +189,7 @@ struct Engine {
     int tc_flags = 0;           // VOC_TC_* experiment switches
     bool fuse_ru = true;        // residual units with C <= 192 as one kernel (ru_fused.cu)
     bool short_windows = true;  // a request's short last window computes only the frames it needs
+    bool fold_head = true;      // the output head rides on the last residual unit (ru_fused.cu, HEAD)
     int num_sms = 148;
     bool debug = false;
     bool tc() const { return gemm_mode != 1; }
@@ -740,6 +741,7 @@ static int run_back(Engine* E, float* x, int x_win0, int L, int nw, float* chunk
         if (E->debug) if (int r = dbg_capture(E, "conv_in", act_f32(bX), (size_t)nw * L * c.decoder_dim, st)) return r;
     }
     // K5/K6: decoder blocks
+    bool head_folded = false;
     static const char* const T_CONVT[] = {"dec0.convt", "dec1.convt", "dec2.convt", "dec3.convt", "decN.convt"};
     static const char* const T_C7[] = {"dec0.ru.conv7", "dec1.ru.conv7", "dec2.ru.conv7", "dec3.ru.conv7", "decN.ru.conv7"};
     static const char* const T_C1[] = {"dec0.ru.conv1", "dec1.ru.conv1", "dec2.ru.conv1", "dec3.ru.conv1", "decN.ru.conv1"};
@@ -774,10 +776,18 @@ static int run_back(Engine* E, float* x, int x_win0, int L, int nw, float* chunk
                 f.W1tc = R.c2.Wtc; f.w1_plane = R.c2.wtc_plane; f.w1scale = R.c2.wscale; f.bias1 = R.c2.bias;
                 f.R = bX; f.Y = (!last_ru_f || E->debug) ? bX2 : nullptr;
                 f.S_hi = Sout.hi; f.S_lo = Sout.lo; f.snn_a = nxt_f.a; f.snn_invb = nxt_f.invb;
+                // the very last unit can take the output head with it: per-tap partial sums (into bT, which S would have
+                // used) instead of the 4 B per element of S that the head kernel would read straight back
+                const bool very_last = last_ru_f && b + 1 == E->blocks.size();
+                if (very_last && E->fold_head && !E->debug && c.conv_kernel == 7) {
+                    RuFusedParams g = f;
+                    g.S_hi = nullptr; g.S_lo = nullptr; g.head_w = E->head_w; g.head_part = bT; g.head_taps = c.conv_kernel;
+                    if (voc_ru_fused_eligible(g)) { f = g; head_folded = true; }
+                }
                 if (voc_ru_fused_eligible(f)) {
                     static const char* const T_FU[] = {"dec0.ru.fused", "dec1.ru.fused", "dec2.ru.fused", "dec3.ru.fused", "decN.ru.fused"};
                     const double el = (double)nw * L * C;
-                    ProfScope ps(E, st, T_FU[ti], 2.0 * el * C * (c.conv_kernel + 1), 4.0 * el * (f.Y ? 4.0 : 3.0));
+                    ProfScope ps(E, st, T_FU[ti], 2.0 * el * C * (c.conv_kernel + 1), 4.0 * el * (f.Y ? 4.0 : f.head_w ? 2.0 : 3.0));
                     CK(voc_launch_ru_fused(f, st, E->num_sms, E->tc_flags));
                     std::swap(bS, bT);
                     if (f.Y) std::swap(bX, bX2);
@@ -809,8 +819,14 @@ static int run_back(Engine* E, float* x, int x_win0, int L, int nw, float* chunk
     }
     // K7: head
     const int ch = c.decoder_dim >> c.upsample_rates.size();
-    KLAUNCH("head", 2.0 * nw * L * ch * c.conv_kernel, 4.0 * nw * L * (ch + 1.0),
-            voc_launch_head(act(E, bS), (long long)L * ch, L, ch, c.conv_kernel, E->head_w, E->head_b, chunk_out, o_bstride, nw, st));
+    if (head_folded) {
+        // (after the swap the partial sums are in bS)
+        KLAUNCH("head", 2.0 * nw * L * 2 * c.conv_kernel, 4.0 * nw * L * (2.0 * c.conv_kernel + 1.0),
+                voc_launch_head_finish(bS, 2, c.conv_kernel, L, E->head_b, chunk_out, o_bstride, nw, st));
+    } else {
+        KLAUNCH("head", 2.0 * nw * L * ch * c.conv_kernel, 4.0 * nw * L * (ch + 1.0),
+                voc_launch_head(act(E, bS), (long long)L * ch, L, ch, c.conv_kernel, E->head_w, E->head_b, chunk_out, o_bstride, nw, st));
+    }
 #undef KLAUNCH
 #undef GEMM
     return VOC_OK;
@@ -1822,6 +1838,7 @@ int voc_set_option(void* h, const char* key, const char* value) {
     if (k == "tc_flags") { E->tc_flags = atoi(v.c_str()); return VOC_OK; }
     if (k == "fuse_ru") { E->fuse_ru = (v == "1"); return VOC_OK; }
     if (k == "short_windows") { E->short_windows = (v == "1"); return VOC_OK; }
+    if (k == "fold_head") { E->fold_head = (v == "1"); return VOC_OK; }
     if (k == "graphs") { E->use_graphs = (v == "1"); return VOC_OK; }
     if (k == "graph_max_wave") { E->graph_max_wave = atoi(v.c_str()); return VOC_OK; }
     if (k == "front_wave") {
