@@ -714,8 +714,12 @@ cudaError_t launch_fused(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
     int dev = -1;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= FU_MAX_DEVICES) return cudaErrorInvalidDevice;
     if (!attr_done[dev].load(std::memory_order_acquire)) {
-        cudaError_t e = cudaFuncSetAttribute(ru_fused_kernel<BN, CP, ALIAS, PIPE, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             SMEM_BUDGET + 1024);
+        // all of the 227 KB opt-in maximum that the kernel's static shared memory leaves
+        cudaFuncAttributes fa;
+        cudaError_t e = cudaFuncGetAttributes(&fa, ru_fused_kernel<BN, CP, ALIAS, PIPE, HEAD>);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(ru_fused_kernel<BN, CP, ALIAS, PIPE, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 232448 - (int)fa.sharedSizeBytes);
         if (e != cudaSuccess) return e;
         attr_done[dev].store(true, std::memory_order_release);
     }
