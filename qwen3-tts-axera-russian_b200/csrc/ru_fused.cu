@@ -58,6 +58,7 @@ struct FuArgs {
     int M, B;
     int ntaps, a_min_off, a_box_rows, tap_row0, tap_step;
     int seg_iters, seg_head;
+    int ring_k;                              // simple order: the first ring_k conv7 segments of a tile share one TMEM buffer
     int m_tiles, total_tiles;                // m_tiles counts tile PAIRS
     int k_chunks, kc_steps, kc_last;
     int SA, SB;
@@ -97,6 +98,18 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
 }
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// Simple order of work (C = 192): which of the two TMEM accumulator buffers a use gets.  The 1x1 chain's accumulator is
+// read by group B 16 columns at a time through its whole final phase (~20 k cycles: no registers to park it in), so a
+// strictly alternating ring leaves the next tile's conv7 ONE buffer after its first segment and the issuing warp waits
+// (14.5 k of 51 k cycles, profiles/r2_ru_prof.txt).  Instead the first K segments of a tile all use the buffer the
+// previous chain is NOT in (group A drains a segment in a few hundred cycles), the rest alternate, and the chain takes
+// the buffer the last segment is not in.  A static function of (previous chain's buffer, segment index): the issuing
+// warp and both groups evaluate it independently.
+__device__ __forceinline__ int fu_seg_buf(int cprev, int k, int K) {
+    const int y = cprev ^ 1;
+    return k < K ? y : (((k - K) & 1) ? y : cprev);
 }
 
 template <int BN, int CP, bool ALIAS, bool PIPE, bool HEAD = false>
@@ -267,6 +280,10 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t b_desc0 = reg(smem_desc_lo(smB));
             const uint32_t a2_desc0 = reg(smem_desc_lo(smA2));
             int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pas = 0, p_a2 = 0;
+            uint32_t ep = 0;                       // !PIPE: bit b = uses of accumulator buffer b so far (mod 2)
+            int cprev = 1, nseg_m = 0;             // !PIPE: buffer of the previous tile's chain; segments per tile
+            for (int rem = iters_per_tile; rem > 0; ++nseg_m) rem -= (nseg_m < a.seg_head ? 2 : 1) * a.seg_iters;
+            const int ringK = a.ring_k < nseg_m ? a.ring_k : nseg_m;
             uint32_t b_lo = b_desc0;
             PF_DECL(pf_w_a); PF_DECL(pf_w_b); PF_DECL(pf_w_acc); PF_DECL(pf_w_t); PF_T0(pf_t0);
             const int n_my = walker < a.total_tiles ? (a.total_tiles - walker + walkers - 1) / walkers : 0;
@@ -283,7 +300,13 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     constexpr int NKS = decltype(nks)::value;
                     for (int t = 0; t < n_inner; ++t) {
                         if (seg_left == 0) {
-                            { PF_T0(tw); mbar_spin_a(acc_empty0 + 8 * as, pas ^ 1); PF_ACC(pf_w_acc, tw); }
+                            if constexpr (PIPE) {
+                                PF_T0(tw); mbar_spin_a(acc_empty0 + 8 * as, pas ^ 1); PF_ACC(pf_w_acc, tw);
+                            } else {
+                                as = fu_seg_buf(cprev, seg_idx, ringK);
+                                PF_T0(tw); mbar_spin_a(acc_empty0 + 8 * as, ((ep >> as) & 1u) ^ 1u); PF_ACC(pf_w_acc, tw);
+                                ep ^= 1u << as;
+                            }
                             tmem_acc = tmem_base + (uint32_t)as * ACC_COLS;
                             accum = 0;
                             const int want = seg_idx < seg_head ? 2 * seg_iters : seg_iters;
@@ -323,7 +346,7 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         a_lo += tap_step16;
                         b_lo += B_STAGE >> 4;
                         if (++sb == SB) { sb = 0; pb ^= 1; b_lo = b_desc0; }
-                        if (last_of_seg) { if (++as == NBUF) { as = 0; pas ^= 1; } }
+                        if constexpr (PIPE) { if (last_of_seg) { if (++as == NBUF) { as = 0; pas ^= 1; } } }
                     }
                     };
                     if (ks_this == 4) stages(std::integral_constant<int, 4>{});
@@ -343,7 +366,14 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 // ---- the 1x1 convolution on the T tiles both CTAs' epilogue warps have written to shared memory
                 { PF_T0(tw); mbar_spin_a(a2_full, (uint32_t)p_a2); PF_ACC(pf_w_t, tw); }
                 p_a2 ^= 1;
-                { PF_T0(tw); mbar_spin_a(acc_empty0 + 8 * as, pas ^ 1); PF_ACC(pf_w_acc, tw); }
+                if constexpr (PIPE) {
+                    PF_T0(tw); mbar_spin_a(acc_empty0 + 8 * as, pas ^ 1); PF_ACC(pf_w_acc, tw);
+                } else {
+                    as = fu_seg_buf(cprev, nseg_m - 1, ringK) ^ 1;      // not where the last segment is
+                    cprev = as;
+                    PF_T0(tw); mbar_spin_a(acc_empty0 + 8 * as, ((ep >> as) & 1u) ^ 1u); PF_ACC(pf_w_acc, tw);
+                    ep ^= 1u << as;
+                }
                 tmem_acc = tmem_base + (uint32_t)as * ACC_COLS;
 #pragma unroll
                 for (int kc = 0; kc < NKC2; ++kc) {
@@ -386,7 +416,7 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     b_lo += B_STAGE >> 4;
                     if (++sb == SB) { sb = 0; pb ^= 1; b_lo = b_desc0; }
                 }
-                if (++as == NBUF) { as = 0; pas ^= 1; }
+                if constexpr (PIPE) { if (++as == NBUF) { as = 0; pas ^= 1; } }
                 if constexpr (ALIAS) {
                     // now the halo ring may be refilled: hand back the stages held since the conv7 loop
                     const int held = n_fills < SA ? n_fills : SA;
@@ -430,9 +460,11 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         asm volatile("bar.sync 1, %0;" ::"n"(64 * EPI_WARPS) : "memory");
         // The accumulator ring is used in the issuing warp's order: per step the conv7 segments, then one 1x1 chain.
         // Each group waits for and hands back only its own buffers and steps over the other group's.
-        int as = 0;                                   // position in the ring (all uses, both groups')
+        int as = 0;                                   // PIPE: position in the alternating ring (all uses, both groups')
         uint32_t par = 0;                             // bit b: parity of this group's next wait on its full barrier of buffer b
-        auto skip = [&](int n) { for (int i = 0; i < n; ++i) if (++as == NBUF) as = 0; };
+        auto skip = [&](int n) { if constexpr (PIPE) { for (int i = 0; i < n; ++i) if (++as == NBUF) as = 0; } };
+        int cprev = 1;                                // !PIPE: buffer of the previous tile's chain (fu_seg_buf)
+        const int ringK = a.ring_k < nseg ? a.ring_k : nseg;
         uint32_t acc_empty_leader[NBUF];
 #pragma unroll
         for (int i = 0; i < NBUF; ++i) acc_empty_leader[i] = mapa_u32(&bar_acc_empty[i], 0);
@@ -453,6 +485,7 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 float acc[HN];
                 // conv7 accumulation segments of tile s, added in FP32 with round-to-nearest as in the unfused kernel
                 for (int seg = 0; seg < nseg; ++seg) {
+                    if constexpr (!PIPE) as = fu_seg_buf(cprev, seg, ringK);
                     { PF_T0(tw); mbar_wait(&bar_acc_full7[as], (par >> as) & 1u); PF_ACC(pf_w7, tw); }
                     par ^= 1u << as;
                     tc_fence_after();
@@ -564,7 +597,8 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (lane == 0) mbar_arrive_remote(a2_full_leader);
                 PF_ACC(pf_emit, te);
                 // step over the 1x1 chain's buffer that follows this tile's segments in the ring
-                if (!PIPE || s > 0) skip(1);
+                if constexpr (PIPE) { if (s > 0) skip(1); }
+                else cprev = fu_seg_buf(cprev, nseg - 1, ringK) ^ 1;
             }
 #ifdef VOC_TC_PROF
             if (warp == 4 && lane == 0) {
@@ -589,7 +623,8 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int s = 0; s < n_my; ++s) {
                 const int tile = walker + s * walkers;
                 // ring order: simple -- segs(s), chain(s);  pipelined -- segs(s+1) (if any), chain(s)
-                if (!PIPE || s + 1 < n_my) skip(nseg);
+                if constexpr (PIPE) { if (s + 1 < n_my) skip(nseg); }
+                else { as = fu_seg_buf(cprev, nseg - 1, ringK) ^ 1; cprev = as; }
                 int m, b; row_of(tile, m, b);
                 const bool valid = m < a.M;
                 const float* Rrow = a.R + (long long)b * a.r_bstride + (long long)(valid ? m : 0) * a.ldr + n0;
@@ -810,6 +845,10 @@ cudaError_t voc_launch_ru_fused(const RuFusedParams& p, cudaStream_t st, int num
     }
     a.seg_iters = std::max(1, seg_mmas / ((cat ? 1 : 3) * a.kc_steps));
     a.seg_head = (!cat && !(flags & VOC_TC_NO_SEG_HEAD)) ? 2 : 0;
+    {
+        static const int rk_env = []() { const char* e = getenv("VOC_RU_RINGK"); return e ? atoi(e) : -1; }();   // experiment hook
+        a.ring_k = rk_env >= 1 ? rk_env : 3;      // measured: 1 (= plain alternation) 0.560 ms, 2 0.536, 3 0.528, 4 0.535, 5 0.546, 6 0.557 per unit on 8 windows
+    }
     const int m_tiles = (p.L + BM - 1) / BM;
     a.m_tiles = (m_tiles + 1) / 2;
     a.total_tiles = a.m_tiles * p.B;
