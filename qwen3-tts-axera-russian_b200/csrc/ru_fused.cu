@@ -125,10 +125,14 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     constexpr int HN = BN / CP;                               // columns per epilogue thread
     // register budgets (setmaxnreg, multiples of 8): a 640-thread CTA starts at 96 per thread; group A at C = 192 holds
     // 96 accumulators per thread
-    constexpr bool REBALANCE = HN > 48;
+#ifndef VOC_RU_REGS96
+#define VOC_RU_REGS96 0          /* experiment: 0 = no rebalancing at C = 96; 1 = A 112 / B 96; 2 = A 120 / B 88 */
+#endif
+    constexpr bool REBALANCE = HN > 48 || VOC_RU_REGS96 != 0;
     // setmaxnreg.inc can only take what setmaxnreg.dec has released inside the CTA (the SM's never-allocated registers
     // are not in that pool: an inc that asks for more blocks for ever)
-    constexpr int REGS_START = 96, REGS_WG0 = 56, REGS_A = 128, REGS_B = 80;
+    constexpr int REGS_START = 96, REGS_WG0 = 56, REGS_A = HN > 48 ? 128 : (VOC_RU_REGS96 == 2 ? 120 : 112),
+                  REGS_B = HN > 48 ? 80 : (VOC_RU_REGS96 == 2 ? 88 : 96);
     static_assert((REGS_START - REGS_WG0) * 128 + (REGS_START - REGS_B) * 32 * EPI_WARPS >= (REGS_A - REGS_START) * 32 * EPI_WARPS,
                   "register pool: released < requested");
     static_assert((128 + 64 * EPI_WARPS) * REGS_START <= 65536, "launch register budget");
@@ -607,7 +611,7 @@ ru_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #endif
         } else {
             // ---------------- group B: 1x1 accumulator -> the unit's outputs ----------------
-            if constexpr (REBALANCE) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_B));
+            if constexpr (REBALANCE && REGS_B < REGS_START) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_B));
             PF_DECL(pf_w1); PF_DECL(pf_final); PF_T0(pf_t0);
             auto row_of = [&](int tile, int& m, int& b) { m = (2 * (tile % a.m_tiles) + (int)rank) * BM + (int)trow; b = tile / a.m_tiles; };
             auto prefetch_res = [&](int tile) {
