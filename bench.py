@@ -125,6 +125,78 @@ def time_oracle(cfg, weights, chunks_per_step: int, steps: int, warmup: int, thr
     return ts
 
 
+def code_predictor_leg(device: int, frames: int = 60):
+    """the code predictor's frame latency (the reference's "86 % of per-token time") through cp_predict
+    -- host hidden state + code_0 embedding in, 15 host int32 codes out, one CUDA-graph launch per frame -- and
+    through the level-1 step interface with the reference's host sampler; the CPU oracle's frame time beside it."""
+    import importlib
+    cpm = importlib.import_module("qwen3-tts-axera-russian_b200.code_predictor")
+    cfg = cpm.CPConfig()
+    w = cpm.init_weights(cfg, 0)
+    cp = cpm.CodePredictor(cfg, w, device=device)
+    rng = np.random.default_rng(11)
+    hs = rng.standard_normal((frames + 5, cfg.hidden)).astype(np.float32)
+    es = rng.standard_normal((frames + 5, cfg.hidden)).astype(np.float32)
+    for i in range(5):
+        cp.predict(hs[i], es[i], 0.1, 50, seed=i)
+    l0 = cp.launches
+    lat = []
+    for i in range(5, frames + 5):
+        t = time.perf_counter()
+        cp.predict(hs[i], es[i], 0.1, 50, seed=i)
+        lat.append((time.perf_counter() - t) * 1e3)
+    per_frame_launches = (cp.launches - l0) // frames
+    lat.sort()
+    # level 1: 16 steps + 15 logits round trips per frame, greedy on the host
+    t = time.perf_counter()
+    n1 = 10
+    for i in range(n1):
+        cp.reset()
+        cp.step(hs[i][None], 0)
+        cp.step(es[i][None], 1)
+        for g in range(cfg.groups):
+            tok = int(np.argmax(cp.logits(g)))
+            if g + 1 < cfg.groups:
+                cp.step(w[f"codec_emb_{g}"][tok][None], g + 2)
+    ms_l1 = (time.perf_counter() - t) * 1e3 / n1
+    layer_bytes = sum(int(np.prod(sh)) for k, sh in cpm.weight_shapes(cfg).items() if k.startswith("layer_")) * 4
+    head_bytes = cfg.vocab * cfg.hidden * 4
+    frame_bytes = (cfg.groups + 1) * layer_bytes + cfg.groups * head_bytes
+    peaks, peak_src = _peaks()
+    hbm = float(peaks.get("hbm_gbs_sustained", peaks.get("hbm_gbs", 6400.0)))
+    p50 = lat[len(lat) // 2]
+    out = {"workload": "code predictor, production shape (5 layers, 1024 hidden, GQA 16/8 x 128, 3072 MLP, 15 groups x 2048), "
+                       "random weights, batch 1: one frame = 16 decode steps + 15 lm_heads + 15 top-k draws",
+           "call": "cp_predict (host float32 hidden state + code_0 embedding -> 15 host int32 codes), T = 0.1, top_k = 50",
+           "frame_ms_p50": p50, "frame_ms_p95": lat[int(0.95 * len(lat)) - 1], "frames_per_s": 1e3 / p50,
+           "realtime_factor_at_12.5_frames_per_s": (1e3 / p50) / 12.5,
+           "gpu_launches_per_frame": int(per_frame_launches), "level1_frame_ms": ms_l1,
+           "dtype": "f32",
+           "roofline": {"bound": "hbm", "unit": "GB/s", "achieved": frame_bytes / (p50 / 1e3) / 1e9, "peak": hbm,
+                        "frac": frame_bytes / (p50 / 1e3) / 1e9 / hbm, "traffic": None,
+                        "algorithmic_bytes_per_frame": int(frame_bytes),
+                        "note": "float32 weights streamed once per decode step (314.6 MB of layer weights x 16 steps + 15 "
+                                "lm_heads); the whole frame incl. H2D / D2H and the graph launch is in the time",
+                        "peak_source": peak_src}}
+    try:
+        from oracle import code_predictor_oracle as CPO
+        ocfg = CPO.CPConfig()
+        W = CPO.Weights(w)
+        torch.set_num_threads(os.cpu_count() or 1)
+        CPO.predict(hs[0], es[0], W, ocfg)
+        t = time.perf_counter()
+        want = CPO.predict(hs[1], es[1], W, ocfg)
+        cpu_ms = (time.perf_counter() - t) * 1e3
+        got = [int(c) for c in cp.predict(hs[1], es[1], 0.1, 1, seed=0)]
+        out["cpu_baseline"] = {"frame_ms": cpu_ms, "cores": os.cpu_count() or 1, "kind": "port",
+                               "sample": "1 frame after 1 warm-up, torch CPU FP32 oracle, greedy"}
+        out["parity"] = {"greedy_codes_equal_oracle": got == want, "frame": 1}
+    except Exception as e:
+        out["cpu_baseline"] = {"error": repr(e)}
+    cp.close()
+    return out
+
+
 def run_reference(args, rank: int):
     """--impl reference: the reference's own implementation of the path is ONNX Runtime CPU on a
     model file that does not exist in this image; what runs is its CPU
@@ -427,6 +499,13 @@ def run_b200(args, rank: int, local_rank: int, world: int):
                   "note": "opt-in mode: output = un-chunked decode (tests/test_gpu_stream.py), not the reference's 64/48/16 stitching"}
         voc_r.close()
 
+    cp_leg = None
+    if not args.no_legs and rank == 0:
+        try:
+            cp_leg = code_predictor_leg(local_rank)
+        except Exception as e:                                # an N4 failure must not cost the headline line
+            cp_leg = {"error": repr(e)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -518,7 +597,8 @@ def run_b200(args, rank: int, local_rank: int, world: int):
                 "latency_ms": {"workload": "1 chunk, batch 1, host to host incl. H2D of 8 KB codes and D2H of the "
                                            "window (BASELINE configs[1]); 200 calls after 20 warm-ups",
                                "p50": lat[len(lat) // 2], "p95": lat[int(0.95 * len(lat)) - 1]},
-                "utterance_10min": utt, "corpus_1k": corpus, "stream_10min": stream},
+                "utterance_10min": utt, "corpus_1k": corpus, "stream_10min": stream,
+                "code_predictor": cp_leg},
         "gpu_launches": int(launches),
         "simt_launches": simt_launches,
         "clocks": clocks,

@@ -1,0 +1,567 @@
+// Code predictor on the GPU: the 5-layer transformer that the reference runs as
+// code_predictor_decode_step.onnx on ONNX Runtime, 17 sequential calls per codec frame
+// (/root/reference/dual_npu/code_predictor_server.py:77-140; "86 % of per-token time", docs/ARCHITECTURE.md:95-107).
+//
+// This is the other roofline of the product: batch 1, sequential, every step a chain of matrix-VECTOR products that
+// streams ~315 MB of float32 weights -- HBM/L2 bandwidth and launch latency, no tensor cores.  So:
+//   * float32 weights and arithmetic throughout (the reference is ORT FP32; logits feed a temperature-0.1 sampler);
+//   * one warp per output row, 128-bit coalesced weight loads, the input vector(s) staged in shared memory, the
+//     surrounding element-wise work fused into the GEMV's epilogue (residual add, SwiGLU) or prologue kernels
+//     (RMSNorm; q/k-norm + rotary + cache append + attention over <= 17 positions in one small kernel);
+//   * the whole predict() -- 2 prefill positions, 15 x (lm_head, top-k sample, embedding lookup, decode step) -- is ONE
+//     CUDA graph of ~640 launches replayed per frame, sampling included, so a frame costs one launch and one 60-byte D2H.
+// Level 1 (cp_step / cp_logits) is the reference's _ort_step interface with the KV cache kept on the device.
+#include "../../include/cp_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct CpCfg {
+    int hidden = 1024, layers = 5, heads = 16, kv_heads = 8, head_dim = 128, inter = 3072, vocab = 2048, groups = 15;
+    double rms_eps = 1e-6, rope_theta = 10000.0;
+    int max_positions = 32;
+    int qdim() const { return heads * head_dim; }
+    int kvdim() const { return kv_heads * head_dim; }
+};
+
+// ---- tiny flat-JSON number reader (keys of CPConfig.to_json) ----
+static bool json_num(const std::string& js, const char* key, double& v) {
+    const std::string k = std::string("\"") + key + "\"";
+    size_t p = js.find(k);
+    if (p == std::string::npos) return false;
+    p = js.find(':', p + k.size());
+    if (p == std::string::npos) return false;
+    char* e = nullptr;
+    const double d = strtod(js.c_str() + p + 1, &e);
+    if (e == js.c_str() + p + 1) return false;
+    v = d;
+    return true;
+}
+
+constexpr int CP_MAX_S = 2;          // tokens per step call: 1, or the reference's 2-token batch prefill
+
+// ------------------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------------------
+// y[s] = w * x[s] * rsqrt(mean(x[s]^2) + eps)            (sibling Qwen3OmniMoeRMSNorm)
+__global__ void cp_rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y, int H, float eps) {
+    const int s = blockIdx.x;
+    const float* xr = x + (size_t)s * H;
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) ss += xr[i] * xr[i];
+    __shared__ float red[32];
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+    const float inv = rsqrtf(tot / (float)H + eps);
+    for (int i = threadIdx.x; i < H; i += blockDim.x) y[(size_t)s * H + i] = w[i] * (xr[i] * inv);
+}
+
+// Matrix-vector product(s) with the input vector(s) in shared memory: one warp per output row.
+//   MODE 0: out[s][n] = W[n] . x[s]
+//   MODE 1: out[s][n] = res[s][n] + W[n] . x[s]                  (residual add; out may be res)
+//   MODE 2: out[s][n] = silu(W[n] . x[s]) * (W[N + n] . x[s])    (SwiGLU: gate rows, then up rows)
+enum { CP_PLAIN = 0, CP_RESIDUAL = 1, CP_SWIGLU = 2 };
+template <int MODE>
+__global__ void __launch_bounds__(256)
+cp_gemv_kernel(const float* __restrict__ W, const float* __restrict__ x, int S, int N, int K, float* __restrict__ out,
+               const float* res) {
+    extern __shared__ float xs[];                      // [S][K]
+    for (int i = threadIdx.x; i < S * K; i += blockDim.x) xs[i] = x[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (n >= N) return;
+    const float4* w0 = reinterpret_cast<const float4*>(W + (size_t)n * K);
+    const float4* w1 = MODE == CP_SWIGLU ? reinterpret_cast<const float4*>(W + (size_t)(N + n) * K) : nullptr;
+    float a0[CP_MAX_S] = {0.f, 0.f}, a1[CP_MAX_S] = {0.f, 0.f};
+    for (int k4 = lane; k4 < K / 4; k4 += 32) {
+        const float4 wv = __ldg(w0 + k4);
+        float4 uv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (MODE == CP_SWIGLU) uv = __ldg(w1 + k4);
+#pragma unroll
+        for (int s = 0; s < CP_MAX_S; ++s) {
+            if (s < S) {
+                const float4 xv = *reinterpret_cast<const float4*>(xs + (size_t)s * K + 4 * k4);
+                a0[s] = fmaf(wv.x, xv.x, a0[s]); a0[s] = fmaf(wv.y, xv.y, a0[s]);
+                a0[s] = fmaf(wv.z, xv.z, a0[s]); a0[s] = fmaf(wv.w, xv.w, a0[s]);
+                if (MODE == CP_SWIGLU) {
+                    a1[s] = fmaf(uv.x, xv.x, a1[s]); a1[s] = fmaf(uv.y, xv.y, a1[s]);
+                    a1[s] = fmaf(uv.z, xv.z, a1[s]); a1[s] = fmaf(uv.w, xv.w, a1[s]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < CP_MAX_S; ++s) {
+        for (int o = 16; o; o >>= 1) {
+            a0[s] += __shfl_xor_sync(0xffffffffu, a0[s], o);
+            if (MODE == CP_SWIGLU) a1[s] += __shfl_xor_sync(0xffffffffu, a1[s], o);
+        }
+    }
+    if (lane == 0) {
+        for (int s = 0; s < S; ++s) {
+            float v = a0[s];
+            if (MODE == CP_RESIDUAL) v += res[(size_t)s * N + n];
+            if (MODE == CP_SWIGLU) v = (v / (1.f + expf(-v))) * a1[s];
+            out[(size_t)s * N + n] = v;
+        }
+    }
+}
+
+// q/k RMSNorm over head_dim, rotary embedding, KV-cache append and causal attention for the S tokens of one call
+// (sibling :2352-2424).  One block per (query head, token of this call), one thread per head dimension.
+// qkv [S][q + 2 kv]; cache K/V [kv_heads][max_pos][hd]; positions pos0 .. pos0 + S - 1; rows < pos0 of the cache come
+// from earlier calls.  Every block rebuilds the normalised, rotated keys of THIS call's tokens for itself (its KV
+// head's writer block may not have run yet); the block of the group's first query head writes them to the cache.
+__global__ void cp_attn_kernel(const float* __restrict__ qkv, int S, int pos0, int heads, int kv_heads, int hd, int max_pos,
+                               const float* __restrict__ qn, const float* __restrict__ kn, const float* __restrict__ rope_cos,
+                               const float* __restrict__ rope_sin, float* __restrict__ kc, float* __restrict__ vc, float eps,
+                               float* __restrict__ att) {
+    extern __shared__ float sm[];
+    // blockDim.x = head_dim rounded up to whole warps; threads past head_dim only take part in the reductions
+    const int h = blockIdx.x, s = blockIdx.y, d = threadIdx.x;
+    const bool live = d < hd;
+    const int rep = heads / kv_heads, g = h / rep;
+    const int qd = heads * hd, kvd = kv_heads * hd, ld = qd + 2 * kvd, H2 = hd / 2;
+    float* buf = sm;                           // [hd] scratch for the rotation partner
+    float* red = sm + hd;                      // [32]
+    float* knew = sm + hd + 32;                // [S][hd]: this call's keys (normalised, rotated)
+    float* pr = knew + CP_MAX_S * hd;          // [max_pos] scores / probabilities
+    auto block_sum = [&](float v) -> float {
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __syncthreads();
+        if ((d & 31) == 0) red[d >> 5] = v;
+        __syncthreads();
+        float t = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+        return t;
+    };
+    auto norm_rope = [&](float v, const float* w, int pos) -> float {
+        const float ss = block_sum(v * v);
+        if (live) v = w[d] * (v * rsqrtf(ss / (float)hd + eps));
+        __syncthreads();
+        if (live) buf[d] = v;
+        __syncthreads();
+        if (!live) return 0.f;
+        const float partner = d < H2 ? -buf[d + H2] : buf[d - H2];      // rotate_half (sibling :816-820)
+        const int f = d < H2 ? d : d - H2;
+        return v * rope_cos[pos * H2 + f] + partner * rope_sin[pos * H2 + f];
+    };
+    // this call's keys (all tokens up to and including s)
+    for (int t = 0; t <= s; ++t) {
+        const float kv_ = norm_rope(live ? qkv[(size_t)t * ld + qd + g * hd + d] : 0.f, kn, pos0 + t);
+        if (live) knew[t * hd + d] = kv_;
+        if (live && t == s && h % rep == 0) {
+            kc[((size_t)g * max_pos + pos0 + s) * hd + d] = kv_;
+            vc[((size_t)g * max_pos + pos0 + s) * hd + d] = qkv[(size_t)s * ld + qd + kvd + g * hd + d];
+        }
+    }
+    const float q = norm_rope(live ? qkv[(size_t)s * ld + h * hd + d] : 0.f, qn, pos0 + s);
+    const int P = pos0 + s + 1;                                // keys 0 .. pos0 + s
+    const float scaling = rsqrtf((float)hd);
+    for (int j = 0; j < P; ++j) {
+        const float kj = !live ? 0.f : j < pos0 ? kc[((size_t)g * max_pos + j) * hd + d] : knew[(j - pos0) * hd + d];
+        const float sc = block_sum(q * kj) * scaling;
+        if (d == 0) pr[j] = sc;
+    }
+    __syncthreads();
+    if (!live) return;
+    float mx = -INFINITY;
+    for (int j = 0; j < P; ++j) mx = fmaxf(mx, pr[j]);
+    float l = 0.f;
+    for (int j = 0; j < P; ++j) l += expf(pr[j] - mx);
+    float o = 0.f;
+    for (int j = 0; j < P; ++j) {
+        const float vj = j < pos0 ? vc[((size_t)g * max_pos + j) * hd + d] : qkv[(size_t)(j - pos0) * ld + qd + kvd + g * hd + d];
+        o = fmaf(expf(pr[j] - mx), vj, o);
+    }
+    att[(size_t)s * qd + h * hd + d] = o / l;
+}
+
+// Device parameters of one predict() (updated by a small H2D copy before the graph is launched)
+struct CpSampleParams { float temperature; int top_k; unsigned long long seed; };
+
+__device__ __forceinline__ unsigned long long cp_splitmix(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+// code_predictor_server.py:87-92 on the device: the top_k largest logits, softmax of (l - max) / max(T, 1e-6), one
+// categorical draw (inverse CDF over the candidates in descending order; counter-based generator keyed by seed and
+// group -- the reference draws from numpy's global generator, which no device code can reproduce: the distribution is
+// the same, the stream is not).  Also the next step's input: out_embed = emb_table[code].  One block.
+__global__ void __launch_bounds__(256)
+cp_sample_kernel(const float* __restrict__ logits, int vocab, const CpSampleParams* __restrict__ sp, int group,
+                 const float* __restrict__ emb_table, int H, int* __restrict__ codes, float* __restrict__ out_embed) {
+    __shared__ float vals[4096];
+    __shared__ float cand_v[64];
+    __shared__ int cand_i[64];
+    __shared__ float rv[8];
+    __shared__ int ri[8];
+    __shared__ int chosen;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < vocab; i += blockDim.x) vals[i] = logits[i];
+    __syncthreads();
+    int K = sp->top_k; if (K > 64) K = 64; if (K > vocab) K = vocab; if (K < 1) K = 1;
+    for (int r = 0; r < K; ++r) {
+        float bv = -INFINITY; int bi = 0x7fffffff;
+        for (int i = tid; i < vocab; i += blockDim.x) { const float v = vals[i]; if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; } }
+        for (int o = 16; o; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if ((tid & 31) == 0) { rv[tid >> 5] = bv; ri[tid >> 5] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < (int)(blockDim.x >> 5); ++w) if (rv[w] > bv || (rv[w] == bv && ri[w] < bi)) { bv = rv[w]; bi = ri[w]; }
+            cand_v[r] = bv; cand_i[r] = bi; vals[bi] = -INFINITY;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const float T = fmaxf(sp->temperature, 1e-6f);
+        float sum = 0.f;
+        for (int r = 0; r < K; ++r) { cand_v[r] = expf((cand_v[r] - cand_v[0]) / T); sum += cand_v[r]; }
+        const unsigned long long bits = cp_splitmix(sp->seed * 0x100000001B3ull + (unsigned long long)group);
+        const float u = (float)((bits >> 40) * (1.0 / 16777216.0)) * sum;          // uniform in [0, sum)
+        float c = 0.f; int pick = K - 1;
+        for (int r = 0; r < K; ++r) { c += cand_v[r]; if (u < c) { pick = r; break; } }
+        chosen = cand_i[pick];
+        codes[group] = chosen;
+    }
+    __syncthreads();
+    if (out_embed) for (int i = tid; i < H; i += blockDim.x) out_embed[i] = emb_table[(size_t)chosen * H + i];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+struct CpEngine {
+    CpCfg cfg;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    bool finalized = false;
+    std::map<std::string, std::vector<float>> raw;
+    std::vector<void*> owned;
+    struct Layer { float *ln1, *wqkv, *qn, *kn, *wo, *ln2, *wgu, *wd; };
+    std::vector<Layer> L;
+    float* fnorm = nullptr;
+    std::vector<float*> emb, head;
+    float *rope_cos = nullptr, *rope_sin = nullptr;
+    float *kc = nullptr, *vc = nullptr;              // [layers][kv_heads][max_pos][hd]
+    int cache_len = 0;                               // positions filled
+    int last_S = 1;                                  // tokens of the last step (cp_logits reads the last one)
+    long long graph_kernels = 0;
+    // scratch
+    float *d_x = nullptr, *d_xn = nullptr, *d_qkv = nullptr, *d_att = nullptr, *d_act = nullptr, *d_out = nullptr, *d_logits = nullptr;
+    float *d_in_hidden = nullptr, *d_in_embed = nullptr;
+    int* d_codes = nullptr;
+    CpSampleParams* d_sp = nullptr;
+    cudaGraphExec_t graph = nullptr;
+    long long launches = 0;
+
+    ~CpEngine() {
+        if (graph) cudaGraphExecDestroy(graph);
+        for (void* p : owned) cudaFree(p);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+thread_local std::string g_cp_create_error;
+
+#define CPK(expr)                                                                        \
+    do { cudaError_t _e = (expr);                                                        \
+         if (_e != cudaSuccess) {                                                        \
+             E->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                \
+             fprintf(stderr, "cp_b200: %s\n", E->err.c_str());                           \
+             return CP_E_CUDA; } } while (0)
+
+int cp_fail(CpEngine* E, int code, const std::string& m) {
+    E->err = m;
+    fprintf(stderr, "cp_b200: %s\n", m.c_str());
+    return code;
+}
+
+template <class T>
+T* cp_alloc(CpEngine* E, size_t n) {
+    T* p = nullptr;
+    if (cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) return nullptr;
+    E->owned.push_back(p);
+    return p;
+}
+
+float* cp_upload(CpEngine* E, const float* h, size_t n) {
+    float* d = cp_alloc<float>(E, n);
+    if (!d) return nullptr;
+    if (cudaMemcpyAsync(d, h, n * sizeof(float), cudaMemcpyHostToDevice, E->stream) != cudaSuccess) return nullptr;
+    return d;
+}
+
+const std::vector<float>* cp_raw(CpEngine* E, const std::string& name, size_t n) {
+    auto it = E->raw.find(name);
+    if (it == E->raw.end()) { E->err = "missing tensor " + name; return nullptr; }
+    if (it->second.size() != n) { E->err = "tensor " + name + " has wrong size"; return nullptr; }
+    return &it->second;
+}
+
+// one transformer pass over the S tokens in d_x (positions pos0 ..): d_out = final-normed hidden, caches grown
+int cp_forward(CpEngine* E, int S, int pos0, cudaStream_t st) {
+    const CpCfg& c = E->cfg;
+    const int H = c.hidden, Q = c.qdim(), KV = c.kvdim(), I = c.inter, hd = c.head_dim;
+    const size_t layer_cache = (size_t)c.kv_heads * c.max_positions * hd;
+    for (int l = 0; l < c.layers; ++l) {
+        auto& Ly = E->L[l];
+        cp_rmsnorm_kernel<<<S, 256, 0, st>>>(E->d_x, Ly.ln1, E->d_xn, H, (float)c.rms_eps);
+        cp_gemv_kernel<CP_PLAIN><<<(Q + 2 * KV + 7) / 8, 256, (size_t)S * H * 4, st>>>(Ly.wqkv, E->d_xn, S, Q + 2 * KV, H, E->d_qkv, nullptr);
+        const size_t asm_ = (size_t)(hd + 32 + CP_MAX_S * hd + c.max_positions) * 4;
+        cp_attn_kernel<<<dim3(c.heads, S), (hd + 31) / 32 * 32, asm_, st>>>(E->d_qkv, S, pos0, c.heads, c.kv_heads, hd, c.max_positions, Ly.qn, Ly.kn,
+                                                           E->rope_cos, E->rope_sin, E->kc + l * layer_cache, E->vc + l * layer_cache,
+                                                           (float)c.rms_eps, E->d_att);
+        cp_gemv_kernel<CP_RESIDUAL><<<(H + 7) / 8, 256, (size_t)S * Q * 4, st>>>(Ly.wo, E->d_att, S, H, Q, E->d_x, E->d_x);
+        cp_rmsnorm_kernel<<<S, 256, 0, st>>>(E->d_x, Ly.ln2, E->d_xn, H, (float)c.rms_eps);
+        cp_gemv_kernel<CP_SWIGLU><<<(I + 7) / 8, 256, (size_t)S * H * 4, st>>>(Ly.wgu, E->d_xn, S, I, H, E->d_act, nullptr);
+        cp_gemv_kernel<CP_RESIDUAL><<<(H + 7) / 8, 256, (size_t)S * I * 4, st>>>(Ly.wd, E->d_act, S, H, I, E->d_x, E->d_x);
+        E->launches += 7;
+    }
+    cp_rmsnorm_kernel<<<S, 256, 0, st>>>(E->d_x, E->fnorm, E->d_out, H, (float)c.rms_eps);
+    E->launches += 1;
+    CPK(cudaGetLastError());
+    return CP_OK;
+}
+
+int cp_build_graph(CpEngine* E) {
+    // predict(): position 0 = hidden state, position 1 = embedding of code_0, then 15 x (lm_head, sample + embed, step)
+    const CpCfg& c = E->cfg;
+    const int H = c.hidden;
+    cudaStream_t st = E->stream;
+    CPK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+    int rc = CP_OK;
+    const long long before = E->launches;
+    do {
+        if (cudaMemcpyAsync(E->d_x, E->d_in_hidden, (size_t)H * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess) { rc = CP_E_CUDA; break; }
+        if ((rc = cp_forward(E, 1, 0, st))) break;
+        if (cudaMemcpyAsync(E->d_x, E->d_in_embed, (size_t)H * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess) { rc = CP_E_CUDA; break; }
+        if ((rc = cp_forward(E, 1, 1, st))) break;
+        for (int g = 0; g < c.groups; ++g) {
+            cp_gemv_kernel<CP_PLAIN><<<(c.vocab + 7) / 8, 256, (size_t)H * 4, st>>>(E->head[g], E->d_out, 1, c.vocab, H, E->d_logits, nullptr);
+            const bool more = g + 1 < c.groups;
+            cp_sample_kernel<<<1, 256, 0, st>>>(E->d_logits, c.vocab, E->d_sp, g, more ? E->emb[g] : nullptr, H, E->d_codes,
+                                                more ? E->d_x : nullptr);
+            E->launches += 2;
+            if (more && (rc = cp_forward(E, 1, g + 2, st))) break;
+        }
+    } while (0);
+    E->graph_kernels = E->launches - before;
+    E->launches = before;
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess || !graph) return cp_fail(E, CP_E_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(ce));
+    CPK(cudaGraphInstantiate(&E->graph, graph, 0));
+    cudaGraphDestroy(graph);
+    return CP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void* cp_create(const char* cfg_json, int device) {
+    try {
+        auto E = std::make_unique<CpEngine>();
+        if (cfg_json && *cfg_json) {
+            const std::string js = cfg_json;
+            double v;
+            auto geti = [&](const char* k, int& dst) { if (json_num(js, k, v)) dst = (int)v; };
+            geti("hidden", E->cfg.hidden); geti("layers", E->cfg.layers); geti("heads", E->cfg.heads); geti("kv_heads", E->cfg.kv_heads);
+            geti("head_dim", E->cfg.head_dim); geti("inter", E->cfg.inter); geti("vocab", E->cfg.vocab); geti("groups", E->cfg.groups);
+            geti("max_positions", E->cfg.max_positions);
+            if (json_num(js, "rms_eps", v)) E->cfg.rms_eps = v;
+            if (json_num(js, "rope_theta", v)) E->cfg.rope_theta = v;
+        }
+        const CpCfg& c = E->cfg;
+        auto bad = [&](const char* m) -> void* { g_cp_create_error = m; fprintf(stderr, "cp_create: %s\n", m); return nullptr; };
+        if (c.hidden % 4 || c.inter % 4 || c.qdim() % 4 || c.head_dim % 2 || c.head_dim > 256 || c.head_dim < 2) return bad("dimensions must be multiples of 4 (head_dim even, <= 256)");
+        if (c.heads % c.kv_heads || c.layers < 1 || c.groups < 1 || c.vocab < 1 || c.vocab > 4096) return bad("bad head / layer / vocabulary configuration");
+        if (c.max_positions < c.groups + 2) return bad("max_positions must cover groups + 2 positions");
+        if ((size_t)CP_MAX_S * std::max(c.inter, std::max(c.hidden, c.qdim())) * 4 > 48 * 1024) return bad("layer too wide for the shared-memory staged GEMV");
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return bad("no usable CUDA device (there is no CPU fallback)");
+        E->device = device;
+        if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking) != cudaSuccess)
+            return bad("cudaSetDevice / stream creation failed");
+        return E.release();
+    } catch (...) { g_cp_create_error = "cp_create: internal error"; return nullptr; }
+}
+
+void cp_destroy(void* h) {
+    if (!h) return;
+    CpEngine* E = (CpEngine*)h;
+    cudaSetDevice(E->device);
+    cudaDeviceSynchronize();
+    delete E;
+}
+
+int cp_set_tensor(void* h, const char* name, const float* data, long long n) {
+    CpEngine* E = (CpEngine*)h;
+    if (!E || !name || !data || n <= 0) return CP_E_INVALID;
+    if (E->finalized) return cp_fail(E, CP_E_STATE, "cp_set_tensor after cp_finalize");
+    try { E->raw[name].assign(data, data + n); } catch (...) { return CP_E_NOMEM; }
+    return CP_OK;
+}
+
+int cp_finalize(void* h) {
+    CpEngine* E = (CpEngine*)h;
+    if (!E) return CP_E_INVALID;
+    if (E->finalized) return cp_fail(E, CP_E_STATE, "already finalized");
+    try {
+        const CpCfg& c = E->cfg;
+        CPK(cudaSetDevice(E->device));
+        const int H = c.hidden, Q = c.qdim(), KV = c.kvdim(), I = c.inter, hd = c.head_dim;
+#define CPREQ(x) do { if (!(x)) return cp_fail(E, E->err.rfind("missing", 0) == 0 || E->err.rfind("tensor", 0) == 0 ? CP_E_STATE : CP_E_CUDA, E->err.empty() ? std::string("cp_finalize failed: " #x) : E->err); } while (0)
+        E->L.resize(c.layers);
+        for (int l = 0; l < c.layers; ++l) {
+            const std::string p = "layer_" + std::to_string(l) + "_";
+            auto& Ly = E->L[l];
+            auto up = [&](const char* nm, size_t n) -> float* { auto* v = cp_raw(E, p + nm, n); return v ? cp_upload(E, v->data(), n) : nullptr; };
+            CPREQ(Ly.ln1 = up("input_ln", H)); CPREQ(Ly.ln2 = up("post_ln", H));
+            CPREQ(Ly.qn = up("q_norm", hd)); CPREQ(Ly.kn = up("k_norm", hd));
+            CPREQ(Ly.wo = up("o_proj", (size_t)H * Q)); CPREQ(Ly.wd = up("down_proj", (size_t)H * I));
+            // q | k | v rows stacked: one GEMV; gate rows then up rows: one GEMV with the SwiGLU epilogue
+            auto *wq = cp_raw(E, p + "q_proj", (size_t)Q * H), *wk = cp_raw(E, p + "k_proj", (size_t)KV * H), *wv = cp_raw(E, p + "v_proj", (size_t)KV * H);
+            CPREQ(wq && wk && wv);
+            std::vector<float> cat; cat.reserve((size_t)(Q + 2 * KV) * H);
+            cat.insert(cat.end(), wq->begin(), wq->end()); cat.insert(cat.end(), wk->begin(), wk->end()); cat.insert(cat.end(), wv->begin(), wv->end());
+            CPREQ(Ly.wqkv = cp_upload(E, cat.data(), cat.size()));
+            CPK(cudaStreamSynchronize(E->stream));
+            auto *wg = cp_raw(E, p + "gate_proj", (size_t)I * H), *wu = cp_raw(E, p + "up_proj", (size_t)I * H);
+            CPREQ(wg && wu);
+            cat.clear(); cat.insert(cat.end(), wg->begin(), wg->end()); cat.insert(cat.end(), wu->begin(), wu->end());
+            CPREQ(Ly.wgu = cp_upload(E, cat.data(), cat.size()));
+            CPK(cudaStreamSynchronize(E->stream));
+        }
+        { auto* v = cp_raw(E, "final_norm", H); CPREQ(v); CPREQ(E->fnorm = cp_upload(E, v->data(), H)); }
+        E->emb.resize(c.groups); E->head.resize(c.groups);
+        for (int g = 0; g < c.groups; ++g) {
+            auto* e = cp_raw(E, "codec_emb_" + std::to_string(g), (size_t)c.vocab * H); CPREQ(e);
+            auto* l = cp_raw(E, "lm_head_" + std::to_string(g), (size_t)c.vocab * H); CPREQ(l);
+            CPREQ(E->emb[g] = cp_upload(E, e->data(), e->size()));
+            CPREQ(E->head[g] = cp_upload(E, l->data(), l->size()));
+        }
+        // rotary table in float64, cast to float32: angle = pos * theta^(-2 i / hd)
+        {
+            const int H2 = hd / 2;
+            std::vector<float> cs((size_t)c.max_positions * H2), sn((size_t)c.max_positions * H2);
+            for (int p = 0; p < c.max_positions; ++p) for (int i = 0; i < H2; ++i) {
+                const double inv = 1.0 / std::pow(c.rope_theta, (2.0 * i) / hd);
+                cs[(size_t)p * H2 + i] = (float)std::cos(p * inv);
+                sn[(size_t)p * H2 + i] = (float)std::sin(p * inv);
+            }
+            CPREQ(E->rope_cos = cp_upload(E, cs.data(), cs.size())); CPREQ(E->rope_sin = cp_upload(E, sn.data(), sn.size()));
+            CPK(cudaStreamSynchronize(E->stream));
+        }
+        const size_t cache = (size_t)c.layers * c.kv_heads * c.max_positions * hd;
+        CPREQ(E->kc = cp_alloc<float>(E, cache)); CPREQ(E->vc = cp_alloc<float>(E, cache));
+        CPREQ(E->d_x = cp_alloc<float>(E, (size_t)CP_MAX_S * H)); CPREQ(E->d_xn = cp_alloc<float>(E, (size_t)CP_MAX_S * H));
+        CPREQ(E->d_qkv = cp_alloc<float>(E, (size_t)CP_MAX_S * (Q + 2 * KV))); CPREQ(E->d_att = cp_alloc<float>(E, (size_t)CP_MAX_S * Q));
+        CPREQ(E->d_act = cp_alloc<float>(E, (size_t)CP_MAX_S * I)); CPREQ(E->d_out = cp_alloc<float>(E, (size_t)CP_MAX_S * H));
+        CPREQ(E->d_logits = cp_alloc<float>(E, c.vocab)); CPREQ(E->d_in_hidden = cp_alloc<float>(E, H)); CPREQ(E->d_in_embed = cp_alloc<float>(E, H));
+        CPREQ(E->d_codes = cp_alloc<int>(E, c.groups)); CPREQ(E->d_sp = cp_alloc<CpSampleParams>(E, 1));
+#undef CPREQ
+        CPK(cudaStreamSynchronize(E->stream));
+        E->raw.clear();
+        E->finalized = true;
+        if (int r = cp_build_graph(E)) return r;
+        CPK(cudaStreamSynchronize(E->stream));
+        E->cache_len = 0;
+        return CP_OK;
+    } catch (const std::bad_alloc&) { return cp_fail(E, CP_E_NOMEM, "out of host memory"); }
+    catch (...) { return cp_fail(E, CP_E_INVALID, "internal error"); }
+}
+
+int cp_reset(void* h) {
+    CpEngine* E = (CpEngine*)h;
+    if (!E) return CP_E_INVALID;
+    E->cache_len = 0;
+    return CP_OK;
+}
+
+int cp_cache_len(void* h) { return h ? ((CpEngine*)h)->cache_len : CP_E_INVALID; }
+
+int cp_step(void* h, const float* hidden_in, int S, int position, float* hidden_out) {
+    CpEngine* E = (CpEngine*)h;
+    if (!E) return CP_E_INVALID;
+    if (!E->finalized) return cp_fail(E, CP_E_STATE, "cp_finalize has not been called");
+    if (!hidden_in || !hidden_out || S < 1 || S > CP_MAX_S) return cp_fail(E, CP_E_INVALID, "bad argument (1 or 2 tokens per step)");
+    if (position != E->cache_len) return cp_fail(E, CP_E_INVALID, "position must equal the number of cached positions (cp_reset starts a frame)");
+    if (position + S > E->cfg.max_positions) return cp_fail(E, CP_E_INVALID, "position beyond max_positions");
+    CPK(cudaSetDevice(E->device));
+    const int H = E->cfg.hidden;
+    CPK(cudaMemcpyAsync(E->d_x, hidden_in, (size_t)S * H * 4, cudaMemcpyHostToDevice, E->stream));
+    if (int r = cp_forward(E, S, position, E->stream)) return r;
+    CPK(cudaMemcpyAsync(hidden_out, E->d_out, (size_t)S * H * 4, cudaMemcpyDeviceToHost, E->stream));
+    CPK(cudaStreamSynchronize(E->stream));
+    E->cache_len = position + S;
+    E->last_S = S;
+    return CP_OK;
+}
+
+int cp_logits(void* h, int group, float* logits_out) {
+    CpEngine* E = (CpEngine*)h;
+    if (!E) return CP_E_INVALID;
+    if (!E->finalized) return cp_fail(E, CP_E_STATE, "cp_finalize has not been called");
+    if (!logits_out || group < 0 || group >= E->cfg.groups) return cp_fail(E, CP_E_INVALID, "bad argument");
+    if (E->cache_len < 1) return cp_fail(E, CP_E_STATE, "no step has run");
+    CPK(cudaSetDevice(E->device));
+    const CpCfg& c = E->cfg;
+    // the LAST token of the last step (row S - 1 of d_out; single-token steps write row 0)
+    cp_gemv_kernel<CP_PLAIN><<<(c.vocab + 7) / 8, 256, (size_t)c.hidden * 4, E->stream>>>(E->head[group], E->d_out + (size_t)(E->last_S - 1) * c.hidden, 1, c.vocab, c.hidden, E->d_logits, nullptr);
+    E->launches += 1;
+    CPK(cudaGetLastError());
+    CPK(cudaMemcpyAsync(logits_out, E->d_logits, (size_t)c.vocab * 4, cudaMemcpyDeviceToHost, E->stream));
+    CPK(cudaStreamSynchronize(E->stream));
+    return CP_OK;
+}
+
+int cp_predict(void* h, const float* hidden_state, const float* code0_embed, float temperature, int top_k,
+               unsigned long long seed, int* codes_out) {
+    CpEngine* E = (CpEngine*)h;
+    if (!E) return CP_E_INVALID;
+    if (!E->finalized || !E->graph) return cp_fail(E, CP_E_STATE, "cp_finalize has not been called");
+    if (!hidden_state || !code0_embed || !codes_out || top_k < 1) return cp_fail(E, CP_E_INVALID, "bad argument");
+    CPK(cudaSetDevice(E->device));
+    const CpCfg& c = E->cfg;
+    const CpSampleParams sp{temperature, top_k, seed};
+    CPK(cudaMemcpyAsync(E->d_in_hidden, hidden_state, (size_t)c.hidden * 4, cudaMemcpyHostToDevice, E->stream));
+    CPK(cudaMemcpyAsync(E->d_in_embed, code0_embed, (size_t)c.hidden * 4, cudaMemcpyHostToDevice, E->stream));
+    CPK(cudaMemcpyAsync(E->d_sp, &sp, sizeof sp, cudaMemcpyHostToDevice, E->stream));
+    CPK(cudaGraphLaunch(E->graph, E->stream));
+    CPK(cudaMemcpyAsync(codes_out, E->d_codes, (size_t)c.groups * sizeof(int), cudaMemcpyDeviceToHost, E->stream));
+    CPK(cudaStreamSynchronize(E->stream));
+    E->cache_len = c.groups + 1;
+    E->last_S = 1;
+    E->launches += E->graph_kernels;
+    return CP_OK;
+}
+
+int cp_hidden_size(void* h) { return h ? ((CpEngine*)h)->cfg.hidden : CP_E_INVALID; }
+int cp_num_groups(void* h) { return h ? ((CpEngine*)h)->cfg.groups : CP_E_INVALID; }
+int cp_vocab_size(void* h) { return h ? ((CpEngine*)h)->cfg.vocab : CP_E_INVALID; }
+long long cp_launches(void* h) { return h ? ((CpEngine*)h)->launches : CP_E_INVALID; }
+const char* cp_last_error(void* h) { return h ? ((CpEngine*)h)->err.c_str() : g_cp_create_error.c_str(); }
+void* cp_stream(void* h) { return h ? (void*)((CpEngine*)h)->stream : nullptr; }
+
+}  // extern "C"
