@@ -130,6 +130,7 @@ def code_predictor_leg(device: int, frames: int = 60):
     -- host hidden state + code_0 embedding in, 15 host int32 codes out, one CUDA-graph launch per frame -- and
     through the level-1 step interface with the reference's host sampler; the CPU oracle's frame time beside it."""
     import importlib
+    import torch
     cpm = importlib.import_module("qwen3-tts-axera-russian_b200.code_predictor")
     cfg = cpm.CPConfig()
     w = cpm.init_weights(cfg, 0)

@@ -55,6 +55,7 @@ constexpr int CP_MAX_S = 2;          // tokens per step call: 1, or the referenc
 // kernels
 // ------------------------------------------------------------------------------------------------------------
 // y[s] = w * x[s] * rsqrt(mean(x[s]^2) + eps)            (sibling Qwen3OmniMoeRMSNorm)
+// Only the level-1 interface launches this (hidden_out of cp_step); inside a step the norms are GEMV prologues.
 __global__ void cp_rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y, int H, float eps) {
     const int s = blockIdx.x;
     const float* xr = x + (size_t)s * H;
@@ -70,37 +71,80 @@ __global__ void cp_rmsnorm_kernel(const float* __restrict__ x, const float* __re
     for (int i = threadIdx.x; i < H; i += blockDim.x) y[(size_t)s * H + i] = w[i] * (xr[i] * inv);
 }
 
-// Matrix-vector product(s) with the input vector(s) in shared memory: one warp per output row.
+// Matrix-vector product(s), the op this whole path is made of.  Each launch streams one weight matrix (8 - 25 MB)
+// exactly once; everything else is arranged so that enough 128-bit loads are in flight to cover HBM latency:
+//   * the input vector(s) are staged in shared memory once per block -- with the preceding RMSNorm folded into the
+//     staging when NORM (sum of squares of the S x K inputs is a 256-thread reduction, cheaper than a launch);
+//   * KSPLIT warps share one output row (contiguous K segments, combined through shared memory), so that even the
+//     1024-row projections put >= 4096 warps on the machine and every lane issues its loads back to back.
 //   MODE 0: out[s][n] = W[n] . x[s]
 //   MODE 1: out[s][n] = res[s][n] + W[n] . x[s]                  (residual add; out may be res)
 //   MODE 2: out[s][n] = silu(W[n] . x[s]) * (W[N + n] . x[s])    (SwiGLU: gate rows, then up rows)
 enum { CP_PLAIN = 0, CP_RESIDUAL = 1, CP_SWIGLU = 2 };
-template <int MODE>
-__global__ void __launch_bounds__(256)
+constexpr int CP_GEMV_WARPS = 16;
+template <int MODE, int KSPLIT, bool NORM>
+__global__ void __launch_bounds__(CP_GEMV_WARPS * 32)
 cp_gemv_kernel(const float* __restrict__ W, const float* __restrict__ x, int S, int N, int K, float* __restrict__ out,
-               const float* res) {
+               const float* res, const float* __restrict__ ln_w, float eps) {
     extern __shared__ float xs[];                      // [S][K]
-    for (int i = threadIdx.x; i < S * K; i += blockDim.x) xs[i] = x[i];
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (n >= N) return;
-    const float4* w0 = reinterpret_cast<const float4*>(W + (size_t)n * K);
-    const float4* w1 = MODE == CP_SWIGLU ? reinterpret_cast<const float4*>(W + (size_t)(N + n) * K) : nullptr;
-    float a0[CP_MAX_S] = {0.f, 0.f}, a1[CP_MAX_S] = {0.f, 0.f};
-    for (int k4 = lane; k4 < K / 4; k4 += 32) {
-        const float4 wv = __ldg(w0 + k4);
-        float4 uv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (MODE == CP_SWIGLU) uv = __ldg(w1 + k4);
+    constexpr int NT = CP_GEMV_WARPS * 32;
+    __shared__ float red[CP_MAX_S][CP_GEMV_WARPS];
+    __shared__ float part[CP_GEMV_WARPS][2 * CP_MAX_S];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (NORM) {
+        float ss[CP_MAX_S] = {0.f, 0.f};
+        for (int i = tid; i < K; i += NT)
+            for (int s = 0; s < S; ++s) { const float v = x[(size_t)s * K + i]; xs[s * K + i] = v; ss[s] = fmaf(v, v, ss[s]); }
 #pragma unroll
         for (int s = 0; s < CP_MAX_S; ++s) {
-            if (s < S) {
-                const float4 xv = *reinterpret_cast<const float4*>(xs + (size_t)s * K + 4 * k4);
-                a0[s] = fmaf(wv.x, xv.x, a0[s]); a0[s] = fmaf(wv.y, xv.y, a0[s]);
-                a0[s] = fmaf(wv.z, xv.z, a0[s]); a0[s] = fmaf(wv.w, xv.w, a0[s]);
-                if (MODE == CP_SWIGLU) {
-                    a1[s] = fmaf(uv.x, xv.x, a1[s]); a1[s] = fmaf(uv.y, xv.y, a1[s]);
-                    a1[s] = fmaf(uv.z, xv.z, a1[s]); a1[s] = fmaf(uv.w, xv.w, a1[s]);
+            for (int o = 16; o; o >>= 1) ss[s] += __shfl_xor_sync(0xffffffffu, ss[s], o);
+            if (lane == 0) red[s][warp] = ss[s];
+        }
+        __syncthreads();
+        for (int s = 0; s < S; ++s) {
+            float tot = 0.f;
+#pragma unroll
+            for (int w = 0; w < CP_GEMV_WARPS; ++w) tot += red[s][w];
+            const float inv = rsqrtf(tot / (float)K + eps);
+            for (int i = tid; i < K; i += NT) xs[s * K + i] = ln_w[i] * (xs[s * K + i] * inv);
+        }
+    } else {
+        for (int i = tid; i < S * K; i += NT) xs[i] = x[i];
+    }
+    __syncthreads();
+    constexpr int RPB = CP_GEMV_WARPS / KSPLIT;        // output rows per block
+    const int n = blockIdx.x * RPB + warp / KSPLIT, ks = warp % KSPLIT;
+    const int K4 = K >> 2, seg = (K4 + KSPLIT - 1) / KSPLIT;
+    const int k0 = ks * seg, k1 = min(K4, k0 + seg);
+    float a0[CP_MAX_S] = {0.f, 0.f}, a1[CP_MAX_S] = {0.f, 0.f};
+    if (n < N) {
+        const float4* w0 = reinterpret_cast<const float4*>(W + (size_t)n * K);
+        const float4* w1 = reinterpret_cast<const float4*>(W + (size_t)(MODE == CP_SWIGLU ? N + n : n) * K);
+        // four (SwiGLU: eight) independent 128-bit loads per lane are issued before the first FMA needs one; rows past
+        // the segment load nothing and multiply zeros (branch-free)
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int kb = k0 + lane; kb < k1; kb += 128) {
+            float4 wv[4], uv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k4 = kb + 32 * u;
+                wv[u] = k4 < k1 ? __ldcs(w0 + k4) : z4;      // streamed once: evict-first keeps the L2 for activations
+                uv[u] = (MODE == CP_SWIGLU && k4 < k1) ? __ldcs(w1 + k4) : z4;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k4 = min(kb + 32 * u, K4 - 1);
+#pragma unroll
+                for (int s = 0; s < CP_MAX_S; ++s) {
+                    if (s < S) {
+                        const float4 xv = *reinterpret_cast<const float4*>(xs + (size_t)s * K + 4 * k4);
+                        a0[s] = fmaf(wv[u].x, xv.x, a0[s]); a0[s] = fmaf(wv[u].y, xv.y, a0[s]);
+                        a0[s] = fmaf(wv[u].z, xv.z, a0[s]); a0[s] = fmaf(wv[u].w, xv.w, a0[s]);
+                        if (MODE == CP_SWIGLU) {
+                            a1[s] = fmaf(uv[u].x, xv.x, a1[s]); a1[s] = fmaf(uv[u].y, xv.y, a1[s]);
+                            a1[s] = fmaf(uv[u].z, xv.z, a1[s]); a1[s] = fmaf(uv[u].w, xv.w, a1[s]);
+                        }
+                    }
                 }
             }
         }
@@ -112,7 +156,21 @@ cp_gemv_kernel(const float* __restrict__ W, const float* __restrict__ x, int S, 
             if (MODE == CP_SWIGLU) a1[s] += __shfl_xor_sync(0xffffffffu, a1[s], o);
         }
     }
-    if (lane == 0) {
+    if (KSPLIT > 1) {
+        if (lane == 0) {
+#pragma unroll
+            for (int s = 0; s < CP_MAX_S; ++s) { part[warp][2 * s] = a0[s]; part[warp][2 * s + 1] = a1[s]; }
+        }
+        __syncthreads();
+        if (ks == 0 && lane == 0) {
+#pragma unroll
+            for (int s = 0; s < CP_MAX_S; ++s) {
+                a0[s] = 0.f; a1[s] = 0.f;
+                for (int q = 0; q < KSPLIT; ++q) { a0[s] += part[warp + q][2 * s]; a1[s] += part[warp + q][2 * s + 1]; }
+            }
+        }
+    }
+    if (ks == 0 && lane == 0 && n < N) {
         for (int s = 0; s < S; ++s) {
             float v = a0[s];
             if (MODE == CP_RESIDUAL) v += res[(size_t)s * N + n];
@@ -123,73 +181,85 @@ cp_gemv_kernel(const float* __restrict__ W, const float* __restrict__ x, int S, 
 }
 
 // q/k RMSNorm over head_dim, rotary embedding, KV-cache append and causal attention for the S tokens of one call
-// (sibling :2352-2424).  One block per (query head, token of this call), one thread per head dimension.
-// qkv [S][q + 2 kv]; cache K/V [kv_heads][max_pos][hd]; positions pos0 .. pos0 + S - 1; rows < pos0 of the cache come
-// from earlier calls.  Every block rebuilds the normalised, rotated keys of THIS call's tokens for itself (its KV
-// head's writer block may not have run yet); the block of the group's first query head writes them to the cache.
-__global__ void cp_attn_kernel(const float* __restrict__ qkv, int S, int pos0, int heads, int kv_heads, int hd, int max_pos,
-                               const float* __restrict__ qn, const float* __restrict__ kn, const float* __restrict__ rope_cos,
-                               const float* __restrict__ rope_sin, float* __restrict__ kc, float* __restrict__ vc, float eps,
-                               float* __restrict__ att) {
-    extern __shared__ float sm[];
-    // blockDim.x = head_dim rounded up to whole warps; threads past head_dim only take part in the reductions
-    const int h = blockIdx.x, s = blockIdx.y, d = threadIdx.x;
-    const bool live = d < hd;
+// (sibling :2352-2424).  One block of four warps per (query head, token of this call); a lane owns four consecutive
+// head dimensions (head_dim = 4 * live lanes, a power of two <= 128), so the norms, the rotation partner
+// (lane ^ live/2) and the dot products are warp shuffles -- no block barrier until the final merge.  Warp w takes key
+// positions w, w + 4, ... with its own online softmax.  Positions < pos0 come from the cache; this call's keys are
+// normalised and rotated in place by whichever warp meets them (the writer block of that KV head may not have run
+// yet), and the block of the group's first query head appends them to the cache.
+// qkv [S][q + 2 kv]; cache K/V [kv_heads][max_pos][hd].
+__global__ void __launch_bounds__(128)
+cp_attn_kernel(const float* __restrict__ qkv, int S, int pos0, int heads, int kv_heads, int hd, int max_pos,
+               const float* __restrict__ qn, const float* __restrict__ kn, const float* __restrict__ rope_cos,
+               const float* __restrict__ rope_sin, float* __restrict__ kc, float* __restrict__ vc, float eps,
+               float* __restrict__ att) {
+    __shared__ float sm_m[4], sm_l[4];
+    __shared__ float4 sm_o[4][32];
+    const int h = blockIdx.x, s = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int live_lanes = hd >> 2, half = live_lanes >> 1, H2 = hd >> 1;
+    const bool live = lane < live_lanes;
     const int rep = heads / kv_heads, g = h / rep;
-    const int qd = heads * hd, kvd = kv_heads * hd, ld = qd + 2 * kvd, H2 = hd / 2;
-    float* buf = sm;                           // [hd] scratch for the rotation partner
-    float* red = sm + hd;                      // [32]
-    float* knew = sm + hd + 32;                // [S][hd]: this call's keys (normalised, rotated)
-    float* pr = knew + CP_MAX_S * hd;          // [max_pos] scores / probabilities
-    auto block_sum = [&](float v) -> float {
-        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        __syncthreads();
-        if ((d & 31) == 0) red[d >> 5] = v;
-        __syncthreads();
-        float t = 0.f;
-        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
-        return t;
+    const int qd = heads * hd, kvd = kv_heads * hd, ld = qd + 2 * kvd;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto wsum = [](float v) { for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); return v; };
+    auto ld4 = [&](const float* p) { return live ? *reinterpret_cast<const float4*>(p + 4 * lane) : zero4; };
+    auto norm_rope = [&](float4 v, const float* w, int pos) -> float4 {
+        const float inv = rsqrtf(wsum(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w) / (float)hd + eps);
+        const float4 wv = ld4(w);
+        v = make_float4(wv.x * (v.x * inv), wv.y * (v.y * inv), wv.z * (v.z * inv), wv.w * (v.w * inv));
+        float4 r;                                       // rotate_half (sibling :816-820): (-x2, x1)
+        r.x = __shfl_xor_sync(0xffffffffu, v.x, half); r.y = __shfl_xor_sync(0xffffffffu, v.y, half);
+        r.z = __shfl_xor_sync(0xffffffffu, v.z, half); r.w = __shfl_xor_sync(0xffffffffu, v.w, half);
+        if (!live) return zero4;
+        const float sg = lane < half ? -1.f : 1.f;
+        const int f = 4 * (lane < half ? lane : lane - half);
+        const float4 c = *reinterpret_cast<const float4*>(rope_cos + (size_t)pos * H2 + f);
+        const float4 sn = *reinterpret_cast<const float4*>(rope_sin + (size_t)pos * H2 + f);
+        return make_float4(v.x * c.x + sg * r.x * sn.x, v.y * c.y + sg * r.y * sn.y, v.z * c.z + sg * r.z * sn.z,
+                           v.w * c.w + sg * r.w * sn.w);
     };
-    auto norm_rope = [&](float v, const float* w, int pos) -> float {
-        const float ss = block_sum(v * v);
-        if (live) v = w[d] * (v * rsqrtf(ss / (float)hd + eps));
-        __syncthreads();
-        if (live) buf[d] = v;
-        __syncthreads();
-        if (!live) return 0.f;
-        const float partner = d < H2 ? -buf[d + H2] : buf[d - H2];      // rotate_half (sibling :816-820)
-        const int f = d < H2 ? d : d - H2;
-        return v * rope_cos[pos * H2 + f] + partner * rope_sin[pos * H2 + f];
-    };
-    // this call's keys (all tokens up to and including s)
-    for (int t = 0; t <= s; ++t) {
-        const float kv_ = norm_rope(live ? qkv[(size_t)t * ld + qd + g * hd + d] : 0.f, kn, pos0 + t);
-        if (live) knew[t * hd + d] = kv_;
-        if (live && t == s && h % rep == 0) {
-            kc[((size_t)g * max_pos + pos0 + s) * hd + d] = kv_;
-            vc[((size_t)g * max_pos + pos0 + s) * hd + d] = qkv[(size_t)s * ld + qd + kvd + g * hd + d];
-        }
-    }
-    const float q = norm_rope(live ? qkv[(size_t)s * ld + h * hd + d] : 0.f, qn, pos0 + s);
+    const float4 q = norm_rope(ld4(qkv + (size_t)s * ld + h * hd), qn, pos0 + s);
     const int P = pos0 + s + 1;                                // keys 0 .. pos0 + s
     const float scaling = rsqrtf((float)hd);
-    for (int j = 0; j < P; ++j) {
-        const float kj = !live ? 0.f : j < pos0 ? kc[((size_t)g * max_pos + j) * hd + d] : knew[(j - pos0) * hd + d];
-        const float sc = block_sum(q * kj) * scaling;
-        if (d == 0) pr[j] = sc;
+    float m = -INFINITY, l = 0.f;
+    float4 o = zero4;
+    for (int j = warp; j < P; j += 4) {
+        float4 k4, v4;
+        if (j < pos0) {
+            k4 = ld4(kc + ((size_t)g * max_pos + j) * hd);
+            v4 = ld4(vc + ((size_t)g * max_pos + j) * hd);
+        } else {
+            const int t = j - pos0;
+            k4 = norm_rope(ld4(qkv + (size_t)t * ld + qd + g * hd), kn, j);
+            v4 = ld4(qkv + (size_t)t * ld + qd + kvd + g * hd);
+            if (t == s && h % rep == 0 && live) {
+                *reinterpret_cast<float4*>(kc + ((size_t)g * max_pos + j) * hd + 4 * lane) = k4;
+                *reinterpret_cast<float4*>(vc + ((size_t)g * max_pos + j) * hd + 4 * lane) = v4;
+            }
+        }
+        const float sc = wsum(q.x * k4.x + q.y * k4.y + q.z * k4.z + q.w * k4.w) * scaling;
+        const float mn = fmaxf(m, sc), a = expf(m - mn), p = expf(sc - mn);
+        l = l * a + p;
+        o = make_float4(o.x * a + p * v4.x, o.y * a + p * v4.y, o.z * a + p * v4.z, o.w * a + p * v4.w);
+        m = mn;
     }
+    if (lane == 0) { sm_m[warp] = m; sm_l[warp] = l; }
+    sm_o[warp][lane] = o;
     __syncthreads();
-    if (!live) return;
-    float mx = -INFINITY;
-    for (int j = 0; j < P; ++j) mx = fmaxf(mx, pr[j]);
-    float l = 0.f;
-    for (int j = 0; j < P; ++j) l += expf(pr[j] - mx);
-    float o = 0.f;
-    for (int j = 0; j < P; ++j) {
-        const float vj = j < pos0 ? vc[((size_t)g * max_pos + j) * hd + d] : qkv[(size_t)(j - pos0) * ld + qd + kvd + g * hd + d];
-        o = fmaf(expf(pr[j] - mx), vj, o);
+    if (warp == 0 && live) {
+        float M = sm_m[0];
+        for (int w = 1; w < 4; ++w) M = fmaxf(M, sm_m[w]);
+        float L = 0.f;
+        float4 acc = zero4;
+        for (int w = 0; w < 4; ++w) {
+            const float a = expf(sm_m[w] - M);             // warps that met no key: exp(-inf) = 0
+            const float4 ow = sm_o[w][lane];
+            L += sm_l[w] * a;
+            acc = make_float4(acc.x + ow.x * a, acc.y + ow.y * a, acc.z + ow.z * a, acc.w + ow.w * a);
+        }
+        const float il = 1.f / L;
+        *reinterpret_cast<float4*>(att + (size_t)s * qd + h * hd + 4 * lane) = make_float4(acc.x * il, acc.y * il, acc.z * il, acc.w * il);
     }
-    att[(size_t)s * qd + h * hd + d] = o / l;
 }
 
 // Device parameters of one predict() (updated by a small H2D copy before the graph is launched)
@@ -201,47 +271,92 @@ __device__ __forceinline__ unsigned long long cp_splitmix(unsigned long long x) 
 }
 
 // code_predictor_server.py:87-92 on the device: the top_k largest logits, softmax of (l - max) / max(T, 1e-6), one
-// categorical draw (inverse CDF over the candidates in descending order; counter-based generator keyed by seed and
-// group -- the reference draws from numpy's global generator, which no device code can reproduce: the distribution is
-// the same, the stream is not).  Also the next step's input: out_embed = emb_table[code].  One block.
+// categorical draw.  One block of 256 threads, 16 logits per thread in registers (vocab <= 4096):
+//   1. the k-th largest logit by bisection on the order-preserving integer image of the floats: 32 counting passes,
+//      one barrier each (no k rounds of arg-max: k = 50 of those cost 60 us);
+//   2. the candidates (> threshold, plus the lowest-indexed ties) compacted in index order by a block scan;
+//   3. warp 0: softmax over the <= 64 candidates, inclusive scan, inverse-CDF pick with a counter-based generator
+//      keyed by (seed, group).  The reference draws from NumPy's global generator, which no device code can
+//      reproduce: same distribution, different stream.  top_k = 1 is arg-max with NumPy's lowest-index tie-break.
+// Also writes the next step's input: out_embed = emb_table[code].
+constexpr int CP_VPT = 16;
+__device__ __forceinline__ unsigned cp_ordered(float v) {
+    const unsigned u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
 __global__ void __launch_bounds__(256)
 cp_sample_kernel(const float* __restrict__ logits, int vocab, const CpSampleParams* __restrict__ sp, int group,
                  const float* __restrict__ emb_table, int H, int* __restrict__ codes, float* __restrict__ out_embed) {
-    __shared__ float vals[4096];
+    __shared__ int cnt[34];
+    __shared__ int wtot[2][8];
     __shared__ float cand_v[64];
     __shared__ int cand_i[64];
-    __shared__ float rv[8];
-    __shared__ int ri[8];
     __shared__ int chosen;
-    const int tid = threadIdx.x;
-    for (int i = tid; i < vocab; i += blockDim.x) vals[i] = logits[i];
-    __syncthreads();
-    int K = sp->top_k; if (K > 64) K = 64; if (K > vocab) K = vocab; if (K < 1) K = 1;
-    for (int r = 0; r < K; ++r) {
-        float bv = -INFINITY; int bi = 0x7fffffff;
-        for (int i = tid; i < vocab; i += blockDim.x) { const float v = vals[i]; if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; } }
-        for (int o = 16; o; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-        }
-        if ((tid & 31) == 0) { rv[tid >> 5] = bv; ri[tid >> 5] = bi; }
-        __syncthreads();
-        if (tid == 0) {
-            for (int w = 1; w < (int)(blockDim.x >> 5); ++w) if (rv[w] > bv || (rv[w] == bv && ri[w] < bi)) { bv = rv[w]; bi = ri[w]; }
-            cand_v[r] = bv; cand_i[r] = bi; vals[bi] = -INFINITY;
-        }
-        __syncthreads();
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned key[CP_VPT];
+#pragma unroll
+    for (int r = 0; r < CP_VPT; ++r) {
+        const int i = tid * CP_VPT + r;
+        key[r] = i < vocab ? cp_ordered(logits[i]) : 0u;          // 0 sorts below every float
     }
-    if (tid == 0) {
+    if (tid < 34) cnt[tid] = 0;
+    int K = sp->top_k; if (K > 64) K = 64; if (K > vocab) K = vocab; if (K < 1) K = 1;
+    __syncthreads();
+    unsigned thr = 0;                                             // largest t with |{key >= t}| >= K
+    for (int bit = 31; bit >= 0; --bit) {
+        const unsigned cand = thr | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int r = 0; r < CP_VPT; ++r) c += key[r] >= cand;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (lane == 0 && c) atomicAdd(&cnt[bit], c);
+        __syncthreads();
+        if (cnt[bit] >= K) thr = cand;
+    }
+    // compaction: all keys > thr, then ties == thr in index order until K candidates
+    int ngt = 0, neq = 0;
+#pragma unroll
+    for (int r = 0; r < CP_VPT; ++r) { ngt += key[r] > thr; neq += key[r] == thr; }
+    int sgt = ngt, seq = neq;                                     // inclusive scans over the block, thread order
+    for (int o = 1; o < 32; o <<= 1) {
+        const int a = __shfl_up_sync(0xffffffffu, sgt, o), b = __shfl_up_sync(0xffffffffu, seq, o);
+        if (lane >= o) { sgt += a; seq += b; }
+    }
+    if (lane == 31) { wtot[0][warp] = sgt; wtot[1][warp] = seq; }
+    __syncthreads();
+    int bgt = 0, beq = 0, tgt = 0;
+    for (int w = 0; w < 8; ++w) { if (w < warp) { bgt += wtot[0][w]; beq += wtot[1][w]; } tgt += wtot[0][w]; }
+    int pgt = bgt + sgt - ngt, peq = beq + seq - neq;             // exclusive prefixes of this thread
+    const int take_eq = K - tgt;                                  // >= 1 by construction of thr
+#pragma unroll
+    for (int r = 0; r < CP_VPT; ++r) {
+        const int i = tid * CP_VPT + r;
+        if (key[r] > thr) { cand_v[pgt] = logits[i]; cand_i[pgt] = i; ++pgt; }
+        else if (key[r] == thr) { if (peq < take_eq) { cand_v[tgt + peq] = logits[i]; cand_i[tgt + peq] = i; } ++peq; }
+    }
+    __syncthreads();
+    if (warp == 0) {
         const float T = fmaxf(sp->temperature, 1e-6f);
-        float sum = 0.f;
-        for (int r = 0; r < K; ++r) { cand_v[r] = expf((cand_v[r] - cand_v[0]) / T); sum += cand_v[r]; }
+        const float v0 = lane < K ? cand_v[lane] : -INFINITY, v1 = lane + 32 < K ? cand_v[lane + 32] : -INFINITY;
+        float mx = fmaxf(v0, v1);
+        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        const float e0 = lane < K ? expf((v0 - mx) / T) : 0.f, e1 = lane + 32 < K ? expf((v1 - mx) / T) : 0.f;
+        float c0 = e0, c1 = e1;
+        for (int o = 1; o < 32; o <<= 1) {
+            const float a = __shfl_up_sync(0xffffffffu, c0, o), b = __shfl_up_sync(0xffffffffu, c1, o);
+            if (lane >= o) { c0 += a; c1 += b; }
+        }
+        const float tot0 = __shfl_sync(0xffffffffu, c0, 31), tot1 = __shfl_sync(0xffffffffu, c1, 31);
+        c1 += tot0;
         const unsigned long long bits = cp_splitmix(sp->seed * 0x100000001B3ull + (unsigned long long)group);
-        const float u = (float)((bits >> 40) * (1.0 / 16777216.0)) * sum;          // uniform in [0, sum)
-        float c = 0.f; int pick = K - 1;
-        for (int r = 0; r < K; ++r) { c += cand_v[r]; if (u < c) { pick = r; break; } }
-        chosen = cand_i[pick];
-        codes[group] = chosen;
+        const float u = (float)((bits >> 40) * (1.0 / 16777216.0)) * (tot0 + tot1);      // uniform in [0, sum)
+        const unsigned b0 = __ballot_sync(0xffffffffu, lane < K && u < c0);
+        const unsigned b1 = __ballot_sync(0xffffffffu, lane + 32 < K && u < c1);
+        if (lane == 0) {
+            const int pick = b0 ? __ffs(b0) - 1 : b1 ? 32 + __ffs(b1) - 1 : K - 1;
+            chosen = cand_i[pick];
+            codes[group] = chosen;
+        }
     }
     __syncthreads();
     if (out_embed) for (int i = tid; i < H; i += blockDim.x) out_embed[i] = emb_table[(size_t)chosen * H + i];
@@ -317,29 +432,48 @@ const std::vector<float>* cp_raw(CpEngine* E, const std::string& name, size_t n)
     return &it->second;
 }
 
-// one transformer pass over the S tokens in d_x (positions pos0 ..): d_out = final-normed hidden, caches grown
+template <int MODE, bool NORM>
+void cp_gemv(cudaStream_t st, const float* W, const float* x, int S, int N, int K, float* out, const float* res,
+             const float* ln_w, float eps) {
+    const size_t smem = (size_t)S * K * sizeof(float);
+    if (N >= 3072) {
+        constexpr int RPB = CP_GEMV_WARPS / 2;
+        cp_gemv_kernel<MODE, 2, NORM><<<(N + RPB - 1) / RPB, CP_GEMV_WARPS * 32, smem, st>>>(W, x, S, N, K, out, res, ln_w, eps);
+    } else {
+        constexpr int RPB = CP_GEMV_WARPS / 4;
+        cp_gemv_kernel<MODE, 4, NORM><<<(N + RPB - 1) / RPB, CP_GEMV_WARPS * 32, smem, st>>>(W, x, S, N, K, out, res, ln_w, eps);
+    }
+}
+
+// one transformer pass over the S tokens in d_x (positions pos0 ..): the residual stream stays in d_x (un-normed; the
+// final norm is the prologue of the lm_head GEMV, or cp_rmsnorm_kernel for level 1's hidden_out), caches grown.
+// Five launches per layer.
 int cp_forward(CpEngine* E, int S, int pos0, cudaStream_t st) {
     const CpCfg& c = E->cfg;
     const int H = c.hidden, Q = c.qdim(), KV = c.kvdim(), I = c.inter, hd = c.head_dim;
+    const float eps = (float)c.rms_eps;
     const size_t layer_cache = (size_t)c.kv_heads * c.max_positions * hd;
     for (int l = 0; l < c.layers; ++l) {
         auto& Ly = E->L[l];
-        cp_rmsnorm_kernel<<<S, 256, 0, st>>>(E->d_x, Ly.ln1, E->d_xn, H, (float)c.rms_eps);
-        cp_gemv_kernel<CP_PLAIN><<<(Q + 2 * KV + 7) / 8, 256, (size_t)S * H * 4, st>>>(Ly.wqkv, E->d_xn, S, Q + 2 * KV, H, E->d_qkv, nullptr);
-        const size_t asm_ = (size_t)(hd + 32 + CP_MAX_S * hd + c.max_positions) * 4;
-        cp_attn_kernel<<<dim3(c.heads, S), (hd + 31) / 32 * 32, asm_, st>>>(E->d_qkv, S, pos0, c.heads, c.kv_heads, hd, c.max_positions, Ly.qn, Ly.kn,
-                                                           E->rope_cos, E->rope_sin, E->kc + l * layer_cache, E->vc + l * layer_cache,
-                                                           (float)c.rms_eps, E->d_att);
-        cp_gemv_kernel<CP_RESIDUAL><<<(H + 7) / 8, 256, (size_t)S * Q * 4, st>>>(Ly.wo, E->d_att, S, H, Q, E->d_x, E->d_x);
-        cp_rmsnorm_kernel<<<S, 256, 0, st>>>(E->d_x, Ly.ln2, E->d_xn, H, (float)c.rms_eps);
-        cp_gemv_kernel<CP_SWIGLU><<<(I + 7) / 8, 256, (size_t)S * H * 4, st>>>(Ly.wgu, E->d_xn, S, I, H, E->d_act, nullptr);
-        cp_gemv_kernel<CP_RESIDUAL><<<(H + 7) / 8, 256, (size_t)S * I * 4, st>>>(Ly.wd, E->d_act, S, H, I, E->d_x, E->d_x);
-        E->launches += 7;
+        cp_gemv<CP_PLAIN, true>(st, Ly.wqkv, E->d_x, S, Q + 2 * KV, H, E->d_qkv, nullptr, Ly.ln1, eps);
+        cp_attn_kernel<<<dim3(c.heads, S), 128, 0, st>>>(E->d_qkv, S, pos0, c.heads, c.kv_heads, hd, c.max_positions, Ly.qn, Ly.kn,
+                                                         E->rope_cos, E->rope_sin, E->kc + l * layer_cache, E->vc + l * layer_cache,
+                                                         eps, E->d_att);
+        cp_gemv<CP_RESIDUAL, false>(st, Ly.wo, E->d_att, S, H, Q, E->d_x, E->d_x, nullptr, 0.f);
+        cp_gemv<CP_SWIGLU, true>(st, Ly.wgu, E->d_x, S, I, H, E->d_act, nullptr, Ly.ln2, eps);
+        cp_gemv<CP_RESIDUAL, false>(st, Ly.wd, E->d_act, S, H, I, E->d_x, E->d_x, nullptr, 0.f);
+        E->launches += 5;
     }
-    cp_rmsnorm_kernel<<<S, 256, 0, st>>>(E->d_x, E->fnorm, E->d_out, H, (float)c.rms_eps);
-    E->launches += 1;
     CPK(cudaGetLastError());
     return CP_OK;
+}
+
+// logits of `group` from row `row` of the residual stream: final RMSNorm folded into the lm_head GEMV
+void cp_head(CpEngine* E, int group, int row, cudaStream_t st) {
+    const CpCfg& c = E->cfg;
+    cp_gemv<CP_PLAIN, true>(st, E->head[group], E->d_x + (size_t)row * c.hidden, 1, c.vocab, c.hidden, E->d_logits, nullptr, E->fnorm,
+                            (float)c.rms_eps);
+    E->launches += 1;
 }
 
 int cp_build_graph(CpEngine* E) {
@@ -356,11 +490,11 @@ int cp_build_graph(CpEngine* E) {
         if (cudaMemcpyAsync(E->d_x, E->d_in_embed, (size_t)H * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess) { rc = CP_E_CUDA; break; }
         if ((rc = cp_forward(E, 1, 1, st))) break;
         for (int g = 0; g < c.groups; ++g) {
-            cp_gemv_kernel<CP_PLAIN><<<(c.vocab + 7) / 8, 256, (size_t)H * 4, st>>>(E->head[g], E->d_out, 1, c.vocab, H, E->d_logits, nullptr);
+            cp_head(E, g, 0, st);
             const bool more = g + 1 < c.groups;
             cp_sample_kernel<<<1, 256, 0, st>>>(E->d_logits, c.vocab, E->d_sp, g, more ? E->emb[g] : nullptr, H, E->d_codes,
                                                 more ? E->d_x : nullptr);
-            E->launches += 2;
+            E->launches += 1;
             if (more && (rc = cp_forward(E, 1, g + 2, st))) break;
         }
     } while (0);
@@ -394,7 +528,8 @@ void* cp_create(const char* cfg_json, int device) {
         }
         const CpCfg& c = E->cfg;
         auto bad = [&](const char* m) -> void* { g_cp_create_error = m; fprintf(stderr, "cp_create: %s\n", m); return nullptr; };
-        if (c.hidden % 4 || c.inter % 4 || c.qdim() % 4 || c.head_dim % 2 || c.head_dim > 256 || c.head_dim < 2) return bad("dimensions must be multiples of 4 (head_dim even, <= 256)");
+        if (c.hidden % 4 || c.inter % 4) return bad("hidden and inter must be multiples of 4");
+        if (c.head_dim < 8 || c.head_dim > 128 || (c.head_dim & (c.head_dim - 1))) return bad("head_dim must be a power of two in [8, 128]");
         if (c.heads % c.kv_heads || c.layers < 1 || c.groups < 1 || c.vocab < 1 || c.vocab > 4096) return bad("bad head / layer / vocabulary configuration");
         if (c.max_positions < c.groups + 2) return bad("max_positions must cover groups + 2 positions");
         if ((size_t)CP_MAX_S * std::max(c.inter, std::max(c.hidden, c.qdim())) * 4 > 48 * 1024) return bad("layer too wide for the shared-memory staged GEMV");
@@ -512,6 +647,9 @@ int cp_step(void* h, const float* hidden_in, int S, int position, float* hidden_
     const int H = E->cfg.hidden;
     CPK(cudaMemcpyAsync(E->d_x, hidden_in, (size_t)S * H * 4, cudaMemcpyHostToDevice, E->stream));
     if (int r = cp_forward(E, S, position, E->stream)) return r;
+    cp_rmsnorm_kernel<<<S, 256, 0, E->stream>>>(E->d_x, E->fnorm, E->d_out, H, (float)E->cfg.rms_eps);
+    E->launches += 1;
+    CPK(cudaGetLastError());
     CPK(cudaMemcpyAsync(hidden_out, E->d_out, (size_t)S * H * 4, cudaMemcpyDeviceToHost, E->stream));
     CPK(cudaStreamSynchronize(E->stream));
     E->cache_len = position + S;
@@ -527,9 +665,7 @@ int cp_logits(void* h, int group, float* logits_out) {
     if (E->cache_len < 1) return cp_fail(E, CP_E_STATE, "no step has run");
     CPK(cudaSetDevice(E->device));
     const CpCfg& c = E->cfg;
-    // the LAST token of the last step (row S - 1 of d_out; single-token steps write row 0)
-    cp_gemv_kernel<CP_PLAIN><<<(c.vocab + 7) / 8, 256, (size_t)c.hidden * 4, E->stream>>>(E->head[group], E->d_out + (size_t)(E->last_S - 1) * c.hidden, 1, c.vocab, c.hidden, E->d_logits, nullptr);
-    E->launches += 1;
+    cp_head(E, group, E->last_S - 1, E->stream);          // the LAST token of the last step
     CPK(cudaGetLastError());
     CPK(cudaMemcpyAsync(logits_out, E->d_logits, (size_t)c.vocab * 4, cudaMemcpyDeviceToHost, E->stream));
     CPK(cudaStreamSynchronize(E->stream));
