@@ -23,6 +23,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace {
@@ -49,6 +50,14 @@ static bool json_num(const std::string& js, const char* key, double& v) {
     return true;
 }
 
+// Programmatic dependent launch: every kernel of a step lets its successor start while it is still running
+// (griddepcontrol.launch_dependents at the top) and touches activations only after griddepcontrol.wait, which returns
+// once the predecessor grid has completed and its writes are visible.  Weights are read-only for the life of the
+// handle, so a GEMV issues its first batch of weight loads BEFORE the wait: the HBM stream of kernel N + 1 starts under
+// the tail of kernel N instead of after a launch gap.
+__device__ __forceinline__ void cp_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void cp_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 constexpr int CP_MAX_S = 2;          // tokens per step call: 1, or the reference's 2-token batch prefill
 
 // ------------------------------------------------------------------------------------------------------------
@@ -59,6 +68,8 @@ constexpr int CP_MAX_S = 2;          // tokens per step call: 1, or the referenc
 __global__ void cp_rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y, int H, float eps) {
     const int s = blockIdx.x;
     const float* xr = x + (size_t)s * H;
+    cp_pdl_launch_dependents();
+    cp_pdl_wait();
     float ss = 0.f;
     for (int i = threadIdx.x; i < H; i += blockDim.x) ss += xr[i] * xr[i];
     __shared__ float red[32];
@@ -83,7 +94,7 @@ __global__ void cp_rmsnorm_kernel(const float* __restrict__ x, const float* __re
 enum { CP_PLAIN = 0, CP_RESIDUAL = 1, CP_SWIGLU = 2 };
 constexpr int CP_GEMV_WARPS = 16;
 template <int MODE, int KSPLIT, bool NORM>
-__global__ void __launch_bounds__(CP_GEMV_WARPS * 32)
+__global__ void __launch_bounds__(CP_GEMV_WARPS * 32, 2)
 cp_gemv_kernel(const float* __restrict__ W, const float* __restrict__ x, int S, int N, int K, float* __restrict__ out,
                const float* res, const float* __restrict__ ln_w, float eps) {
     extern __shared__ float xs[];                      // [S][K]
@@ -91,6 +102,28 @@ cp_gemv_kernel(const float* __restrict__ W, const float* __restrict__ x, int S, 
     __shared__ float red[CP_MAX_S][CP_GEMV_WARPS];
     __shared__ float part[CP_GEMV_WARPS][2 * CP_MAX_S];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    cp_pdl_launch_dependents();
+    constexpr int RPB = CP_GEMV_WARPS / KSPLIT;        // output rows per block
+    const int n = blockIdx.x * RPB + warp / KSPLIT, ks = warp % KSPLIT;
+    const int K4 = K >> 2, seg = (K4 + KSPLIT - 1) / KSPLIT;
+    const int k0 = ks * seg, k1 = n < N ? min(K4, k0 + seg) : 0;
+    const float4* w0 = reinterpret_cast<const float4*>(W + (size_t)min(n, N - 1) * K);
+    const float4* w1 = reinterpret_cast<const float4*>(W + (size_t)(MODE == CP_SWIGLU ? N + min(n, N - 1) : 0) * K);
+    // four independent 128-bit loads per lane per batch; slots past the segment load nothing and
+    // multiply zeros (branch-free).  Streamed once: evict-first keeps the L2 for activations.
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    constexpr int U = MODE == CP_SWIGLU ? 2 : 4;       // float4 slots per matrix per batch: four loads in flight per lane
+    float4 wv[U], uv[U];
+    auto load_batch = [&](int kb) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int k4 = kb + 32 * u;
+            wv[u] = k4 < k1 ? __ldcs(w0 + k4) : z4;
+            uv[u] = (MODE == CP_SWIGLU && k4 < k1) ? __ldcs(w1 + k4) : z4;
+        }
+    };
+    load_batch(k0 + lane);                             // in flight across the wait and the staging below
+    cp_pdl_wait();
     if (NORM) {
         float ss[CP_MAX_S] = {0.f, 0.f};
         for (int i = tid; i < K; i += NT)
@@ -112,38 +145,24 @@ cp_gemv_kernel(const float* __restrict__ W, const float* __restrict__ x, int S, 
         for (int i = tid; i < S * K; i += NT) xs[i] = x[i];
     }
     __syncthreads();
-    constexpr int RPB = CP_GEMV_WARPS / KSPLIT;        // output rows per block
-    const int n = blockIdx.x * RPB + warp / KSPLIT, ks = warp % KSPLIT;
-    const int K4 = K >> 2, seg = (K4 + KSPLIT - 1) / KSPLIT;
-    const int k0 = ks * seg, k1 = min(K4, k0 + seg);
     float a0[CP_MAX_S] = {0.f, 0.f}, a1[CP_MAX_S] = {0.f, 0.f};
-    if (n < N) {
-        const float4* w0 = reinterpret_cast<const float4*>(W + (size_t)n * K);
-        const float4* w1 = reinterpret_cast<const float4*>(W + (size_t)(MODE == CP_SWIGLU ? N + n : n) * K);
-        // four (SwiGLU: eight) independent 128-bit loads per lane are issued before the first FMA needs one; rows past
-        // the segment load nothing and multiply zeros (branch-free)
-        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int kb = k0 + lane; kb < k1; kb += 128) {
-            float4 wv[4], uv[4];
+    for (int kb = k0 + lane; kb < k1; kb += 32 * U) {
+        float4 cw[U], cu[U];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int k4 = kb + 32 * u;
-                wv[u] = k4 < k1 ? __ldcs(w0 + k4) : z4;      // streamed once: evict-first keeps the L2 for activations
-                uv[u] = (MODE == CP_SWIGLU && k4 < k1) ? __ldcs(w1 + k4) : z4;
-            }
+        for (int u = 0; u < U; ++u) { cw[u] = wv[u]; cu[u] = uv[u]; }
+        if (kb + 32 * U < k1) load_batch(kb + 32 * U);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int k4 = min(kb + 32 * u, K4 - 1);
+        for (int u = 0; u < U; ++u) {
+            const int k4 = min(kb + 32 * u, K4 - 1);
 #pragma unroll
-                for (int s = 0; s < CP_MAX_S; ++s) {
-                    if (s < S) {
-                        const float4 xv = *reinterpret_cast<const float4*>(xs + (size_t)s * K + 4 * k4);
-                        a0[s] = fmaf(wv[u].x, xv.x, a0[s]); a0[s] = fmaf(wv[u].y, xv.y, a0[s]);
-                        a0[s] = fmaf(wv[u].z, xv.z, a0[s]); a0[s] = fmaf(wv[u].w, xv.w, a0[s]);
-                        if (MODE == CP_SWIGLU) {
-                            a1[s] = fmaf(uv[u].x, xv.x, a1[s]); a1[s] = fmaf(uv[u].y, xv.y, a1[s]);
-                            a1[s] = fmaf(uv[u].z, xv.z, a1[s]); a1[s] = fmaf(uv[u].w, xv.w, a1[s]);
-                        }
+            for (int s = 0; s < CP_MAX_S; ++s) {
+                if (s < S) {
+                    const float4 xv = *reinterpret_cast<const float4*>(xs + (size_t)s * K + 4 * k4);
+                    a0[s] = fmaf(cw[u].x, xv.x, a0[s]); a0[s] = fmaf(cw[u].y, xv.y, a0[s]);
+                    a0[s] = fmaf(cw[u].z, xv.z, a0[s]); a0[s] = fmaf(cw[u].w, xv.w, a0[s]);
+                    if (MODE == CP_SWIGLU) {
+                        a1[s] = fmaf(cu[u].x, xv.x, a1[s]); a1[s] = fmaf(cu[u].y, xv.y, a1[s]);
+                        a1[s] = fmaf(cu[u].z, xv.z, a1[s]); a1[s] = fmaf(cu[u].w, xv.w, a1[s]);
                     }
                 }
             }
@@ -201,6 +220,8 @@ cp_attn_kernel(const float* __restrict__ qkv, int S, int pos0, int heads, int kv
     const int rep = heads / kv_heads, g = h / rep;
     const int qd = heads * hd, kvd = kv_heads * hd, ld = qd + 2 * kvd;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    cp_pdl_launch_dependents();
+    cp_pdl_wait();
     auto wsum = [](float v) { for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); return v; };
     auto ld4 = [&](const float* p) { return live ? *reinterpret_cast<const float4*>(p + 4 * lane) : zero4; };
     auto norm_rope = [&](float4 v, const float* w, int pos) -> float4 {
@@ -293,6 +314,8 @@ cp_sample_kernel(const float* __restrict__ logits, int vocab, const CpSamplePara
     __shared__ int cand_i[64];
     __shared__ int chosen;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    cp_pdl_launch_dependents();
+    cp_pdl_wait();
     unsigned key[CP_VPT];
 #pragma unroll
     for (int r = 0; r < CP_VPT; ++r) {
@@ -432,16 +455,29 @@ const std::vector<float>* cp_raw(CpEngine* E, const std::string& name, size_t n)
     return &it->second;
 }
 
+// every kernel of the path is launched with the programmatic-stream-serialization attribute (see cp_pdl_wait)
+template <typename... Exp, typename... Act>
+void cp_launch(void (*kernel)(Exp...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Act&&... args) {
+    static const bool pdl = !(getenv("CP_NO_PDL") && atoi(getenv("CP_NO_PDL")));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, std::forward<Act>(args)...);      // errors surface through cudaGetLastError
+}
+
 template <int MODE, bool NORM>
 void cp_gemv(cudaStream_t st, const float* W, const float* x, int S, int N, int K, float* out, const float* res,
              const float* ln_w, float eps) {
     const size_t smem = (size_t)S * K * sizeof(float);
     if (N >= 3072) {
         constexpr int RPB = CP_GEMV_WARPS / 2;
-        cp_gemv_kernel<MODE, 2, NORM><<<(N + RPB - 1) / RPB, CP_GEMV_WARPS * 32, smem, st>>>(W, x, S, N, K, out, res, ln_w, eps);
+        cp_launch(cp_gemv_kernel<MODE, 2, NORM>, dim3((N + RPB - 1) / RPB), dim3(CP_GEMV_WARPS * 32), smem, st, W, x, S, N, K, out, res, ln_w, eps);
     } else {
         constexpr int RPB = CP_GEMV_WARPS / 4;
-        cp_gemv_kernel<MODE, 4, NORM><<<(N + RPB - 1) / RPB, CP_GEMV_WARPS * 32, smem, st>>>(W, x, S, N, K, out, res, ln_w, eps);
+        cp_launch(cp_gemv_kernel<MODE, 4, NORM>, dim3((N + RPB - 1) / RPB), dim3(CP_GEMV_WARPS * 32), smem, st, W, x, S, N, K, out, res, ln_w, eps);
     }
 }
 
@@ -456,9 +492,8 @@ int cp_forward(CpEngine* E, int S, int pos0, cudaStream_t st) {
     for (int l = 0; l < c.layers; ++l) {
         auto& Ly = E->L[l];
         cp_gemv<CP_PLAIN, true>(st, Ly.wqkv, E->d_x, S, Q + 2 * KV, H, E->d_qkv, nullptr, Ly.ln1, eps);
-        cp_attn_kernel<<<dim3(c.heads, S), 128, 0, st>>>(E->d_qkv, S, pos0, c.heads, c.kv_heads, hd, c.max_positions, Ly.qn, Ly.kn,
-                                                         E->rope_cos, E->rope_sin, E->kc + l * layer_cache, E->vc + l * layer_cache,
-                                                         eps, E->d_att);
+        cp_launch(cp_attn_kernel, dim3(c.heads, S), dim3(128), 0, st, E->d_qkv, S, pos0, c.heads, c.kv_heads, hd, c.max_positions, Ly.qn,
+                  Ly.kn, E->rope_cos, E->rope_sin, E->kc + l * layer_cache, E->vc + l * layer_cache, eps, E->d_att);
         cp_gemv<CP_RESIDUAL, false>(st, Ly.wo, E->d_att, S, H, Q, E->d_x, E->d_x, nullptr, 0.f);
         cp_gemv<CP_SWIGLU, true>(st, Ly.wgu, E->d_x, S, I, H, E->d_act, nullptr, Ly.ln2, eps);
         cp_gemv<CP_RESIDUAL, false>(st, Ly.wd, E->d_act, S, H, I, E->d_x, E->d_x, nullptr, 0.f);
@@ -492,8 +527,8 @@ int cp_build_graph(CpEngine* E) {
         for (int g = 0; g < c.groups; ++g) {
             cp_head(E, g, 0, st);
             const bool more = g + 1 < c.groups;
-            cp_sample_kernel<<<1, 256, 0, st>>>(E->d_logits, c.vocab, E->d_sp, g, more ? E->emb[g] : nullptr, H, E->d_codes,
-                                                more ? E->d_x : nullptr);
+            cp_launch(cp_sample_kernel, dim3(1), dim3(256), 0, st, E->d_logits, c.vocab, E->d_sp, g, more ? E->emb[g] : nullptr, H,
+                      E->d_codes, more ? E->d_x : nullptr);
             E->launches += 1;
             if (more && (rc = cp_forward(E, 1, g + 2, st))) break;
         }
@@ -647,7 +682,7 @@ int cp_step(void* h, const float* hidden_in, int S, int position, float* hidden_
     const int H = E->cfg.hidden;
     CPK(cudaMemcpyAsync(E->d_x, hidden_in, (size_t)S * H * 4, cudaMemcpyHostToDevice, E->stream));
     if (int r = cp_forward(E, S, position, E->stream)) return r;
-    cp_rmsnorm_kernel<<<S, 256, 0, E->stream>>>(E->d_x, E->fnorm, E->d_out, H, (float)E->cfg.rms_eps);
+    cp_launch(cp_rmsnorm_kernel, dim3(S), dim3(256), 0, E->stream, E->d_x, E->fnorm, E->d_out, H, (float)E->cfg.rms_eps);
     E->launches += 1;
     CPK(cudaGetLastError());
     CPK(cudaMemcpyAsync(hidden_out, E->d_out, (size_t)S * H * 4, cudaMemcpyDeviceToHost, E->stream));
