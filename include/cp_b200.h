@@ -55,12 +55,19 @@ int cp_logits(void* h, int group, float* logits_out);
  * Replaces: CodePredictorServer.predict(hidden_state, code_0_embed, temperature, top_k)   code_predictor_server.py:94-140
  *   hidden_state, code0_embed : float32 [hidden]
  *   codes_out : int32 [groups]
- * One CUDA-graph launch: 2 prefill positions, then per group lm_head -> top-k sample -> embedding -> decode step,
+ * One launch from the host: 2 prefill positions, then per group lm_head -> top-k sample -> embedding -> decode step,
  * the sampler on the device (top_k <= 64).  top_k = 1 is greedy decoding and is deterministic; for top_k > 1 the
  * draw comes from a counter-based generator keyed by `seed` and the group index: same distribution as the reference's
  * np.random.choice over the renormalised top-k, a different random stream.                                     */
 int cp_predict(void* h, const float* hidden_state, const float* code0_embed, float temperature, int top_k,
                unsigned long long seed, int* codes_out);
+
+/* cp_predict runs as a CUDA graph of ~430 launches chained by programmatic dependent launch (default), or -- opt-in,
+ * when the shape fits the device -- as ONE persistent cooperative kernel (432 phases separated by grid barriers,
+ * next-phase weights loaded under each barrier).  Same results, same speed on a B200; the graph leaves
+ * SMs to other streams.  cp_set_option(h, "predict", "graph" | "persistent") selects; cp_predict_path reports.  */
+int cp_set_option(void* h, const char* key, const char* value);
+const char* cp_predict_path(void* h);
 
 int cp_hidden_size(void* h);
 int cp_num_groups(void* h);

@@ -30,6 +30,8 @@ SIGNATURES = {
     "cp_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "cp_logits": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "cp_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_ulonglong, C.c_void_p]),
+    "cp_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
+    "cp_predict_path": (C.c_char_p, [C.c_void_p]),
     "cp_hidden_size": (C.c_int, [C.c_void_p]),
     "cp_num_groups": (C.c_int, [C.c_void_p]),
     "cp_vocab_size": (C.c_int, [C.c_void_p]),
@@ -197,6 +199,13 @@ class CodePredictor:
     @property
     def cache_len(self) -> int:
         return int(self.lib.cp_cache_len(self._h))
+
+    def set_option(self, key: str, value: str):
+        self._ck(self.lib.cp_set_option(self._h, key.encode(), value.encode()))
+
+    @property
+    def predict_path(self) -> str:
+        return self.lib.cp_predict_path(self._h).decode()
 
     def reset(self):
         self._ck(self.lib.cp_reset(self._h))

@@ -83,10 +83,15 @@ def test_batch_prefill_matches_sequential(cpm):
     assert float(np.abs(la - cp.logits(0)).max()) < 1e-5
 
 
+@pytest.mark.parametrize("path", ["persistent", "graph"])
 @pytest.mark.parametrize("tiny", [True, False])
-def test_greedy_frame_equals_the_oracle(cpm, tiny):
-    """cp_predict with top_k = 1 (one graph launch) == the oracle's predict loop with argmax, over several frames."""
+def test_greedy_frame_equals_the_oracle(cpm, tiny, path):
+    """cp_predict with top_k = 1 == the oracle's predict loop with argmax, over several frames, through both
+    implementations of the frame: the CUDA graph of per-phase kernels (default) and the persistent cooperative kernel."""
     ocfg, cfg, w, W, cp = _pair(cpm, tiny=tiny)
+    assert cp.predict_path == "graph"                    # the default; the persistent kernel is opt-in
+    cp.set_option("predict", path)
+    assert cp.predict_path == path
     rng = np.random.default_rng(5)
     for frame in range(6 if tiny else 3):
         h = rng.standard_normal(cfg.hidden).astype(np.float32)
@@ -99,6 +104,7 @@ def test_greedy_frame_equals_the_oracle(cpm, tiny):
         assert list(got) == want, frame
         # the last step's logits through level 1 agree with the oracle's last logits
         assert float(np.abs(cp.logits(cfg.groups - 1) - logits[-1]).max()) < TOL
+    assert cp.launches < 100 if path == "persistent" else cp.launches > 100
 
 
 def test_frames_are_independent_and_deterministic(cpm):
