@@ -136,8 +136,12 @@ def code_predictor_leg(device: int, frames: int = 60):
     w = cpm.init_weights(cfg, 0)
     cp = cpm.CodePredictor(cfg, w, device=device)
     rng = np.random.default_rng(11)
-    hs = rng.standard_normal((frames + 5, cfg.hidden)).astype(np.float32)
-    es = rng.standard_normal((frames + 5, cfg.hidden)).astype(np.float32)
+    hs = rng.standard_normal((frames + 16, cfg.hidden)).astype(np.float32)
+    es = rng.standard_normal((frames + 16, cfg.hidden)).astype(np.float32)
+
+    def frame_bytes_fn():
+        layer_bytes = sum(int(np.prod(sh)) for k, sh in cpm.weight_shapes(cfg).items() if k.startswith("layer_")) * 4
+        return (cfg.groups + 1) * layer_bytes + cfg.groups * cfg.vocab * cfg.hidden * 4
     for i in range(5):
         cp.predict(hs[i], es[i], 0.1, 50, seed=i)
     l0 = cp.launches
@@ -166,6 +170,24 @@ def code_predictor_leg(device: int, frames: int = 60):
     except Exception as e:
         persistent = {"error": repr(e)}
     cp.set_option("predict", path)
+    # B independent streams per launch (cp_predict_batch): the weights are streamed once for all of them
+    batched = {}
+    try:
+        for B in (2, 4, 8):
+            sd = np.arange(B, dtype=np.uint64)
+            for i in range(3):
+                cp.predict_batch(hs[i:i + B], es[i:i + B], 0.1, 50, seeds=sd)
+            lb = []
+            for i in range(5, 5 + max(10, frames // 3)):
+                t = time.perf_counter()
+                cp.predict_batch(hs[i:i + B], es[i:i + B], 0.1, 50, seeds=sd)
+                lb.append((time.perf_counter() - t) * 1e3)
+            lb.sort()
+            ms = lb[len(lb) // 2]
+            batched[str(B)] = {"ms_per_launch_p50": ms, "frames_per_s": B * 1e3 / ms,
+                               "weight_stream_gbs": frame_bytes_fn() / (ms / 1e3) / 1e9}
+    except Exception as e:
+        batched["error"] = repr(e)
     # level 1: 16 steps + 15 logits round trips per frame, greedy on the host
     t = time.perf_counter()
     n1 = 10
@@ -178,9 +200,7 @@ def code_predictor_leg(device: int, frames: int = 60):
             if g + 1 < cfg.groups:
                 cp.step(w[f"codec_emb_{g}"][tok][None], g + 2)
     ms_l1 = (time.perf_counter() - t) * 1e3 / n1
-    layer_bytes = sum(int(np.prod(sh)) for k, sh in cpm.weight_shapes(cfg).items() if k.startswith("layer_")) * 4
-    head_bytes = cfg.vocab * cfg.hidden * 4
-    frame_bytes = (cfg.groups + 1) * layer_bytes + cfg.groups * head_bytes
+    frame_bytes = frame_bytes_fn()
     peaks, peak_src = _peaks()
     hbm = float(peaks.get("hbm_gbs_sustained", peaks.get("hbm_gbs", 6400.0)))
     p50 = lat[len(lat) // 2]
@@ -190,6 +210,7 @@ def code_predictor_leg(device: int, frames: int = 60):
            "frame_ms_p50": p50, "frame_ms_p95": lat[int(0.95 * len(lat)) - 1], "frames_per_s": 1e3 / p50,
            "realtime_factor_at_12.5_frames_per_s": (1e3 / p50) / 12.5,
            "predict_path": path, "gpu_launches_per_frame": int(per_frame_launches), "persistent_kernel": persistent,
+           "batched_streams": batched,
            "level1_frame_ms": ms_l1,
            "dtype": "f32",
            "roofline": {"bound": "hbm", "unit": "GB/s", "achieved": frame_bytes / (p50 / 1e3) / 1e9, "peak": hbm,

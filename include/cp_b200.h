@@ -62,6 +62,15 @@ int cp_logits(void* h, int group, float* logits_out);
 int cp_predict(void* h, const float* hidden_state, const float* code0_embed, float temperature, int top_k,
                unsigned long long seed, int* codes_out);
 
+/* No counterpart in the reference (it serves one stream): the frames of B <= cp_max_batch() independent streams in one
+ * launch.  Every kernel carries B input vectors, so the weights -- all of this path's memory traffic -- are streamed once
+ * for all B; each stream has its own KV cache and its own seed.  Row b of every array belongs to stream b; results equal
+ * B calls of cp_predict.
+ *   hidden_states, code0_embeds : float32 [B][hidden];  seeds : [B];  codes_out : int32 [B][groups]            */
+int cp_max_batch(void* h);
+int cp_predict_batch(void* h, int B, const float* hidden_states, const float* code0_embeds, float temperature, int top_k,
+                     const unsigned long long* seeds, int* codes_out);
+
 /* cp_predict runs as a CUDA graph of ~430 launches chained by programmatic dependent launch (default), or -- opt-in,
  * when the shape fits the device -- as ONE persistent cooperative kernel (432 phases separated by grid barriers,
  * next-phase weights loaded under each barrier).  Same results, same speed on a B200; the graph leaves

@@ -30,6 +30,8 @@ SIGNATURES = {
     "cp_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "cp_logits": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "cp_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_ulonglong, C.c_void_p]),
+    "cp_max_batch": (C.c_int, [C.c_void_p]),
+    "cp_predict_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p]),
     "cp_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
     "cp_predict_path": (C.c_char_p, [C.c_void_p]),
     "cp_hidden_size": (C.c_int, [C.c_void_p]),
@@ -199,6 +201,26 @@ class CodePredictor:
     @property
     def cache_len(self) -> int:
         return int(self.lib.cp_cache_len(self._h))
+
+    @property
+    def max_batch(self) -> int:
+        return int(self.lib.cp_max_batch(self._h))
+
+    def predict_batch(self, hidden_states, code0_embeds, temperature: float = 0.1, top_k: int = 50, seeds=None) -> np.ndarray:
+        """The frames of B independent streams in one launch (``cp_predict_batch``): [B, H] x 2 -> codes [B, groups]."""
+        H = self.cfg.hidden
+        h = np.ascontiguousarray(np.asarray(hidden_states, dtype=np.float32).reshape(-1, H))
+        e = np.ascontiguousarray(np.asarray(code0_embeds, dtype=np.float32).reshape(-1, H))
+        B = h.shape[0]
+        if e.shape[0] != B:
+            raise CodePredictorError(CP_E_INVALID, "hidden_states and code0_embeds need the same number of rows")
+        sd = np.ascontiguousarray(np.arange(B) if seeds is None else seeds, dtype=np.uint64)
+        if sd.size != B:
+            raise CodePredictorError(CP_E_INVALID, "one seed per stream")
+        codes = np.empty((B, self.cfg.groups), dtype=np.int32)
+        self._ck(self.lib.cp_predict_batch(self._h, B, h.ctypes.data, e.ctypes.data, float(temperature), int(top_k),
+                                           sd.ctypes.data, codes.ctypes.data))
+        return codes
 
     def set_option(self, key: str, value: str):
         self._ck(self.lib.cp_set_option(self._h, key.encode(), value.encode()))

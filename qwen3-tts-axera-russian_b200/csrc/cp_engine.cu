@@ -59,6 +59,7 @@ __device__ __forceinline__ void cp_pdl_launch_dependents() { asm volatile("gridd
 __device__ __forceinline__ void cp_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 constexpr int CP_MAX_S = 2;          // tokens per step call: 1, or the reference's 2-token batch prefill
+constexpr int CP_MAX_B = 8;          // independent streams per cp_predict_batch
 
 // ------------------------------------------------------------------------------------------------------------
 // kernels
@@ -93,14 +94,16 @@ __global__ void cp_rmsnorm_kernel(const float* __restrict__ x, const float* __re
 //   MODE 2: out[s][n] = silu(W[n] . x[s]) * (W[N + n] . x[s])    (SwiGLU: gate rows, then up rows)
 enum { CP_PLAIN = 0, CP_RESIDUAL = 1, CP_SWIGLU = 2 };
 constexpr int CP_GEMV_WARPS = 16;
-template <int MODE, int KSPLIT, bool NORM>
-__global__ void __launch_bounds__(CP_GEMV_WARPS * 32, 2)
+// SM = the most input vectors a launch may carry: 2 (a decode step or the 2-token prefill) or CP_MAX_B (one token of each of
+// up to 8 independent streams: the weights are streamed once for all of them)
+template <int MODE, int KSPLIT, bool NORM, int SM>
+__global__ void __launch_bounds__(CP_GEMV_WARPS * 32, SM > 2 ? 1 : 2)
 cp_gemv_kernel(const float* __restrict__ W, const float* __restrict__ x, int S, int N, int K, float* __restrict__ out,
                const float* res, const float* __restrict__ ln_w, float eps) {
     extern __shared__ float xs[];                      // [S][K]
     constexpr int NT = CP_GEMV_WARPS * 32;
-    __shared__ float red[CP_MAX_S][CP_GEMV_WARPS];
-    __shared__ float part[CP_GEMV_WARPS][2 * CP_MAX_S];
+    __shared__ float red[SM][CP_GEMV_WARPS];
+    __shared__ float part[CP_GEMV_WARPS][2 * SM];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     cp_pdl_launch_dependents();
     constexpr int RPB = CP_GEMV_WARPS / KSPLIT;        // output rows per block
@@ -125,11 +128,15 @@ cp_gemv_kernel(const float* __restrict__ W, const float* __restrict__ x, int S, 
     load_batch(k0 + lane);                             // in flight across the wait and the staging below
     cp_pdl_wait();
     if (NORM) {
-        float ss[CP_MAX_S] = {0.f, 0.f};
-        for (int i = tid; i < K; i += NT)
-            for (int s = 0; s < S; ++s) { const float v = x[(size_t)s * K + i]; xs[s * K + i] = v; ss[s] = fmaf(v, v, ss[s]); }
+        float ss[SM] = {};
+        for (int i = tid; i < (K >> 2); i += NT)
+            for (int s = 0; s < S; ++s) {
+                const float4 v = reinterpret_cast<const float4*>(x + (size_t)s * K)[i];
+                reinterpret_cast<float4*>(xs + (size_t)s * K)[i] = v;
+                ss[s] = fmaf(v.x, v.x, ss[s]); ss[s] = fmaf(v.y, v.y, ss[s]); ss[s] = fmaf(v.z, v.z, ss[s]); ss[s] = fmaf(v.w, v.w, ss[s]);
+            }
 #pragma unroll
-        for (int s = 0; s < CP_MAX_S; ++s) {
+        for (int s = 0; s < SM; ++s) {
             for (int o = 16; o; o >>= 1) ss[s] += __shfl_xor_sync(0xffffffffu, ss[s], o);
             if (lane == 0) red[s][warp] = ss[s];
         }
@@ -139,13 +146,18 @@ cp_gemv_kernel(const float* __restrict__ W, const float* __restrict__ x, int S, 
 #pragma unroll
             for (int w = 0; w < CP_GEMV_WARPS; ++w) tot += red[s][w];
             const float inv = rsqrtf(tot / (float)K + eps);
-            for (int i = tid; i < K; i += NT) xs[s * K + i] = ln_w[i] * (xs[s * K + i] * inv);
+            for (int i = tid; i < (K >> 2); i += NT) {
+                const float4 g = reinterpret_cast<const float4*>(ln_w)[i];
+                float4 v = reinterpret_cast<float4*>(xs + (size_t)s * K)[i];
+                v = make_float4(g.x * (v.x * inv), g.y * (v.y * inv), g.z * (v.z * inv), g.w * (v.w * inv));
+                reinterpret_cast<float4*>(xs + (size_t)s * K)[i] = v;
+            }
         }
     } else {
-        for (int i = tid; i < S * K; i += NT) xs[i] = x[i];
+        for (int i = tid; i < ((S * K) >> 2); i += NT) reinterpret_cast<float4*>(xs)[i] = reinterpret_cast<const float4*>(x)[i];
     }
     __syncthreads();
-    float a0[CP_MAX_S] = {0.f, 0.f}, a1[CP_MAX_S] = {0.f, 0.f};
+    float a0[SM] = {}, a1[SM] = {};
     for (int kb = k0 + lane; kb < k1; kb += 32 * U) {
         float4 cw[U], cu[U];
 #pragma unroll
@@ -155,7 +167,7 @@ cp_gemv_kernel(const float* __restrict__ W, const float* __restrict__ x, int S, 
         for (int u = 0; u < U; ++u) {
             const int k4 = min(kb + 32 * u, K4 - 1);
 #pragma unroll
-            for (int s = 0; s < CP_MAX_S; ++s) {
+            for (int s = 0; s < SM; ++s) {
                 if (s < S) {
                     const float4 xv = *reinterpret_cast<const float4*>(xs + (size_t)s * K + 4 * k4);
                     a0[s] = fmaf(cw[u].x, xv.x, a0[s]); a0[s] = fmaf(cw[u].y, xv.y, a0[s]);
@@ -169,7 +181,7 @@ cp_gemv_kernel(const float* __restrict__ W, const float* __restrict__ x, int S, 
         }
     }
 #pragma unroll
-    for (int s = 0; s < CP_MAX_S; ++s) {
+    for (int s = 0; s < SM; ++s) {
         for (int o = 16; o; o >>= 1) {
             a0[s] += __shfl_xor_sync(0xffffffffu, a0[s], o);
             if (MODE == CP_SWIGLU) a1[s] += __shfl_xor_sync(0xffffffffu, a1[s], o);
@@ -178,12 +190,12 @@ cp_gemv_kernel(const float* __restrict__ W, const float* __restrict__ x, int S, 
     if (KSPLIT > 1) {
         if (lane == 0) {
 #pragma unroll
-            for (int s = 0; s < CP_MAX_S; ++s) { part[warp][2 * s] = a0[s]; part[warp][2 * s + 1] = a1[s]; }
+            for (int s = 0; s < SM; ++s) { part[warp][2 * s] = a0[s]; part[warp][2 * s + 1] = a1[s]; }
         }
         __syncthreads();
         if (ks == 0 && lane == 0) {
 #pragma unroll
-            for (int s = 0; s < CP_MAX_S; ++s) {
+            for (int s = 0; s < SM; ++s) {
                 a0[s] = 0.f; a1[s] = 0.f;
                 for (int q = 0; q < KSPLIT; ++q) { a0[s] += part[warp + q][2 * s]; a1[s] += part[warp + q][2 * s + 1]; }
             }
@@ -211,15 +223,21 @@ __global__ void __launch_bounds__(128)
 cp_attn_kernel(const float* __restrict__ qkv, int S, int pos0, int heads, int kv_heads, int hd, int max_pos,
                const float* __restrict__ qn, const float* __restrict__ kn, const float* __restrict__ rope_cos,
                const float* __restrict__ rope_sin, float* __restrict__ kc, float* __restrict__ vc, float eps,
-               float* __restrict__ att) {
+               float* __restrict__ att, long long stream_stride) {
     __shared__ float sm_m[4], sm_l[4];
     __shared__ float4 sm_o[4][32];
-    const int h = blockIdx.x, s = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int s = blockIdx.y;
     const int live_lanes = hd >> 2, half = live_lanes >> 1, H2 = hd >> 1;
     const bool live = lane < live_lanes;
     const int rep = heads / kv_heads, g = h / rep;
     const int qd = heads * hd, kvd = kv_heads * hd, ld = qd + 2 * kvd;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (stream_stride) {
+        // batch mode (cp_predict_batch): row s is the one new token of independent stream s, with its own cache
+        qkv += (size_t)s * ld; att += (size_t)s * qd; kc += (size_t)s * stream_stride; vc += (size_t)s * stream_stride;
+        s = 0;
+    }
     cp_pdl_launch_dependents();
     cp_pdl_wait();
     auto wsum = [](float v) { for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); return v; };
@@ -306,7 +324,7 @@ __device__ __forceinline__ unsigned cp_ordered(float v) {
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 __global__ void __launch_bounds__(256)
-cp_sample_kernel(const float* __restrict__ logits, int vocab, const CpSampleParams* __restrict__ sp, int group,
+cp_sample_kernel(const float* __restrict__ logits, int vocab, const CpSampleParams* __restrict__ sp, int group, int groups,
                  const float* __restrict__ emb_table, int H, int* __restrict__ codes, float* __restrict__ out_embed) {
     __shared__ int cnt[34];
     __shared__ int wtot[2][8];
@@ -314,6 +332,11 @@ cp_sample_kernel(const float* __restrict__ logits, int vocab, const CpSamplePara
     __shared__ int cand_i[64];
     __shared__ int chosen;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    {                                                  // block b = stream b
+        const int b = blockIdx.x;
+        logits += (size_t)b * vocab; sp += b; codes += (size_t)b * groups;
+        if (out_embed) out_embed += (size_t)b * H;
+    }
     cp_pdl_launch_dependents();
     cp_pdl_wait();
     unsigned key[CP_VPT];
@@ -919,7 +942,7 @@ struct CpEngine {
     float* fnorm = nullptr;
     std::vector<float*> emb, head;
     float *rope_cos = nullptr, *rope_sin = nullptr;
-    float *kc = nullptr, *vc = nullptr;              // [layers][kv_heads][max_pos][hd]
+    float *kc = nullptr, *vc = nullptr;              // [stream][layers][kv_heads][max_pos][hd]; stream 0 is level 1's
     int cache_len = 0;                               // positions filled
     int last_S = 1;                                  // tokens of the last step (cp_logits reads the last one)
     long long graph_kernels = 0;
@@ -928,7 +951,9 @@ struct CpEngine {
     float *d_in_hidden = nullptr, *d_in_embed = nullptr;
     int* d_codes = nullptr;
     CpSampleParams* d_sp = nullptr;
-    cudaGraphExec_t graph = nullptr;
+    cudaGraphExec_t graph = nullptr;                 // the frame for one stream
+    std::map<int, cudaGraphExec_t> batch_graphs;     // ... and for B streams at once (built on first use)
+    std::map<int, long long> batch_graph_kernels;
     long long launches = 0;
     // persistent frame kernel
     bool persistent = false;                         // cp_predict path: one cooperative kernel (default when it fits) or the graph
@@ -939,6 +964,7 @@ struct CpEngine {
 
     ~CpEngine() {
         if (graph) cudaGraphExecDestroy(graph);
+        for (auto& kv : batch_graphs) cudaGraphExecDestroy(kv.second);
         for (void* p : owned) cudaFree(p);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -994,23 +1020,34 @@ void cp_launch(void (*kernel)(Exp...), dim3 grid, dim3 block, size_t smem, cudaS
     cudaLaunchKernelEx(&cfg, kernel, std::forward<Act>(args)...);      // errors surface through cudaGetLastError
 }
 
+template <int MODE, int KSPLIT, bool NORM, int SM>
+void cp_gemv_inst(cudaStream_t st, const float* W, const float* x, int S, int N, int K, float* out, const float* res,
+                  const float* ln_w, float eps) {
+    constexpr int RPB = CP_GEMV_WARPS / KSPLIT;
+    const size_t smem = (size_t)S * K * sizeof(float);
+    // dynamic + ~2 KB static must stay under the 48 KB default; only the batched form stages more (8 x 3072 floats = 96 KB)
+    if (smem > 40 * 1024)
+        cudaFuncSetAttribute(cp_gemv_kernel<MODE, KSPLIT, NORM, SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cp_launch(cp_gemv_kernel<MODE, KSPLIT, NORM, SM>, dim3((N + RPB - 1) / RPB), dim3(CP_GEMV_WARPS * 32), smem, st, W, x, S, N, K, out, res,
+              ln_w, eps);
+}
 template <int MODE, bool NORM>
 void cp_gemv(cudaStream_t st, const float* W, const float* x, int S, int N, int K, float* out, const float* res,
              const float* ln_w, float eps) {
-    const size_t smem = (size_t)S * K * sizeof(float);
-    if (N >= 3072) {
-        constexpr int RPB = CP_GEMV_WARPS / 2;
-        cp_launch(cp_gemv_kernel<MODE, 2, NORM>, dim3((N + RPB - 1) / RPB), dim3(CP_GEMV_WARPS * 32), smem, st, W, x, S, N, K, out, res, ln_w, eps);
+    if (S <= CP_MAX_S) {
+        if (N >= 3072) cp_gemv_inst<MODE, 2, NORM, CP_MAX_S>(st, W, x, S, N, K, out, res, ln_w, eps);
+        else cp_gemv_inst<MODE, 4, NORM, CP_MAX_S>(st, W, x, S, N, K, out, res, ln_w, eps);
     } else {
-        constexpr int RPB = CP_GEMV_WARPS / 4;
-        cp_launch(cp_gemv_kernel<MODE, 4, NORM>, dim3((N + RPB - 1) / RPB), dim3(CP_GEMV_WARPS * 32), smem, st, W, x, S, N, K, out, res, ln_w, eps);
+        // batched streams: every block stages S x K inputs, so blocks are taller (16 or 8 rows) -- ~128-256 of them
+        if (N >= 2048) cp_gemv_inst<MODE, 1, NORM, CP_MAX_B>(st, W, x, S, N, K, out, res, ln_w, eps);
+        else cp_gemv_inst<MODE, 2, NORM, CP_MAX_B>(st, W, x, S, N, K, out, res, ln_w, eps);
     }
 }
 
 // one transformer pass over the S tokens in d_x (positions pos0 ..): the residual stream stays in d_x (un-normed; the
 // final norm is the prologue of the lm_head GEMV, or cp_rmsnorm_kernel for level 1's hidden_out), caches grown.
 // Five launches per layer.
-int cp_forward(CpEngine* E, int S, int pos0, cudaStream_t st) {
+int cp_forward(CpEngine* E, int S, int pos0, cudaStream_t st, bool batch = false) {
     const CpCfg& c = E->cfg;
     const int H = c.hidden, Q = c.qdim(), KV = c.kvdim(), I = c.inter, hd = c.head_dim;
     const float eps = (float)c.rms_eps;
@@ -1019,7 +1056,8 @@ int cp_forward(CpEngine* E, int S, int pos0, cudaStream_t st) {
         auto& Ly = E->L[l];
         cp_gemv<CP_PLAIN, true>(st, Ly.wqkv, E->d_x, S, Q + 2 * KV, H, E->d_qkv, nullptr, Ly.ln1, eps);
         cp_launch(cp_attn_kernel, dim3(c.heads, S), dim3(128), 0, st, E->d_qkv, S, pos0, c.heads, c.kv_heads, hd, c.max_positions, Ly.qn,
-                  Ly.kn, E->rope_cos, E->rope_sin, E->kc + l * layer_cache, E->vc + l * layer_cache, eps, E->d_att);
+                  Ly.kn, E->rope_cos, E->rope_sin, E->kc + l * layer_cache, E->vc + l * layer_cache, eps, E->d_att,
+                  batch ? (long long)(c.layers * layer_cache) : 0ll);
         cp_gemv<CP_RESIDUAL, false>(st, Ly.wo, E->d_att, S, H, Q, E->d_x, E->d_x, nullptr, 0.f);
         cp_gemv<CP_SWIGLU, true>(st, Ly.wgu, E->d_x, S, I, H, E->d_act, nullptr, Ly.ln2, eps);
         cp_gemv<CP_RESIDUAL, false>(st, Ly.wd, E->d_act, S, H, I, E->d_x, E->d_x, nullptr, 0.f);
@@ -1037,7 +1075,9 @@ void cp_head(CpEngine* E, int group, int row, cudaStream_t st) {
     E->launches += 1;
 }
 
-int cp_build_graph(CpEngine* E) {
+// the frame of B independent streams as one graph: every kernel carries B input vectors, so the weights are streamed
+// once for all of them
+int cp_build_graph(CpEngine* E, int B, cudaGraphExec_t* exec, long long* kernels) {
     // predict(): position 0 = hidden state, position 1 = embedding of code_0, then 15 x (lm_head, sample + embed, step)
     const CpCfg& c = E->cfg;
     const int H = c.hidden;
@@ -1046,26 +1086,26 @@ int cp_build_graph(CpEngine* E) {
     int rc = CP_OK;
     const long long before = E->launches;
     do {
-        if (cudaMemcpyAsync(E->d_x, E->d_in_hidden, (size_t)H * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess) { rc = CP_E_CUDA; break; }
-        if ((rc = cp_forward(E, 1, 0, st))) break;
-        if (cudaMemcpyAsync(E->d_x, E->d_in_embed, (size_t)H * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess) { rc = CP_E_CUDA; break; }
-        if ((rc = cp_forward(E, 1, 1, st))) break;
+        if (cudaMemcpyAsync(E->d_x, E->d_in_hidden, (size_t)B * H * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess) { rc = CP_E_CUDA; break; }
+        if ((rc = cp_forward(E, B, 0, st, true))) break;
+        if (cudaMemcpyAsync(E->d_x, E->d_in_embed, (size_t)B * H * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess) { rc = CP_E_CUDA; break; }
+        if ((rc = cp_forward(E, B, 1, st, true))) break;
         for (int g = 0; g < c.groups; ++g) {
-            cp_head(E, g, 0, st);
+            cp_gemv<CP_PLAIN, true>(st, E->head[g], E->d_x, B, c.vocab, H, E->d_logits, nullptr, E->fnorm, (float)c.rms_eps);
             const bool more = g + 1 < c.groups;
-            cp_launch(cp_sample_kernel, dim3(1), dim3(256), 0, st, E->d_logits, c.vocab, E->d_sp, g, more ? E->emb[g] : nullptr, H,
+            cp_launch(cp_sample_kernel, dim3(B), dim3(256), 0, st, E->d_logits, c.vocab, E->d_sp, g, c.groups, more ? E->emb[g] : nullptr, H,
                       E->d_codes, more ? E->d_x : nullptr);
-            E->launches += 1;
-            if (more && (rc = cp_forward(E, 1, g + 2, st))) break;
+            E->launches += 2;
+            if (more && (rc = cp_forward(E, B, g + 2, st, true))) break;
         }
     } while (0);
-    E->graph_kernels = E->launches - before;
+    *kernels = E->launches - before;
     E->launches = before;
     cudaGraph_t graph = nullptr;
     const cudaError_t ce = cudaStreamEndCapture(st, &graph);
-    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (rc) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }     // leave no stale error behind
     if (ce != cudaSuccess || !graph) return cp_fail(E, CP_E_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(ce));
-    CPK(cudaGraphInstantiate(&E->graph, graph, 0));
+    CPK(cudaGraphInstantiate(exec, graph, 0));
     cudaGraphDestroy(graph);
     return CP_OK;
 }
@@ -1170,6 +1210,7 @@ void* cp_create(const char* cfg_json, int device) {
         if (c.heads % c.kv_heads || c.layers < 1 || c.groups < 1 || c.vocab < 1 || c.vocab > 4096) return bad("bad head / layer / vocabulary configuration");
         if (c.max_positions < c.groups + 2) return bad("max_positions must cover groups + 2 positions");
         if ((size_t)CP_MAX_S * std::max(c.inter, std::max(c.hidden, c.qdim())) * 4 > 48 * 1024) return bad("layer too wide for the shared-memory staged GEMV");
+        static_assert(CP_MAX_B >= CP_MAX_S, "activation buffers are sized for CP_MAX_B rows");
         int ndev = 0;
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return bad("no usable CUDA device (there is no CPU fallback)");
         E->device = device;
@@ -1245,18 +1286,20 @@ int cp_finalize(void* h) {
             CPREQ(E->rope_cos = cp_upload(E, cs.data(), cs.size())); CPREQ(E->rope_sin = cp_upload(E, sn.data(), sn.size()));
             CPK(cudaStreamSynchronize(E->stream));
         }
-        const size_t cache = (size_t)c.layers * c.kv_heads * c.max_positions * hd;
+        const size_t cache = (size_t)CP_MAX_B * c.layers * c.kv_heads * c.max_positions * hd;
         CPREQ(E->kc = cp_alloc<float>(E, cache)); CPREQ(E->vc = cp_alloc<float>(E, cache));
-        CPREQ(E->d_x = cp_alloc<float>(E, (size_t)CP_MAX_S * H)); CPREQ(E->d_xn = cp_alloc<float>(E, (size_t)CP_MAX_S * H));
-        CPREQ(E->d_qkv = cp_alloc<float>(E, (size_t)CP_MAX_S * (Q + 2 * KV))); CPREQ(E->d_att = cp_alloc<float>(E, (size_t)CP_MAX_S * Q));
-        CPREQ(E->d_act = cp_alloc<float>(E, (size_t)CP_MAX_S * I)); CPREQ(E->d_out = cp_alloc<float>(E, (size_t)CP_MAX_S * H));
-        CPREQ(E->d_logits = cp_alloc<float>(E, c.vocab)); CPREQ(E->d_in_hidden = cp_alloc<float>(E, H)); CPREQ(E->d_in_embed = cp_alloc<float>(E, H));
-        CPREQ(E->d_codes = cp_alloc<int>(E, c.groups)); CPREQ(E->d_sp = cp_alloc<CpSampleParams>(E, 1));
+        constexpr int T = CP_MAX_B;                      // rows of every activation buffer (>= CP_MAX_S)
+        CPREQ(E->d_x = cp_alloc<float>(E, (size_t)T * H)); CPREQ(E->d_xn = cp_alloc<float>(E, (size_t)T * H));
+        CPREQ(E->d_qkv = cp_alloc<float>(E, (size_t)T * (Q + 2 * KV))); CPREQ(E->d_att = cp_alloc<float>(E, (size_t)T * Q));
+        CPREQ(E->d_act = cp_alloc<float>(E, (size_t)T * I)); CPREQ(E->d_out = cp_alloc<float>(E, (size_t)T * H));
+        CPREQ(E->d_logits = cp_alloc<float>(E, (size_t)T * c.vocab)); CPREQ(E->d_in_hidden = cp_alloc<float>(E, (size_t)T * H));
+        CPREQ(E->d_in_embed = cp_alloc<float>(E, (size_t)T * H));
+        CPREQ(E->d_codes = cp_alloc<int>(E, (size_t)T * c.groups)); CPREQ(E->d_sp = cp_alloc<CpSampleParams>(E, T));
 #undef CPREQ
         CPK(cudaStreamSynchronize(E->stream));
         E->raw.clear();
         E->finalized = true;
-        if (int r = cp_build_graph(E)) return r;
+        if (int r = cp_build_graph(E, 1, &E->graph, &E->graph_kernels)) return r;
         CPK(cudaStreamSynchronize(E->stream));
         if (int r = cp_setup_frame(E)) return r;
         E->cache_len = 0;
@@ -1335,6 +1378,48 @@ int cp_predict(void* h, const float* hidden_state, const float* code0_embed, flo
     CPK(cudaMemcpyAsync(codes_out, E->d_codes, (size_t)c.groups * sizeof(int), cudaMemcpyDeviceToHost, E->stream));
     CPK(cudaStreamSynchronize(E->stream));
     if (E->persistent && E->fargs.prof) cp_print_prof(E);
+    E->cache_len = c.groups + 1;
+    E->last_S = 1;
+    return CP_OK;
+}
+
+int cp_max_batch(void* h) { return h ? CP_MAX_B : CP_E_INVALID; }
+
+int cp_predict_batch(void* h, int B, const float* hidden_states, const float* code0_embeds, float temperature, int top_k,
+                     const unsigned long long* seeds, int* codes_out) {
+    CpEngine* E = (CpEngine*)h;
+    if (!E) return CP_E_INVALID;
+    if (!E->finalized || !E->graph) return cp_fail(E, CP_E_STATE, "cp_finalize has not been called");
+    if (!hidden_states || !code0_embeds || !codes_out || !seeds || top_k < 1 || B < 1 || B > CP_MAX_B)
+        return cp_fail(E, CP_E_INVALID, "bad argument (1 .. cp_max_batch() streams)");
+    CPK(cudaSetDevice(E->device));
+    const CpCfg& c = E->cfg;
+    if ((size_t)B * std::max(c.inter, std::max(c.hidden, c.qdim())) * 4 > 200 * 1024)
+        return cp_fail(E, CP_E_INVALID, "batch too large for the shared-memory staged GEMV at this width");
+    cudaGraphExec_t exec = B == 1 ? E->graph : nullptr;
+    long long kernels = E->graph_kernels;
+    if (B > 1) {
+        auto it = E->batch_graphs.find(B);
+        if (it == E->batch_graphs.end()) {
+            cudaGraphExec_t g = nullptr;
+            long long k = 0;
+            if (int r = cp_build_graph(E, B, &g, &k)) return r;
+            E->batch_graphs[B] = g;
+            E->batch_graph_kernels[B] = k;
+            it = E->batch_graphs.find(B);
+        }
+        exec = it->second;
+        kernels = E->batch_graph_kernels[B];
+    }
+    CpSampleParams sp[CP_MAX_B];
+    for (int b = 0; b < B; ++b) sp[b] = CpSampleParams{temperature, top_k, seeds[b]};
+    CPK(cudaMemcpyAsync(E->d_in_hidden, hidden_states, (size_t)B * c.hidden * 4, cudaMemcpyHostToDevice, E->stream));
+    CPK(cudaMemcpyAsync(E->d_in_embed, code0_embeds, (size_t)B * c.hidden * 4, cudaMemcpyHostToDevice, E->stream));
+    CPK(cudaMemcpyAsync(E->d_sp, sp, (size_t)B * sizeof(CpSampleParams), cudaMemcpyHostToDevice, E->stream));
+    CPK(cudaGraphLaunch(exec, E->stream));
+    E->launches += kernels;
+    CPK(cudaMemcpyAsync(codes_out, E->d_codes, (size_t)B * c.groups * sizeof(int), cudaMemcpyDeviceToHost, E->stream));
+    CPK(cudaStreamSynchronize(E->stream));
     E->cache_len = c.groups + 1;
     E->last_S = 1;
     return CP_OK;

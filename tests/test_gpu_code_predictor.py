@@ -107,6 +107,30 @@ def test_greedy_frame_equals_the_oracle(cpm, tiny, path):
     assert cp.launches < 100 if path == "persistent" else cp.launches > 100
 
 
+@pytest.mark.parametrize("tiny", [True, False])
+def test_batched_streams_equal_single_streams(cpm, tiny):
+    """cp_predict_batch: B independent streams per launch (weights streamed once) == B calls of cp_predict == the oracle,
+    greedy and sampled (same seed per stream -> same draw), for every batch size up to cp_max_batch()."""
+    ocfg, cfg, w, W, cp = _pair(cpm, tiny=tiny)
+    assert cp.max_batch == 8
+    rng = np.random.default_rng(12)
+    hs = rng.standard_normal((8, cfg.hidden)).astype(np.float32)
+    es = rng.standard_normal((8, cfg.hidden)).astype(np.float32)
+    want = [CPO.predict(hs[b], es[b], W, ocfg) for b in range(8 if tiny else 3)]
+    single_sampled = [list(cp.predict(hs[b], es[b], 0.9, 20, seed=100 + b)) for b in range(8)]
+    for B in (1, 2, 3, 4, 5, 8):
+        got = cp.predict_batch(hs[:B], es[:B], 0.1, 1)
+        for b in range(min(B, len(want))):
+            assert list(got[b]) == want[b], (B, b)
+        got = cp.predict_batch(hs[:B], es[:B], 0.9, 20, seeds=[100 + b for b in range(B)])
+        assert [list(r) for r in got] == single_sampled[:B], B
+    # a stream's result does not depend on its neighbours or its row
+    a = cp.predict_batch(hs[[5, 0, 7]], es[[5, 0, 7]], 0.1, 1)
+    assert list(a[1]) == want[0]
+    with pytest.raises(cpm.CodePredictorError):
+        cp.predict_batch(np.zeros((9, cfg.hidden), np.float32), np.zeros((9, cfg.hidden), np.float32))
+
+
 def test_frames_are_independent_and_deterministic(cpm):
     ocfg, cfg, w, W, cp = _pair(cpm, tiny=False)
     rng = np.random.default_rng(6)
