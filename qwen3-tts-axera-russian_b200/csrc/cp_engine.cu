@@ -3,13 +3,17 @@
 // (/root/reference/dual_npu/code_predictor_server.py:77-140; "86 % of per-token time", docs/ARCHITECTURE.md:95-107).
 //
 // This is the other roofline of the product: batch 1, sequential, every step a chain of matrix-VECTOR products that
-// streams ~315 MB of float32 weights -- HBM/L2 bandwidth and launch latency, no tensor cores.  So:
+// streams ~315 MB of float32 weights -- HBM/L2 bandwidth and, above all, the latency of 432 dependent phases per frame; no
+// tensor cores.  So:
 //   * float32 weights and arithmetic throughout (the reference is ORT FP32; logits feed a temperature-0.1 sampler);
-//   * one warp per output row, 128-bit coalesced weight loads, the input vector(s) staged in shared memory, the
-//     surrounding element-wise work fused into the GEMV's epilogue (residual add, SwiGLU) or prologue kernels
-//     (RMSNorm; q/k-norm + rotary + cache append + attention over <= 17 positions in one small kernel);
+//   * one warp per (output row, K segment), 128-bit evict-first weight loads, the input vector(s) staged in shared
+//     memory, the surrounding element-wise work fused into the GEMV's prologue (RMSNorm) or epilogue (residual add,
+//     SwiGLU); q/k-norm + rotary + cache append + attention over <= 17 positions in one small kernel;
+//   * kernels chained by programmatic dependent launch, weight loads issued before the dependency wait;
 //   * the whole predict() -- 2 prefill positions, 15 x (lm_head, top-k sample, embedding lookup, decode step) -- is ONE
-//     CUDA graph of ~640 launches replayed per frame, sampling included, so a frame costs one launch and one 60-byte D2H.
+//     CUDA graph of 430 launches replayed per frame, sampling included: a frame costs one launch and one 60-byte D2H;
+//     cp_predict_batch carries B <= 8 independent streams through the same kernels (weights streamed once for all);
+//   * opt-in: the frame as one persistent cooperative kernel (cp_frame_kernel), with its own phase profiler.
 // Level 1 (cp_step / cp_logits) is the reference's _ort_step interface with the KV cache kept on the device.
 #include "../../include/cp_b200.h"
 
@@ -947,7 +951,7 @@ struct CpEngine {
     int last_S = 1;                                  // tokens of the last step (cp_logits reads the last one)
     long long graph_kernels = 0;
     // scratch
-    float *d_x = nullptr, *d_xn = nullptr, *d_qkv = nullptr, *d_att = nullptr, *d_act = nullptr, *d_out = nullptr, *d_logits = nullptr;
+    float *d_x = nullptr, *d_qkv = nullptr, *d_att = nullptr, *d_act = nullptr, *d_out = nullptr, *d_logits = nullptr;
     float *d_in_hidden = nullptr, *d_in_embed = nullptr;
     int* d_codes = nullptr;
     CpSampleParams* d_sp = nullptr;
@@ -1289,7 +1293,7 @@ int cp_finalize(void* h) {
         const size_t cache = (size_t)CP_MAX_B * c.layers * c.kv_heads * c.max_positions * hd;
         CPREQ(E->kc = cp_alloc<float>(E, cache)); CPREQ(E->vc = cp_alloc<float>(E, cache));
         constexpr int T = CP_MAX_B;                      // rows of every activation buffer (>= CP_MAX_S)
-        CPREQ(E->d_x = cp_alloc<float>(E, (size_t)T * H)); CPREQ(E->d_xn = cp_alloc<float>(E, (size_t)T * H));
+        CPREQ(E->d_x = cp_alloc<float>(E, (size_t)T * H));
         CPREQ(E->d_qkv = cp_alloc<float>(E, (size_t)T * (Q + 2 * KV))); CPREQ(E->d_att = cp_alloc<float>(E, (size_t)T * Q));
         CPREQ(E->d_act = cp_alloc<float>(E, (size_t)T * I)); CPREQ(E->d_out = cp_alloc<float>(E, (size_t)T * H));
         CPREQ(E->d_logits = cp_alloc<float>(E, (size_t)T * c.vocab)); CPREQ(E->d_in_hidden = cp_alloc<float>(E, (size_t)T * H));
