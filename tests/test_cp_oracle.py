@@ -111,3 +111,42 @@ def test_greedy_predict_is_reproducible_and_in_range():
     e0 = np.random.default_rng(3).standard_normal(cfg.hidden).astype(np.float32)
     a = CP.predict(hs, e0, W, cfg)
     assert a == CP.predict(hs, e0, W, cfg) and len(a) == cfg.groups and all(0 <= c < cfg.vocab for c in a)
+
+
+def test_production_size_oracle_matches_the_sibling_run_live():
+    """The oracle at the PRODUCTION shape (1024 / 5 layers / 16-8 heads x 128 / 3072) against the sibling model built at
+    that shape with the same random weights and run live, token by token with its own KV cache, over the 17 positions of
+    a frame (the golden file pins a small model; this pins the dimensions the product runs)."""
+    M = pytest.importorskip("transformers.models.qwen3_omni_moe.modeling_qwen3_omni_moe")
+    from transformers.models.qwen3_omni_moe.configuration_qwen3_omni_moe import Qwen3OmniMoeTalkerCodePredictorConfig
+    cfg = CP.CPConfig()
+    w = CP.init_weights(cfg, 2)
+    W = CP.Weights(w)
+    c = Qwen3OmniMoeTalkerCodePredictorConfig(hidden_size=cfg.hidden, intermediate_size=cfg.inter, num_hidden_layers=cfg.layers,
+                                              num_attention_heads=cfg.heads, num_key_value_heads=cfg.kv_heads, head_dim=cfg.head_dim,
+                                              vocab_size=cfg.vocab, num_code_groups=cfg.groups + 1, max_position_embeddings=64,
+                                              rms_norm_eps=cfg.rms_eps)
+    c._attn_implementation = "eager"
+    assert float(c.rope_parameters["rope_theta"]) == cfg.rope_theta
+    m = M.Qwen3OmniMoeTalkerCodePredictorModel(c).eval()
+    names = {"input_ln": "input_layernorm.weight", "q_proj": "self_attn.q_proj.weight", "k_proj": "self_attn.k_proj.weight",
+             "v_proj": "self_attn.v_proj.weight", "o_proj": "self_attn.o_proj.weight", "q_norm": "self_attn.q_norm.weight",
+             "k_norm": "self_attn.k_norm.weight", "post_ln": "post_attention_layernorm.weight",
+             "gate_proj": "mlp.gate_proj.weight", "up_proj": "mlp.up_proj.weight", "down_proj": "mlp.down_proj.weight"}
+    sd = m.state_dict()
+    with torch.no_grad():
+        for l in range(cfg.layers):
+            for ours, theirs in names.items():
+                sd[f"layers.{l}.{theirs}"].copy_(torch.from_numpy(w[f"layer_{l}_{ours}"]))
+        sd["norm.weight"].copy_(torch.from_numpy(w["final_norm"]))
+    xs = np.random.default_rng(21).standard_normal((cfg.groups + 2, cfg.hidden)).astype(np.float32)
+    past = kv = None
+    worst = 0.0
+    with torch.no_grad():
+        for t in range(len(xs)):
+            r = m(inputs_embeds=torch.from_numpy(xs[None, t:t + 1]), past_key_values=past, use_cache=True,
+                  cache_position=torch.tensor([t]), position_ids=torch.tensor([[t]]))
+            past = r.past_key_values
+            out, kv = CP.step(torch.from_numpy(xs[t:t + 1]), [t], kv, W, cfg)
+            worst = max(worst, float(np.abs(out.numpy()[0] - r.last_hidden_state[0, 0].numpy()).max()))
+    assert worst < 2e-5, worst

@@ -231,3 +231,45 @@ def test_server_protocol_host_and_device_samplers(cpm, tmp_path):
             want = CPO.predict(hidden, table[17], W, ocfg,
                                sampler=lambda l: CPO.sample_topk(l, 0.1, 50, np.random))
             assert list(codes) == want
+
+
+def test_production_size_step_matches_the_sibling_run_live(cpm):
+    """The executable sibling (``transformers`` Qwen3OmniMoeTalkerCodePredictorModel) built at the PRODUCTION shape with
+    our random weights and run live on the CPU, token by token with its own KV cache, against cp_step on the GPU (and
+    the oracle): 17 positions, hidden states within 2e-4."""
+    M = pytest.importorskip("transformers.models.qwen3_omni_moe.modeling_qwen3_omni_moe")
+    from transformers.models.qwen3_omni_moe.configuration_qwen3_omni_moe import Qwen3OmniMoeTalkerCodePredictorConfig
+    ocfg, cfg, w, W, cp = _pair(cpm, tiny=False, seed=2)
+    c = Qwen3OmniMoeTalkerCodePredictorConfig(hidden_size=cfg.hidden, intermediate_size=cfg.inter, num_hidden_layers=cfg.layers,
+                                              num_attention_heads=cfg.heads, num_key_value_heads=cfg.kv_heads, head_dim=cfg.head_dim,
+                                              vocab_size=cfg.vocab, num_code_groups=cfg.groups + 1, max_position_embeddings=64,
+                                              rms_norm_eps=cfg.rms_eps)
+    c._attn_implementation = "eager"
+    assert abs(float(c.rope_parameters["rope_theta"]) - cfg.rope_theta) < 1e-9
+    m = M.Qwen3OmniMoeTalkerCodePredictorModel(c).eval()
+    names = {"input_ln": "input_layernorm.weight", "q_proj": "self_attn.q_proj.weight", "k_proj": "self_attn.k_proj.weight",
+             "v_proj": "self_attn.v_proj.weight", "o_proj": "self_attn.o_proj.weight", "q_norm": "self_attn.q_norm.weight",
+             "k_norm": "self_attn.k_norm.weight", "post_ln": "post_attention_layernorm.weight",
+             "gate_proj": "mlp.gate_proj.weight", "up_proj": "mlp.up_proj.weight", "down_proj": "mlp.down_proj.weight"}
+    sd = m.state_dict()
+    with torch.no_grad():
+        for l in range(cfg.layers):
+            for ours, theirs in names.items():
+                sd[f"layers.{l}.{theirs}"].copy_(torch.from_numpy(w[f"layer_{l}_{ours}"]))
+        sd["norm.weight"].copy_(torch.from_numpy(w["final_norm"]))
+    n = cfg.groups + 2
+    xs = np.random.default_rng(21).standard_normal((n, cfg.hidden)).astype(np.float32)
+    past, kv = None, None
+    worst_gpu = worst_oracle = 0.0
+    with torch.no_grad():
+        for t in range(n):
+            r = m(inputs_embeds=torch.from_numpy(xs[None, t:t + 1]), past_key_values=past, use_cache=True,
+                  cache_position=torch.tensor([t]), position_ids=torch.tensor([[t]]))
+            past = r.past_key_values
+            sib = r.last_hidden_state[0, 0].numpy()
+            got = cp.step(xs[t:t + 1], t)[0]
+            orc, kv = CPO.step(torch.from_numpy(xs[t:t + 1]), [t], kv, W, ocfg)
+            worst_gpu = max(worst_gpu, float(np.abs(got - sib).max()))
+            worst_oracle = max(worst_oracle, float(np.abs(orc.numpy()[0] - sib).max()))
+    print(f"production-size code predictor vs the sibling run live: GPU max-abs {worst_gpu:.2e}, oracle max-abs {worst_oracle:.2e}")
+    assert worst_oracle < 5e-5 and worst_gpu < TOL
