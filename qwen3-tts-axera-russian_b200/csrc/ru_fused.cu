@@ -839,7 +839,7 @@ cudaError_t voc_launch_ru_fused(const RuFusedParams& p, cudaStream_t st, int num
     a.tap_row0 = 0; a.tap_step = p.dil;
     a.a_box_rows = pl.box_rows;
     // the same K chunking and segment schedule as voc_launch_tapgemm_tc gives these two layers (bit-identical results)
-    const int seg_mmas = (flags >> 8) > 0 ? (flags >> 8) : 24;
+    const int seg_mmas = (flags >> 16) > 0 ? (flags >> 16) : 24;
     {
         const int ksteps = (p.C + 15) / 16;
         a.k_chunks = (p.C + BK - 1) / BK;

@@ -114,7 +114,9 @@ enum { EPI_GENERIC = 0,      // everything decided at run time from TcArgs
        EPI_Y_S = 3,          // bias -> Y; Snake -> split operand S                (transposed convs)
        EPI_RES_S = 4 };      // bias, + residual; Snake -> split operand S         (the last 1x1 conv of a block)
 
-template <int BN, int BK, bool TWO, int EPI = EPI_GENERIC>
+// P3: the 3-pass form on a 96-column tile -- bit-identical, column by column, to BN = 192 (same passes, k-step order
+// and segment schedule); the launcher picks it when 192-column tiles would leave SMs idle (small batches).
+template <int BN, int BK, bool TWO, int EPI = EPI_GENERIC, bool P3 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ TcArgs a) {
@@ -127,7 +129,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // CAT (BN <= 128): see below.  In pair mode the concatenated form stages, per CTA, one whole weight plane
     // (rank 0: B_hi, rank 1: B_lo -- so that the N = 2*BN MMA, which takes BN rows from each CTA, produces
     // [A_hi*B_hi | A_hi*B_lo]) followed by this CTA's half of B_hi for the second MMA (N = BN, BN/2 rows each).
-    constexpr bool CAT = BN <= 128;
+    constexpr bool CAT = BN <= 128 && !P3;
     constexpr int BROWS = TWO ? BN / 2 : BN;                  // weight rows per plane staged by this CTA (3-pass form)
     constexpr uint32_t B_PLANE = (TWO && CAT) ? BN * ROWB : BROWS * ROWB;
     constexpr uint32_t B_STAGE = (TWO && CAT) ? (BN + BN / 2) * ROWB : 2 * B_PLANE;
@@ -653,7 +655,7 @@ inline int current_device() {
     return d;
 }
 
-template <int BN, int BK, int EPI = EPI_GENERIC>
+template <int BN, int BK, int EPI = EPI_GENERIC, bool P3 = false>
 cudaError_t launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, int grid, size_t smem,
                         cudaStream_t st) {
     // the shared-memory opt-in is a per-device attribute: one flag per device ordinal (a process may hold
@@ -662,24 +664,24 @@ cudaError_t launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const Tc
     const int dev = current_device();
     if (dev < 0) return cudaErrorInvalidDevice;
     if (!attr_done[dev].load(std::memory_order_acquire)) {
-        cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, BK, false, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, BK, false, EPI, P3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              SMEM_BUDGET + 1024);
         if (e != cudaSuccess) return e;
         attr_done[dev].store(true, std::memory_order_release);
     }
-    tapgemm_tc_kernel<BN, BK, false, EPI><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmB, a);
+    tapgemm_tc_kernel<BN, BK, false, EPI, P3><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmB, a);
     return cudaGetLastError();
 }
 
 // cta_group::2 launch: clusters of two CTAs
-template <int BN, int BK, int EPI = EPI_GENERIC>
+template <int BN, int BK, int EPI = EPI_GENERIC, bool P3 = false>
 cudaError_t launch_inst2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB2, const TcArgs& a,
                          int grid, size_t smem, cudaStream_t st) {
     static std::atomic<bool> attr_done[VOC_MAX_DEVICES];
     const int dev = current_device();
     if (dev < 0) return cudaErrorInvalidDevice;
     if (!attr_done[dev].load(std::memory_order_acquire)) {
-        cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, BK, true, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, BK, true, EPI, P3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              SMEM_BUDGET + 1024);
         if (e != cudaSuccess) return e;
         attr_done[dev].store(true, std::memory_order_release);
@@ -690,7 +692,7 @@ cudaError_t launch_inst2(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, tapgemm_tc_kernel<BN, BK, true, EPI>, tmA, tmB, tmB2, a);
+    return cudaLaunchKernelEx(&cfg, tapgemm_tc_kernel<BN, BK, true, EPI, P3>, tmA, tmB, tmB2, a);
 }
 
 template <int BK>
@@ -750,12 +752,47 @@ void voc_tc_clear_cache() {
 cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int num_sms, int flags) {
     if (!voc_tc_eligible(p)) return cudaErrorNotSupported;
     if (p.M <= 0 || p.B <= 0) return cudaSuccess;
-    const int BN = pick_bn(p.N);
+    const int BN0 = pick_bn(p.N);                 // the family's widest column tile: fixes the MMA form (3-pass / concatenated)
     // One SS-mode MMA (M 128, K 16) costs ~64 + N/2 cycles from SWIZZLE_128B operands and ~100 + N/2
     // from SWIZZLE_64B ones (tools/mma_rate.py), so 64-wide K chunks are used whenever K > 32.
     int BK = p.K > 32 ? 64 : 32;
     if (flags & VOC_TC_BK32) BK = 32;
     if (flags & VOC_TC_BK64) BK = 64;
+    const int sms = num_sms > 0 ? num_sms : 148;
+    // cta_group::2 pairs are a property of the layer shape (see below), never of the batch
+    const bool two = !(flags & VOC_TC_NO_PAIR) && BK == 64 && p.M > BM && (BN0 == 192 || BN0 == 96) &&
+                     ((flags & VOC_TC_FORCE_PAIR) || (BN0 == 192 && (long long)p.ntaps * p.K >= 768) ||
+                      (BN0 == 96 && (long long)p.ntaps * p.K >= 384));
+    // Column tile WITHIN the family.  A narrower tile of the same form computes every output column with the same
+    // passes, k-step order and segment schedule -- the same bits -- so this choice, unlike the form, may follow the
+    // batch: when the widest tile leaves SMs idle or strands a nearly empty last round (one window: 64 CTAs at
+    // C = 768, 160 tiles on 148 SMs at C = 384, 4 CTAs for the transformer's 512-column projections), a narrower one
+    // spreads the same k-steps over more SMs and each MMA is shorter.  Cost model: the issuing warp's cycles per
+    // k-step, one MMA = max(44 + N/8, N/2) (tools/mma_issue_bench.cu), times k-steps per tile times rounds, plus the
+    // exposed final epilogue of the last tile (~68 cycles per column, profiles/r1_mma_microbench.txt section 5).
+    int BN = BN0;
+    bool p3 = false;                              // 3-pass form on a 96-column tile
+    if (!(flags & VOC_TC_FIXED_TILE) && BK == 64) {
+        const int m_tiles0 = (p.M + BM - 1) / BM;
+        const long long mt = (long long)(two ? (m_tiles0 + 1) / 2 : m_tiles0) * p.B;
+        const long long walkers = two ? sms / 2 : sms;
+        const long long ksteps = (long long)((p.K + 15) / 16) * p.ntaps;
+        auto mma = [](int n) { return std::max(44 + n / 8, n / 2); };
+        auto est = [&](int bn, bool cat) {
+            const long long tiles = mt * (p.N / bn), rounds = (tiles + walkers - 1) / walkers;
+            return rounds * ksteps * (cat ? mma(2 * bn) + mma(bn) : 3 * mma(bn)) + 68LL * bn;
+        };
+        if (BN0 == 192) {
+            if ((flags & VOC_TC_SMALL_TILE) || est(96, false) < est(192, false)) { BN = 96; p3 = true; }
+        } else if (BN0 == 128 || BN0 == 64) {
+            long long best = est(BN0, true);
+            for (int bn = BN0 / 2; bn >= 32; bn /= 2) {
+                const long long e = est(bn, true);
+                if ((flags & VOC_TC_SMALL_TILE) || e < best) { best = e; BN = bn; }
+            }
+        }
+    }
+    const bool cat = BN <= 128 && !p3;            // the kernel's CAT
 
     TcArgs a;
     memset(&a, 0, sizeof(a));
@@ -774,7 +811,7 @@ cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int n
     // MMAs accumulated in the tensor core before a round-to-nearest flush (bits 8.. of flags).  Measured
     // on the full 64-frame window: 12 -> 98.8 dB / 1.2e-5, 24 -> 94.6 dB / 2.0e-5, 48 -> 88.6 dB / 3.9e-5,
     // 96 -> 82.6 dB / 6.9e-5, never -> 68.1 dB / 3.7e-4 (fails the 1e-4 gate).
-    const int seg_mmas = (flags >> 8) > 0 ? (flags >> 8) : 24;
+    const int seg_mmas = (flags >> 16) > 0 ? (flags >> 16) : 24;
     // seg_mmas counts MMAs into the main accumulator per segment as in the 3-pass form (3 per k-step);
     // the concatenated form (BN <= 128) keeps the same number of k-steps per segment
     // (one MMA per k-step reaches its main accumulator, so a segment may span three times the k-steps)
@@ -788,9 +825,7 @@ cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int n
     // BN = 96 (C = 96, the 7-tap convs): the pair halves the weight bytes each CTA re-streams per tile, which is
     // what bounds that layer (258 KB per 128 rows).  Its single-CTA form is the concatenated one, so the choice
     // must not depend on the batch: M here is the per-window length, the same for any number of windows.
-    const bool two = !(flags & VOC_TC_NO_PAIR) && BK == 64 && p.M > BM && (BN == 192 || BN == 96) &&
-                     ((flags & VOC_TC_FORCE_PAIR) || (BN == 192 && (long long)p.ntaps * p.K >= 768) ||
-                      (BN == 96 && (long long)p.ntaps * p.K >= 384));
+    // (`two` is computed above, from the family's widest tile)
     a.m_tiles = (p.M + BM - 1) / BM; a.n_tiles = p.N / BN; a.k_chunks = (p.K + BK - 1) / BK;
     // K chunks of equal depth: K = 96 runs as 48 + 48 (two 64-wide boxes, the second starting at column 48, three
     // k-steps used of each) instead of 64 + 32 -- a 2-k-step stage is shorter than the issuing warp's scalar path.
@@ -800,10 +835,10 @@ cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int n
         a.k_chunks = (ksteps + a.kc_steps - 1) / a.kc_steps;
         a.kc_last = ksteps - (a.k_chunks - 1) * a.kc_steps;
     }
-    a.seg_iters = std::max(1, seg_mmas / ((BN <= 128 ? 1 : 3) * a.kc_steps));
+    a.seg_iters = std::max(1, seg_mmas / ((cat ? 1 : 3) * a.kc_steps));
     // 3-pass form (two 192-column TMEM buffers, a 13 k-cycle final epilogue per tile at C = 192): the first two
     // segments of a tile hold twice the MMAs.  Measured end to end: see profiles/r1_segment_sweep.txt.
-    a.seg_head = (BN > 128 && !(flags & VOC_TC_NO_SEG_HEAD)) ? 2 : 0;
+    a.seg_head = (!cat && !(flags & VOC_TC_NO_SEG_HEAD)) ? 2 : 0;
     if (two) a.m_tiles = (a.m_tiles + 1) / 2;             // M-tile pairs
     a.total_tiles = a.m_tiles * a.n_tiles * p.B;
     a.wscale = p.wscale;
@@ -814,7 +849,7 @@ cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int n
     a.sn_a = p.sn_a; a.sn_invb = p.sn_invb;
 
     // stage plan
-    const bool two_cat = two && BN <= 128;            // pair mode, concatenated form: a plane + a half of B_hi per CTA
+    const bool two_cat = two && cat;                  // pair mode, concatenated form: a plane + a half of B_hi per CTA
     const int a_stage = 2 * a.a_box_rows * BK * 2;
     const int b_stage = two_cat ? (BN + BN / 2) * BK * 2 : 2 * (two ? BN / 2 : BN) * BK * 2;
     if (a.a_reuse) {
@@ -850,26 +885,26 @@ cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int n
         else epi = EPI_RES_S;
     }
     if (two) {
-        const int sms = num_sms > 0 ? num_sms : 148;
         const int grid2 = 2 * std::min(a.total_tiles, sms / 2);
-#define VOC_TC_PAIR(BN_) \
-        (epi == EPI_SNAKE_S ? launch_inst2<BN_, 64, EPI_SNAKE_S>(tmA, tmB, tmB2, a, grid2, smem, st) \
-         : epi == EPI_RES_Y_S ? launch_inst2<BN_, 64, EPI_RES_Y_S>(tmA, tmB, tmB2, a, grid2, smem, st) \
-         : epi == EPI_Y_S ? launch_inst2<BN_, 64, EPI_Y_S>(tmA, tmB, tmB2, a, grid2, smem, st) \
-         : epi == EPI_RES_S ? launch_inst2<BN_, 64, EPI_RES_S>(tmA, tmB, tmB2, a, grid2, smem, st) \
-                          : launch_inst2<BN_, 64, EPI_GENERIC>(tmA, tmB, tmB2, a, grid2, smem, st))
-        return BN == 192 ? VOC_TC_PAIR(192) : VOC_TC_PAIR(96);
+#define VOC_TC_PAIR(BN_, P3_) \
+        (epi == EPI_SNAKE_S ? launch_inst2<BN_, 64, EPI_SNAKE_S, P3_>(tmA, tmB, tmB2, a, grid2, smem, st) \
+         : epi == EPI_RES_Y_S ? launch_inst2<BN_, 64, EPI_RES_Y_S, P3_>(tmA, tmB, tmB2, a, grid2, smem, st) \
+         : epi == EPI_Y_S ? launch_inst2<BN_, 64, EPI_Y_S, P3_>(tmA, tmB, tmB2, a, grid2, smem, st) \
+         : epi == EPI_RES_S ? launch_inst2<BN_, 64, EPI_RES_S, P3_>(tmA, tmB, tmB2, a, grid2, smem, st) \
+                          : launch_inst2<BN_, 64, EPI_GENERIC, P3_>(tmA, tmB, tmB2, a, grid2, smem, st))
+        return BN == 192 ? VOC_TC_PAIR(192, false) : p3 ? VOC_TC_PAIR(96, true) : VOC_TC_PAIR(96, false);
 #undef VOC_TC_PAIR
     }
 
-    const int grid = std::min(a.total_tiles, num_sms > 0 ? num_sms : 148);
-    if (BK == 64 && (BN == 192 || BN == 96) && epi != EPI_GENERIC) {
-#define VOC_TC_SINGLE(BN_) \
-        (epi == EPI_SNAKE_S ? launch_inst<BN_, 64, EPI_SNAKE_S>(tmA, tmB, a, grid, smem, st) \
-         : epi == EPI_RES_Y_S ? launch_inst<BN_, 64, EPI_RES_Y_S>(tmA, tmB, a, grid, smem, st) \
-         : epi == EPI_RES_S ? launch_inst<BN_, 64, EPI_RES_S>(tmA, tmB, a, grid, smem, st) \
-                              : launch_inst<BN_, 64, EPI_Y_S>(tmA, tmB, a, grid, smem, st))
-        return BN == 192 ? VOC_TC_SINGLE(192) : VOC_TC_SINGLE(96);
+    const int grid = std::min(a.total_tiles, sms);
+    if (BK == 64 && (BN == 192 || BN == 96) && (epi != EPI_GENERIC || p3)) {
+#define VOC_TC_SINGLE(BN_, P3_) \
+        (epi == EPI_SNAKE_S ? launch_inst<BN_, 64, EPI_SNAKE_S, P3_>(tmA, tmB, a, grid, smem, st) \
+         : epi == EPI_RES_Y_S ? launch_inst<BN_, 64, EPI_RES_Y_S, P3_>(tmA, tmB, a, grid, smem, st) \
+         : epi == EPI_RES_S ? launch_inst<BN_, 64, EPI_RES_S, P3_>(tmA, tmB, a, grid, smem, st) \
+         : epi == EPI_Y_S ? launch_inst<BN_, 64, EPI_Y_S, P3_>(tmA, tmB, a, grid, smem, st) \
+                          : launch_inst<BN_, 64, EPI_GENERIC, P3_>(tmA, tmB, a, grid, smem, st))
+        return BN == 192 ? VOC_TC_SINGLE(192, false) : p3 ? VOC_TC_SINGLE(96, true) : VOC_TC_SINGLE(96, false);
 #undef VOC_TC_SINGLE
     }
     if (BK == 64) return launch_bn<64>(BN, tmA, tmB, a, grid, smem, st);

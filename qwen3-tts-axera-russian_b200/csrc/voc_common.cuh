@@ -138,10 +138,12 @@ struct RuFusedParams {
 bool voc_ru_fused_eligible(const RuFusedParams& p);
 cudaError_t voc_launch_ru_fused(const RuFusedParams& p, cudaStream_t st, int num_sms, int flags);
 // flags: bit 0 no tap reuse, bit 1 / bit 2 force 64- / 32-wide K chunks, bit 3 run-time (generic) epilogue only,
-// bit 4 no double-length head segments, bit 6 / bit 7 always / never cta_group::2 pairs, bits 8.. MMAs into the main
-// accumulator per round-to-nearest flush (default 24)
+// bit 4 no double-length head segments, bit 6 / bit 7 always / never cta_group::2 pairs, bit 8 / bit 9 always the widest /
+// the narrowest column tile of the layer's family (default: chosen per launch from the number of tiles, tc_gemm.cu),
+// bits 16.. MMAs into the main accumulator per round-to-nearest flush (default 24)
 enum { VOC_TC_NO_REUSE = 1, VOC_TC_BK64 = 2, VOC_TC_BK32 = 4, VOC_TC_GENERIC_EPI = 8, VOC_TC_NO_SEG_HEAD = 16,
-       VOC_TC_NO_PIPE = 32 /* fused residual unit: simple order of work */, VOC_TC_FORCE_PAIR = 64, VOC_TC_NO_PAIR = 128 };
+       VOC_TC_NO_PIPE = 32 /* fused residual unit: simple order of work */, VOC_TC_FORCE_PAIR = 64, VOC_TC_NO_PAIR = 128,
+       VOC_TC_FIXED_TILE = 256, VOC_TC_SMALL_TILE = 512 };
 
 // host-side launch wrappers (simt_kernels.cu)
 cudaError_t voc_launch_tapgemm_simt(const TapGemmParams& p, cudaStream_t st);

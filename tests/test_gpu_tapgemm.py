@@ -8,7 +8,8 @@ Tolerance: the tensor path multiplies split-fp16 operands (~22 mantissa bits) an
 FP32, so a dot product of O(1) terms is good to a few 1e-6 relative to the output scale.
 
 tc_flags: 0 = default (tap reuse through row-shifted descriptors, cta_group::2 pairs where the launcher
-selects them), 1 = per-tap aligned loads, 8 = run-time epilogue only, 128 = single-CTA kernel only."""
+selects them; column tile chosen per launch within the layer's family), 1 = per-tap aligned loads, 8 = run-time epilogue
+only, 128 = single-CTA kernel only, 256 / 512 = always the widest / the narrowest column tile of the family."""
 import numpy as np
 import pytest
 
@@ -117,6 +118,42 @@ def test_tc_compile_time_epilogues(backend, case, kind):
     assert np.array_equal(out[0][1], out[8][1]), (name, kind, "S differs between compile-time and run-time epilogue")
     if want_y:
         assert np.array_equal(out[0][0], out[8][0]), (name, kind, "Y differs")
+
+
+TILE_CASES = [c for c in CASES if c[0] in ("linear", "conv7_d3", "conv7_d9", "conv3", "convt_trim_right", "linear_k72",
+                                            "conv7_k160", "pair_conv7_c192", "pair_convt_k768", "pair_linear_2ntile")]
+
+
+@pytest.mark.parametrize("kind", ["generic", "snake_s", "res_y_s", "y_s", "res_s"])
+@pytest.mark.parametrize("case", TILE_CASES, ids=[c[0] for c in TILE_CASES])
+def test_tc_column_tile_does_not_change_the_bits(backend, case, kind):
+    """The launcher picks the column tile from the number of tiles (small batches get narrower tiles so that no SM
+    idles).  That is only legitimate if every tile of a family produces the same bits: 192 and 96 columns in the
+    3-pass form, 128 / 64 / 32 in the concatenated form, single CTAs and cta_group::2 pairs, every compile-time
+    epilogue.  tc_flags 256 = widest, 512 = narrowest, 0 = the launcher's own choice."""
+    name, B, a_rows, K, N, M, row0, taps = case
+    rng = np.random.default_rng(sum(map(ord, name + kind)) + 1)
+    A = rng.standard_normal((B, a_rows, K)).astype(np.float32)
+    W = (rng.standard_normal((len(taps) * K, N)) / np.sqrt(len(taps) * K)).astype(np.float32)
+    bias = (0.1 * rng.standard_normal(N)).astype(np.float32)
+    generic = kind == "generic"
+    scale = (1.0 + 0.1 * rng.standard_normal(N)).astype(np.float32) if generic else None
+    R = rng.standard_normal((B, M, N)).astype(np.float32) if kind in ("generic", "res_y_s", "res_s") else None
+    sn_a = np.exp(0.1 * rng.standard_normal(N)).astype(np.float32)
+    sn_invb = (1.0 / (np.exp(0.1 * rng.standard_normal(N)) + 1e-9)).astype(np.float32)
+    want_y = kind in ("generic", "res_y_s", "y_s")
+    v_ref, s_ref = ref_tapgemm(A, W, taps, M, row0, bias, scale, 0, R, sn_a, sn_invb)
+    out = {}
+    for flags in (256, 512, 0):
+        rc, Y, S, _ = backend.test_tapgemm(2, A, W, taps, M, row0, bias=bias, scale=scale, R=R, sn_a=sn_a, sn_invb=sn_invb,
+                                           want_y=want_y, want_s=True, tc_flags=flags)
+        assert rc == 0, (name, kind, flags, rc)
+        assert float(np.abs(S - s_ref).max()) < 2e-5, (name, kind, flags)
+        out[flags] = (Y, S)
+    for flags in (512, 0):
+        assert np.array_equal(out[256][1], out[flags][1]), (name, kind, flags, "S differs between column tiles")
+        if want_y:
+            assert np.array_equal(out[256][0], out[flags][0]), (name, kind, flags, "Y differs between column tiles")
 
 
 def test_tc_gelu_and_plain_operand_output(backend):

@@ -1,5 +1,5 @@
 for seg in 12 24 48 96 4000; do
-  f=$((seg*256))
+  f=$((seg*65536))
   echo "== seg $seg"
   python tools/gemm_bench.py --layers dec0.c7d1 dec1.c7d1 dec2.c7d1 dec3.c7d1 dec3.c1 dec2.convt --windows 4 --flags $f 2>&1 | python -c "
 import sys,json
