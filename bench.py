@@ -373,7 +373,21 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         if i >= 20:
             lat.append((time.perf_counter() - t0) * 1e3)
     lat.sort()
-
+    # the serving curve between configs[1] and configs[2]: p50 of the same host-to-host call for small batches (what a
+    # coalescing server sees); the launcher picks narrower column tiles while the widest would leave SMs idle
+    sweep = {}
+    if not args.no_legs:
+        for b in (2, 4, 8, 16, 32):
+            if b > B:
+                break
+            tb = []
+            for i in range(35):
+                t0 = time.perf_counter()
+                voc.lib.voc_infer_chunks(voc._h, h_codes.data_ptr(), b, h_out.data_ptr())
+                if i >= 5:
+                    tb.append((time.perf_counter() - t0) * 1e3)
+            tb.sort()
+            sweep[str(b)] = {"p50_ms": tb[len(tb) // 2], "audio_s_per_s": b * CHUNK_AUDIO_S / (tb[len(tb) // 2] / 1e3)}
 
     # ---- (4) parity of THIS configuration: four windows of the batch just timed (first, last, either side of
     # a wave boundary) against the CPU oracle, computed after the timed regions; rank 0 only
@@ -639,7 +653,9 @@ def run_b200(args, rank: int, local_rank: int, world: int):
                 "parity": parity,
                 "latency_ms": {"workload": "1 chunk, batch 1, host to host incl. H2D of 8 KB codes and D2H of the "
                                            "window (BASELINE configs[1]); 200 calls after 20 warm-ups",
-                               "p50": lat[len(lat) // 2], "p95": lat[int(0.95 * len(lat)) - 1]},
+                               "p50": lat[len(lat) // 2], "p95": lat[int(0.95 * len(lat)) - 1],
+                               "small_batches": sweep,
+                               "small_batches_note": "p50 of 30 calls of the same host-to-host call with 2..32 windows"},
                 "utterance_10min": utt, "corpus_1k": corpus, "stream_10min": stream,
                 "code_predictor": cp_leg},
         "gpu_launches": int(launches),

@@ -172,6 +172,13 @@ void*       voc_stream(void* h);
  * writes a JSON array [{"tag","calls","ms","flops","bytes"}...] (algorithmic FLOPs / bytes of
  * the launches) into buf, clearing the records.  buf = NULL returns the size needed.        */
 long long   voc_profile_report(void* h, char* buf, long long cap);
+/* Operand-range diagnostic for checkpoints other than the random-init one.  GEMM operands are stored as two unscaled
+ * fp16 planes (hi, lo): absolute error <= 2^-25, but a layer whose activations sit far below 2^-3 keeps fewer
+ * significant bits and one beyond 65504 saturates.  After voc_set_option(h,"operand_stats","1") every launch that
+ * writes such an operand (dense layers, fused residual units) is followed by a counting pass; voc_operand_report
+ * writes a JSON array [{"tag","elements","saturated","hi_subnormal","lo_subnormal","rms","max_abs"}...] per layer tag
+ * into buf and clears the counters.  buf = NULL returns the size needed.  Diagnostic mode: no CUDA graphs.          */
+long long   voc_operand_report(void* h, char* buf, long long cap);
 /* Intermediate activations for parity tests: copies stage `name` ("rvq","pre_conv","xf",
  * "up0","up1","conv_in_s","dec0".."dec3") of the last wave into `out` (channels-last
  * [windows][time][channels]); returns the element count or a negative error.               */

@@ -62,6 +62,7 @@ SIGNATURES = {
     "voc_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
     "voc_stream": (C.c_void_p, [C.c_void_p]),
     "voc_profile_report": (C.c_longlong, [C.c_void_p, C.c_void_p, C.c_longlong]),
+    "voc_operand_report": (C.c_longlong, [C.c_void_p, C.c_void_p, C.c_longlong]),
     "voc_debug_stage": (C.c_longlong, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_longlong]),
     "voc_test_tapgemm": (C.c_int, [C.c_int] * 10 + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 5
                          + [C.c_int, C.c_void_p]),
@@ -352,6 +353,19 @@ class Vocoder:
             self._ck(int(n))
         buf = C.create_string_buffer(int(n))
         n2 = self.lib.voc_profile_report(self._h, buf, n)
+        if n2 < 0:
+            self._ck(int(n2))
+        return json.loads(buf.value.decode() or "[]")
+
+    def operand_report(self):
+        """Per-layer range statistics of the split-fp16 operands written since the last call (needs operand_stats=1):
+        saturated / subnormal counts, rms and largest magnitude -- the check to run on a real checkpoint."""
+        import json
+        n = self.lib.voc_operand_report(self._h, None, 0)
+        if n < 0:
+            self._ck(int(n))
+        buf = C.create_string_buffer(int(n))
+        n2 = self.lib.voc_operand_report(self._h, buf, n)
         if n2 < 0:
             self._ck(int(n2))
         return json.loads(buf.value.decode() or "[]")

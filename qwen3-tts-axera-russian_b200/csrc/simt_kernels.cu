@@ -993,3 +993,54 @@ cudaError_t voc_launch_unsplit(const __half* hi, const __half* lo, float* out, l
     unsplit_kernel<<<(unsigned)blocks, 256, 0, st>>>(hi, lo, out, n);
     return cudaGetLastError();
 }
+
+// ---------------------------------------------------------------------------------------------
+// Diagnostic (option "operand_stats"): how well a split-fp16 operand tensor uses its format.  Operands are unscaled
+// (hi = fp16(x), lo = fp16(x - hi)): the absolute error is <= 2^-25 whatever the magnitude, but a layer whose values sit
+// far below 2^-3 keeps fewer significant bits (lo, then hi, fall into the fp16 subnormals) and a value beyond 65504
+// saturates.  Random-init weights keep every layer O(1); a real checkpoint may not -- this pass says so per layer.
+// out[0] elements, [1] saturated (|hi| = 65504), [2] hi subnormal (0 < |hi| < 2^-14), [3] lo subnormal,
+// [4] sum of squares (double bits), [5] max |hi| (fp16 bits).
+// ---------------------------------------------------------------------------------------------
+__global__ void operand_stats_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, int B, long long rows,
+                                     int cols, int ld, long long bstride, unsigned long long* __restrict__ out) {
+    const long long per = rows * cols, n = per * B;
+    unsigned long long sat = 0, hsub = 0, lsub = 0;
+    double ss = 0.0;
+    unsigned mx = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / per, r = (i - b * per) / cols, c = i - b * per - r * cols;
+        const long long off = b * bstride + r * ld + c;
+        const unsigned short hb = __half_as_ushort(hi[off]) & 0x7FFF, lb = __half_as_ushort(lo[off]) & 0x7FFF;
+        sat += hb == 0x7BFF;
+        hsub += hb != 0 && hb < 0x0400;
+        lsub += lb != 0 && lb < 0x0400;
+        const float v = __half2float(hi[off]) + __half2float(lo[off]);
+        ss += (double)v * v;
+        mx = max(mx, (unsigned)hb);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        sat += __shfl_xor_sync(0xffffffffu, sat, o);
+        hsub += __shfl_xor_sync(0xffffffffu, hsub, o);
+        lsub += __shfl_xor_sync(0xffffffffu, lsub, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (sat) atomicAdd(out + 1, sat);
+        if (hsub) atomicAdd(out + 2, hsub);
+        if (lsub) atomicAdd(out + 3, lsub);
+        atomicAdd(reinterpret_cast<double*>(out + 4), ss);
+        atomicMax(out + 5, (unsigned long long)mx);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(out, (unsigned long long)n);
+}
+
+cudaError_t voc_launch_operand_stats(const __half* hi, const __half* lo, int B, long long rows, int cols, int ld,
+                                     long long bstride, unsigned long long* out, cudaStream_t st) {
+    const long long n = (long long)B * rows * cols;
+    if (n <= 0) return cudaSuccess;
+    long long blocks = (n + 2047) / 2048; if (blocks > 148 * 8) blocks = 148 * 8;
+    operand_stats_kernel<<<(unsigned)blocks, 256, 0, st>>>(hi, lo, B, rows, cols, ld, bstride, out);
+    return cudaGetLastError();
+}

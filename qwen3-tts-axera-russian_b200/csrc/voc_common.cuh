@@ -176,3 +176,6 @@ cudaError_t voc_launch_append_window(float* res, long long res_len, const float*
 cudaError_t voc_launch_pcm16(const float* in, short* out, long long n, cudaStream_t st);
 // split-fp16 -> float32 (debug captures of operand tensors)
 cudaError_t voc_launch_unsplit(const __half* hi, const __half* lo, float* out, long long n, cudaStream_t st);
+// range statistics of a split-fp16 operand tensor [B][rows][cols] (row stride ld, window stride bstride), added into out[6]
+cudaError_t voc_launch_operand_stats(const __half* hi, const __half* lo, int B, long long rows, int cols, int ld,
+                                     long long bstride, unsigned long long* out, cudaStream_t st);

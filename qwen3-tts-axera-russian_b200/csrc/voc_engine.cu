@@ -227,6 +227,13 @@ struct Engine {
     struct Stream { long long pos = 0; std::vector<std::pair<float*, size_t>> halos; } strm;
     int rope_positions = 0;
 
+    // operand-range statistics (option "operand_stats" = "1"), read by voc_operand_report: one slot of six counters per
+    // layer tag, filled by a counting pass after every launch that writes a split-fp16 operand
+    bool opstats = false;
+    static constexpr int OPSTAT_SLOTS = 96, OPSTAT_WORDS = 6;
+    unsigned long long* d_opstats = nullptr;
+    std::vector<std::string> opstat_tags;
+    std::string opstat_json;
     // per-launch CUDA-event profile (option "profile" = "1"), read by voc_profile_report
     bool profile = false;
     struct ProfRec { const char* tag; double flops, bytes; cudaEvent_t e0, e1; };
@@ -243,6 +250,7 @@ struct Engine {
         for (void* p : owned) cudaFree(p);
         for (auto& hl : strm.halos) cudaFree(hl.first);
         if (d_err) cudaFree(d_err);
+        if (d_opstats) cudaFree(d_opstats);
         if (d_meta) cudaFree(d_meta);
         if (d_fade_out) cudaFree(d_fade_out);
         if (d_fade_in) cudaFree(d_fade_in);
@@ -278,6 +286,26 @@ static int fail(Engine* E, int code, const std::string& msg) {
     E->err = msg;
     fprintf(stderr, "voc_b200: %s\n", msg.c_str());
     return code;
+}
+
+// operand-range statistics of the tensor a launch has just written (diagnostic mode only; not counted as a launch)
+static cudaError_t opstat(Engine* E, cudaStream_t st, const char* tag, const __half* hi, const __half* lo, int B,
+                          long long rows, int cols, int ld, long long bstride) {
+    if (!E->opstats || !hi || !lo) return cudaSuccess;
+    if (!E->d_opstats) {
+        const size_t bytes = (size_t)Engine::OPSTAT_SLOTS * Engine::OPSTAT_WORDS * sizeof(unsigned long long);
+        cudaError_t e = cudaMalloc(&E->d_opstats, bytes);
+        if (e != cudaSuccess) return e;
+        e = cudaMemsetAsync(E->d_opstats, 0, bytes, st);
+        if (e != cudaSuccess) return e;
+    }
+    size_t slot = 0;
+    while (slot < E->opstat_tags.size() && E->opstat_tags[slot] != tag) ++slot;
+    if (slot == E->opstat_tags.size()) {
+        if (slot >= (size_t)Engine::OPSTAT_SLOTS) return cudaSuccess;       // more layer tags than slots: not recorded
+        E->opstat_tags.push_back(tag);
+    }
+    return voc_launch_operand_stats(hi, lo, B, rows, cols, ld, bstride, E->d_opstats + slot * Engine::OPSTAT_WORDS, st);
 }
 
 static float* upload(Engine* E, const std::vector<float>& v) {
@@ -408,6 +436,7 @@ static cudaError_t run_gemm(Engine* E, TapGemmParams& p, cudaStream_t st, const 
     cudaError_t e = cudaErrorNotSupported;
     if (voc_tc_eligible(p)) {
         e = voc_launch_tapgemm_tc(p, st, E->num_sms, E->tc_flags);
+        if (e == cudaSuccess) return opstat(E, st, tag, p.S_hi, p.S_lo, p.B, p.M, p.N, p.lds, p.s_bstride);
         if (e != cudaErrorNotSupported) return e;
         (void)cudaGetLastError();
     }
@@ -789,6 +818,7 @@ static int run_back(Engine* E, float* x, int x_win0, int L, int nw, float* chunk
                     const double el = (double)nw * L * C;
                     ProfScope ps(E, st, T_FU[ti], 2.0 * el * C * (c.conv_kernel + 1), 4.0 * el * (f.Y ? 4.0 : f.head_w ? 2.0 : 3.0));
                     CK(voc_launch_ru_fused(f, st, E->num_sms, E->tc_flags));
+                    CK(opstat(E, st, T_FU[ti], f.S_hi, f.S_lo, f.B, f.L, f.C, f.C, (long long)f.L * f.C));
                     std::swap(bS, bT);
                     if (f.Y) std::swap(bX, bX2);
                     continue;
@@ -1017,6 +1047,7 @@ static int stream_segment(Engine* E, const long long* d_codes, int n, float* out
                     const double el = (double)L * C;
                     ProfScope ps(E, st, T_FU[ti], 2.0 * el * C * (c.conv_kernel + 1), 4.0 * el * (f.Y ? 4.0 : 3.0));
                     CK(voc_launch_ru_fused(f, st, E->num_sms, E->tc_flags));
+                    CK(opstat(E, st, T_FU[ti], f.S_hi, f.S_lo, f.B, f.L, f.C, f.C, (long long)f.L * f.C));
                     done = true;
                 }
             }
@@ -1076,7 +1107,7 @@ static int run_windows(Engine* E, const long long* d_codes, int n_frames, int wi
         // Small waves are launch-bound, so a wave that recurs with the same buffers (the streaming client's
         // one-window requests through the host entry points) is replayed as a CUDA graph: first sight runs
         // eagerly (lazy set-up: kernel attributes, tensor maps), second sight is captured, later ones replay.
-        const bool graphable = E->use_graphs && nw <= E->graph_max_wave && !E->profile && !E->debug;
+        const bool graphable = E->use_graphs && nw <= E->graph_max_wave && !E->profile && !E->debug && !E->opstats;
         if (!graphable) {
             if (int r = run_wave(E, d_codes, n_frames, win_step, w, nw, out, st, nullptr, T)) return r;
             continue;
@@ -1846,6 +1877,7 @@ int voc_set_option(void* h, const char* key, const char* value) {
         E->front_wave = atoi(v.c_str()); return VOC_OK;
     }
     if (k == "profile") { E->profile = (v == "1"); return VOC_OK; }
+    if (k == "operand_stats") { E->opstats = (v == "1"); return VOC_OK; }
     if (k == "debug") { E->debug = (v == "1"); if (!E->debug) E->dbg.clear(); return VOC_OK; }
     return fail(E, VOC_E_INVALID, "unknown option " + k);
 }
@@ -1885,6 +1917,44 @@ long long voc_profile_report(void* h, char* buf, long long cap) {
     if (cap < need) return fail(E, VOC_E_INVALID, "buffer too small");
     memcpy(buf, E->prof_json.c_str(), (size_t)need);
     E->prof_json.clear();
+    return need;
+}
+
+long long voc_operand_report(void* h, char* buf, long long cap) {
+    Engine* E = (Engine*)h;
+    if (!E) return VOC_E_INVALID;
+    CK(cudaSetDevice(E->device));
+    if (E->opstat_json.empty()) {
+        std::string js = "[";
+        if (E->d_opstats && !E->opstat_tags.empty()) {
+            const size_t n = E->opstat_tags.size() * Engine::OPSTAT_WORDS;
+            std::vector<unsigned long long> hst(n);
+            CK(cudaStreamSynchronize(E->stream));
+            CK(cudaDeviceSynchronize());
+            CK(cudaMemcpy(hst.data(), E->d_opstats, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            CK(cudaMemset(E->d_opstats, 0, (size_t)Engine::OPSTAT_SLOTS * Engine::OPSTAT_WORDS * sizeof(unsigned long long)));
+            char tmp[512];
+            for (size_t i = 0; i < E->opstat_tags.size(); ++i) {
+                const unsigned long long* w = hst.data() + i * Engine::OPSTAT_WORDS;
+                double ss; memcpy(&ss, &w[4], sizeof ss);
+                const unsigned hb = (unsigned)w[5] & 0x7FFF;       // largest |hi| as fp16 bits -> float
+                const int ex = (int)(hb >> 10), ma = (int)(hb & 0x3FF);
+                const double mx = ex == 0 ? ldexp((double)ma, -24) : ldexp(1.0 + ma / 1024.0, ex - 15);
+                snprintf(tmp, sizeof tmp, "%s{\"tag\":\"%s\",\"elements\":%llu,\"saturated\":%llu,\"hi_subnormal\":%llu,"
+                         "\"lo_subnormal\":%llu,\"rms\":%.6e,\"max_abs\":%.6e}", i ? "," : "", E->opstat_tags[i].c_str(),
+                         w[0], w[1], w[2], w[3], w[0] ? sqrt(ss / (double)w[0]) : 0.0, mx);
+                js += tmp;
+            }
+            E->opstat_tags.clear();
+        }
+        js += "]";
+        E->opstat_json = js;
+    }
+    const long long need = (long long)E->opstat_json.size() + 1;
+    if (!buf) return need;
+    if (cap < need) return fail(E, VOC_E_INVALID, "buffer too small");
+    memcpy(buf, E->opstat_json.c_str(), (size_t)need);
+    E->opstat_json.clear();
     return need;
 }
 

@@ -108,6 +108,44 @@ def test_batch_invariance(full_model):
     assert np.array_equal(a[4], b[0])
 
 
+def test_operand_range_report(full_model, backend, pkg):
+    """The diagnostic for checkpoints other than the random-init one: per layer, how the unscaled split-fp16 operands
+    use their format.  On the random-init model no operand saturates and every layer is O(1); a Snake with a tiny beta
+    (1 / (e^beta + 1e-9) ~ 1e9) must show up as saturated values in the layer that applies it, and the windowed result
+    of the healthy model must not change by having looked."""
+    cfg, w, voc = full_model
+    codes = _codes(cfg, (2, 64, 16), seed=9)
+    base = voc.infer_chunks(codes)
+    voc.set_option("operand_stats", "1")
+    try:
+        got = voc.infer_chunks(codes)
+        rep = {r["tag"]: r for r in voc.operand_report()}
+    finally:
+        voc.set_option("operand_stats", "0")
+    assert np.array_equal(base, got)
+    for tag in ("dec0.convt", "dec1.ru.conv7", "dec2.ru.fused", "dec3.ru.fused", "xf.gemm", "conv_in"):
+        assert tag in rep, (tag, sorted(rep))
+    for tag, r in rep.items():
+        print(f"{tag:16s} elements {r['elements']:>12d} rms {r['rms']:.3f} max {r['max_abs']:.1f} "
+              f"hi_subnormal {r['hi_subnormal'] / r['elements']:.2e} lo_subnormal {r['lo_subnormal'] / r['elements']:.2e}")
+        assert r["elements"] > 0 and r["saturated"] == 0, (tag, r)
+        assert 1e-3 < r["rms"] < 1e3, (tag, r)
+    assert voc.operand_report() == []                      # the counters were cleared
+
+    small = pkg.VocoderConfig(chunk_frames=8)
+    w2 = dict(pkg.init_weights(small, seed=0))
+    w2["dec.3.ru.1.snake1.beta"] = np.full_like(w2["dec.3.ru.1.snake1.beta"], -40.0)
+    bad = backend.Vocoder(small, w2, wave=2)
+    try:
+        bad.set_option("operand_stats", "1")
+        bad.infer_chunks(_codes(small, (1, 8, 16), seed=3))
+        rep2 = {r["tag"]: r for r in bad.operand_report()}
+    finally:
+        bad.close()
+    assert rep2["dec3.ru.fused"]["saturated"] > 0 and rep2["dec3.ru.fused"]["max_abs"] == 65504.0, rep2["dec3.ru.fused"]
+    assert rep2["dec2.ru.fused"]["saturated"] == 0
+
+
 def test_code_out_of_range_is_an_error(full_model, backend):
     cfg, w, voc = full_model
     codes = _codes(cfg, (1, 64, 16))
