@@ -90,6 +90,31 @@ def test_production_architecture_two_pieces(pkg, backend):
     voc.close()
 
 
+def test_production_architecture_live_pieces(pkg, backend):
+    """The live-streaming case (the talker emits 12.5 frames/s): the default architecture decoded in pieces of 1, 4, 3,
+    16, 1 and 7 frames -- block 0 then sees 32-row inputs, the fused residual units a few tiles, every layer its halo from
+    the previous call -- against the oracle run once on all 32 frames."""
+    cfg = pkg.VocoderConfig(transconv_trim="right")
+    w = pkg.init_weights(cfg, 0)
+    pieces = [1, 4, 3, 16, 1, 7]
+    n = sum(pieces)
+    codes = _codes(cfg, n, 13)
+    ref, _ = VO.forward(codes[None], VO.Weights(w), cfg)
+    ref = ref.numpy()[0]
+    voc = backend.Vocoder(cfg, w, wave=4)
+    voc.set_option("gemm", "tc")
+    out, at = [], 0
+    for k in pieces:
+        out.append(voc.stream_decode(codes[at:at + k]))
+        assert out[-1].shape == (k * 1920,)
+        at += k
+    got = np.concatenate(out)
+    assert got.shape == ref.shape == (n * 1920,)
+    _check("production, pieces 1 + 4 + 3 + 16 + 1 + 7", ref, got)
+    assert voc.simt_launches == 0
+    voc.close()
+
+
 def test_stream_needs_the_causal_trim(pkg, backend):
     cfg = pkg.VocoderConfig.tiny(chunk_frames=8)                 # transconv_trim = "both": one input step of look-ahead
     voc = backend.Vocoder(cfg, pkg.init_weights(cfg, 0), wave=2)

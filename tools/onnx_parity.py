@@ -74,6 +74,13 @@ def main():
                                         and row["b200_vs_onnx"]["max_abs"] <= 1e-4)
             rows.append(row)
         if voc is not None:
+            # how the real checkpoint's activations sit in the unscaled split-fp16 operand format (voc_operand_report):
+            # a saturated count > 0 or an rms far below 2^-3 names the layer that needs an activation scale
+            voc.set_option("operand_stats", "1")
+            voc.infer_chunks(codes)
+            report.setdefault("operand_ranges", {})[trim] = [
+                dict(r, flag=("saturated" if r["saturated"] else "small" if r["rms"] < 2.0 ** -6 else "ok"))
+                for r in voc.operand_report()]
             voc.close()
         report["settings"][trim] = rows
     print(json.dumps(report, indent=1))
