@@ -466,14 +466,20 @@ attention_kernel(const float* __restrict__ qkv, VocAct out, int T, int heads,
     }
 }
 
-// Streaming form (carried-state decode): one sequence; the qkv buffer holds `kv_halo` rows of history
-// (the previous segments' last rows, K and V parts used) before the T new rows, whose absolute positions start at pos0.
+// Streaming form (carried-state decode): one sequence; the qkv buffer holds `kv_max` rows of history
+// (the previous segments' last rows, K and V parts used; the last min(kv_max, pos0) of them exist) before the T new
+// rows, whose absolute positions start at pos0 = *pos_ptr.
 template <int HD>
 __global__ void __launch_bounds__(64)
-attention_stream_kernel(const float* __restrict__ qkv, VocAct out, int T, int heads,
+attention_stream_kernel(const float* __restrict__ qkv_base, VocAct out, int T, int heads,
                         const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, int window,
-                        int kv_halo, int pos0) {
+                        int kv_max, const int* __restrict__ pos_ptr) {
     constexpr int H2 = HD / 2;
+    // the stream position comes from device memory so that the launch is position-independent (replayable as a CUDA
+    // graph); the buffer holds kv_max history rows, of which the last min(kv_max, pos0) exist
+    const int pos0 = *pos_ptr;
+    const int kv_halo = min(kv_max, pos0);
+    const float* __restrict__ qkv = qkv_base + (long long)(kv_max - kv_halo) * 3 * heads * HD;
     __shared__ __align__(16) float Ks[64][HD];
     __shared__ __align__(16) float Vs[64][HD];
     const int hh = blockIdx.y, q0 = blockIdx.x * 64;
@@ -564,14 +570,14 @@ attention_stream_kernel(const float* __restrict__ qkv, VocAct out, int T, int he
 }
 
 cudaError_t voc_launch_attention_stream(const float* qkv, VocAct out, int T, int heads, int head_dim,
-                                        const float* rope_cos, const float* rope_sin, int window, int kv_halo,
-                                        int pos0, cudaStream_t st) {
+                                        const float* rope_cos, const float* rope_sin, int window, int kv_max,
+                                        const int* pos_ptr, cudaStream_t st) {
     if (T <= 0) return cudaSuccess;
     dim3 grid((T + 63) / 64, heads, 1);
     switch (head_dim) {
-        case 64: attention_stream_kernel<64><<<grid, 64, 0, st>>>(qkv, out, T, heads, rope_cos, rope_sin, window, kv_halo, pos0); break;
-        case 32: attention_stream_kernel<32><<<grid, 64, 0, st>>>(qkv, out, T, heads, rope_cos, rope_sin, window, kv_halo, pos0); break;
-        case 16: attention_stream_kernel<16><<<grid, 64, 0, st>>>(qkv, out, T, heads, rope_cos, rope_sin, window, kv_halo, pos0); break;
+        case 64: attention_stream_kernel<64><<<grid, 64, 0, st>>>(qkv, out, T, heads, rope_cos, rope_sin, window, kv_max, pos_ptr); break;
+        case 32: attention_stream_kernel<32><<<grid, 64, 0, st>>>(qkv, out, T, heads, rope_cos, rope_sin, window, kv_max, pos_ptr); break;
+        case 16: attention_stream_kernel<16><<<grid, 64, 0, st>>>(qkv, out, T, heads, rope_cos, rope_sin, window, kv_max, pos_ptr); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -1042,5 +1048,27 @@ cudaError_t voc_launch_operand_stats(const __half* hi, const __half* lo, int B, 
     if (n <= 0) return cudaSuccess;
     long long blocks = (n + 2047) / 2048; if (blocks > 148 * 8) blocks = 148 * 8;
     operand_stats_kernel<<<(unsigned)blocks, 256, 0, st>>>(hi, lo, B, rows, cols, ld, bstride, out);
+    return cudaGetLastError();
+}
+
+// Two equally long device-to-device copies in one launch (the hi and lo planes of a layer's halo rows in the carried-state
+// decode: a kernel node replays faster than two memcpy nodes, and a live piece of a stream is ~90 of these).
+__global__ void copy_pair_kernel(void* __restrict__ d0, const void* __restrict__ s0, void* __restrict__ d1,
+                                 const void* __restrict__ s1, size_t bytes) {
+    char* d = static_cast<char*>(blockIdx.y ? d1 : d0);
+    const char* sr = static_cast<const char*>(blockIdx.y ? s1 : s0);
+    if (!d) return;
+    const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    if (((reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(sr) | bytes) & 15) == 0) {
+        for (size_t i = i0; i < bytes / 16; i += stride) reinterpret_cast<uint4*>(d)[i] = reinterpret_cast<const uint4*>(sr)[i];
+    } else {
+        for (size_t i = i0; i < bytes; i += stride) d[i] = sr[i];
+    }
+}
+
+cudaError_t voc_launch_copy_pair(void* d0, const void* s0, void* d1, const void* s1, size_t bytes, cudaStream_t st) {
+    if (!bytes) return cudaSuccess;
+    size_t blocks = (bytes / 16 + 255) / 256; if (blocks < 1) blocks = 1; if (blocks > 148 * 4) blocks = 148 * 4;
+    copy_pair_kernel<<<dim3((unsigned)blocks, d1 ? 2 : 1), 256, 0, st>>>(d0, s0, d1, s1, bytes);
     return cudaGetLastError();
 }

@@ -160,8 +160,8 @@ cudaError_t voc_launch_attention(const float* qkv, VocAct out, int B, int T, int
                                  const float* rope_cos, const float* rope_sin, int window,
                                  cudaStream_t st);
 cudaError_t voc_launch_attention_stream(const float* qkv, VocAct out, int T, int heads, int head_dim,
-                                        const float* rope_cos, const float* rope_sin, int window, int kv_halo,
-                                        int pos0, cudaStream_t st);
+                                        const float* rope_cos, const float* rope_sin, int window, int kv_max,
+                                        const int* pos_ptr, cudaStream_t st);
 cudaError_t voc_launch_swiglu(const float* gu, VocAct out, long long rows, int inter, cudaStream_t st);
 cudaError_t voc_launch_head(VocAct S, long long s_bstride, int L, int C, int ksz, const float* w,
                             float bias, float* out, long long o_bstride, int B, cudaStream_t st, int halo = 0);
@@ -176,6 +176,8 @@ cudaError_t voc_launch_append_window(float* res, long long res_len, const float*
 cudaError_t voc_launch_pcm16(const float* in, short* out, long long n, cudaStream_t st);
 // split-fp16 -> float32 (debug captures of operand tensors)
 cudaError_t voc_launch_unsplit(const __half* hi, const __half* lo, float* out, long long n, cudaStream_t st);
+// two equally long device-to-device copies in one launch (d1 = nullptr: one)
+cudaError_t voc_launch_copy_pair(void* d0, const void* s0, void* d1, const void* s1, size_t bytes, cudaStream_t st);
 // range statistics of a split-fp16 operand tensor [B][rows][cols] (row stride ld, window stride bstride), added into out[6]
 cudaError_t voc_launch_operand_stats(const __half* hi, const __half* lo, int B, long long rows, int cols, int ld,
                                      long long bstride, unsigned long long* out, cudaStream_t st);

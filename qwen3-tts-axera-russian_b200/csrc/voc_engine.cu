@@ -216,6 +216,7 @@ struct Engine {
     float *f_rvq, *f_pre, *f_h, *f_hn, *f_qkv, *f_att, *f_gu, *f_act, *f_x, *f_ln, *f_mid, *f_x2;
     size_t big_elems = 0;
     int* d_err = nullptr;
+    int* d_strm_pos = nullptr;                  // carried-state decode: frames decoded so far, read by the attention kernel
     int* d_meta = nullptr; size_t meta_cap = 0;
     float* d_fade_out = nullptr; float* d_fade_in = nullptr;
     long long* d_codes = nullptr; size_t codes_cap = 0;
@@ -250,6 +251,7 @@ struct Engine {
         for (void* p : owned) cudaFree(p);
         for (auto& hl : strm.halos) cudaFree(hl.first);
         if (d_err) cudaFree(d_err);
+        if (d_strm_pos) cudaFree(d_strm_pos);
         if (d_opstats) cudaFree(d_opstats);
         if (d_meta) cudaFree(d_meta);
         if (d_fade_out) cudaFree(d_fade_out);
@@ -886,9 +888,11 @@ static int run_wave(Engine* E, const long long* d_codes, int n_frames, int win_s
 // for a transposed convolution, sliding_window-1 rows of K/V for the attention -- in a halo that precedes row 0 of its
 // input buffer and was saved from the previous segment.  Output = the un-chunked decoder on the whole sequence.
 // --------------------------------------------------------------------------------------
+// The segment depends on the stream position only through the attention kernel, which reads it from device memory
+// (E->d_strm_pos, written by the caller before the segment): the same launch sequence serves every position, so the
+// live pieces of a stream (a few frames per call, ~280 small launches and copies) replay as one CUDA graph.
 static int stream_segment(Engine* E, const long long* d_codes, int n, float* out, cudaStream_t st) {
     const Cfg& c = E->cfg;
-    const long long pos0 = E->strm.pos;
     size_t hidx = 0;
     // the state buffer of the next layer in walking order (zeros = the causal zero padding of frame 0)
     auto halo_state = [&](size_t elems, float** ptr) -> int {
@@ -902,25 +906,24 @@ static int stream_segment(Engine* E, const long long* d_codes, int n, float* out
         *ptr = E->strm.halos[hidx++].first;
         return VOC_OK;
     };
-    auto cpy = [&](void* d, const void* sr, size_t bytes) -> int {
-        if (bytes) CK(cudaMemcpyAsync(d, sr, bytes, cudaMemcpyDeviceToDevice, st));
+    auto cpy2 = [&](void* d0, const void* s0, void* d1, const void* s1, size_t bytes) -> int {
+        if (bytes) CK(voc_launch_copy_pair(d0, s0, d1, s1, bytes, st));
         E->launches++;
         return VOC_OK;
     };
+    auto cpy = [&](void* d, const void* sr, size_t bytes) -> int { return cpy2(d, sr, nullptr, nullptr, bytes); };
     // operand tensors (two fp16 planes, or float32 on the CUDA-core path): rows [0, H) <- state; state <- rows [L, L + H)
     auto restore_op = [&](float* buf, const float* stt, int H, int C) -> int {
         const VocAct a = act(E, buf);
         const size_t n_el = (size_t)H * C;
         if (a.f) return cpy(a.f, stt, n_el * 4);
-        if (int r = cpy(a.hi, stt, n_el * 2)) return r;
-        return cpy(a.lo, reinterpret_cast<const __half*>(stt) + n_el, n_el * 2);
+        return cpy2(a.hi, stt, a.lo, reinterpret_cast<const __half*>(stt) + n_el, n_el * 2);
     };
     auto save_op = [&](float* buf, float* stt, int H, int C, int L) -> int {
         const VocAct a = act(E, buf);
         const size_t n_el = (size_t)H * C, off = (size_t)L * C;
         if (a.f) return cpy(stt, a.f + off, n_el * 4);
-        if (int r = cpy(stt, a.hi + off, n_el * 2)) return r;
-        return cpy(reinterpret_cast<__half*>(stt) + n_el, a.lo + off, n_el * 2);
+        return cpy2(stt, a.hi + off, reinterpret_cast<__half*>(stt) + n_el, a.lo + off, n_el * 2);
     };
 #define KLAUNCH(tag, flops, bytes, call) do { ProfScope _ps(E, st, tag, flops, bytes); CK(call); } while (0)
 #define GEMM(tag, p) do { if (int _r = gemm_ck(E, p, st, tag)) return _r; } while (0)
@@ -942,7 +945,6 @@ static int stream_segment(Engine* E, const long long* d_codes, int n, float* out
     if (c.pre_transformer) {
         const int rows = T, H = c.xf_hidden, A = c.attn_dim();
         const int Hq = std::max(c.sliding_window - 1, 0);
-        const int kvh = (int)std::min<long long>(Hq, pos0);            // rows of history that exist
         const double nb = 8.0 * rows * H;
         { TapGemmParams p = gp(E->xf_in, act(E, x), 0, rows, 0, rows, 1); setY(p, E->f_h); GEMM("xf.gemm", p); }
         for (int l = 0; l < c.xf_layers; ++l) {
@@ -952,9 +954,9 @@ static int stream_segment(Engine* E, const long long* d_codes, int n, float* out
             float* qkv_new = E->f_qkv + (size_t)Hq * 3 * A;          // this segment's rows follow the history rows
             { TapGemmParams p = gp(Ly.qkv, act(E, E->f_hn), 0, rows, 0, rows, 1); setY(p, qkv_new); GEMM("xf.gemm", p); }
             if (int r = cpy(E->f_qkv, stt, (size_t)Hq * 3 * A * 4)) return r;
-            KLAUNCH("xf.attn", 4.0 * c.xf_heads * (double)T * std::min(T + kvh, c.sliding_window) * c.xf_head_dim, 16.0 * rows * A,
-                    voc_launch_attention_stream(E->f_qkv + (size_t)(Hq - kvh) * 3 * A, act(E, E->f_att), T, c.xf_heads, c.xf_head_dim,
-                                                E->rope_cos, E->rope_sin, c.sliding_window, kvh, (int)pos0, st));
+            KLAUNCH("xf.attn", 4.0 * c.xf_heads * (double)T * std::min(T + Hq, c.sliding_window) * c.xf_head_dim, 16.0 * rows * A,
+                    voc_launch_attention_stream(E->f_qkv, act(E, E->f_att), T, c.xf_heads, c.xf_head_dim,
+                                                E->rope_cos, E->rope_sin, c.sliding_window, Hq, E->d_strm_pos, st));
             if (int r = cpy(stt, E->f_qkv + (size_t)T * 3 * A, (size_t)Hq * 3 * A * 4)) return r;
             { TapGemmParams p = gp(Ly.o, act(E, E->f_att), 0, rows, 0, rows, 1); p.scale = Ly.ls_attn; setR(p, E->f_h); setY(p, E->f_h); GEMM("xf.gemm", p); }
             KLAUNCH("xf.norm", 0.0, nb, voc_launch_rmsnorm(E->f_h, Ly.ln2, act(E, E->f_hn), rows, H, (float)c.rms_eps, st));
@@ -1081,7 +1083,6 @@ static int stream_segment(Engine* E, const long long* d_codes, int n, float* out
     }
 #undef KLAUNCH
 #undef GEMM
-    E->strm.pos += n;
     return VOC_OK;
 }
 
@@ -1096,6 +1097,55 @@ static int check_codes_flag(Engine* E, cudaStream_t st) {
     return VOC_OK;
 }
 
+// A launch sequence that recurs with the same buffers (the streaming client's one-window requests, the live pieces of
+// the carried-state decode) is launch-bound, so it is replayed as a CUDA graph: first sight of a key runs eagerly (lazy
+// set-up: kernel attributes, tensor maps, state buffers), second sight is captured, later ones replay.  `body` must
+// depend on nothing but the key.  The cache is bounded: the least recently used entry goes.
+typedef std::tuple<const void*, const void*, int, int, int, int, int, int> GraphKey;
+template <class F>
+static int graph_or_run(Engine* E, const GraphKey& key, cudaStream_t st, F&& body) {
+    auto git = E->graphs.find(key);
+    if (git != E->graphs.end() && git->second.exec) {
+        git->second.last_use = ++E->graph_clock;
+        CK(cudaGraphLaunch(git->second.exec, st));
+        E->launches += git->second.launches;
+        return VOC_OK;
+    }
+    if (git == E->graphs.end()) {
+        if (E->graphs.size() >= (size_t)E->graph_cache_max) {
+            auto lru = E->graphs.begin();
+            for (auto it = E->graphs.begin(); it != E->graphs.end(); ++it)
+                if (it->second.last_use < lru->second.last_use) lru = it;
+            if (lru->second.exec) cudaGraphExecDestroy(lru->second.exec);
+            E->graphs.erase(lru);
+        }
+        Engine::WaveGraph& N = E->graphs[key];
+        N.seen = 1; N.last_use = ++E->graph_clock;
+        return body();
+    }
+    Engine::WaveGraph& G = git->second;
+    G.last_use = ++E->graph_clock;
+    if (G.seen < 0) return body();                    // known not to be capturable
+    const long long l0 = E->launches;
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+    const int r = body();
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (r) { if (graph) cudaGraphDestroy(graph); return r; }
+    if (ce != cudaSuccess || !graph) {                // not capturable here: stay eager for this key
+        (void)cudaGetLastError();
+        G.seen = -1000000;
+        return body();
+    }
+    G.launches = E->launches - l0;
+    E->launches = l0;
+    CK(cudaGraphInstantiate(&G.exec, graph, 0));
+    cudaGraphDestroy(graph);
+    CK(cudaGraphLaunch(G.exec, st));
+    E->launches += G.launches;
+    return VOC_OK;
+}
+
 static int run_windows(Engine* E, const long long* d_codes, int n_frames, int win_step, int w0, int w1,
                        float* chunk_out, cudaStream_t st, int T = 0) {
     if (T <= 0) T = E->cfg.chunk_frames;
@@ -1104,62 +1154,15 @@ static int run_windows(Engine* E, const long long* d_codes, int n_frames, int wi
     for (int w = w0; w < w1; w += fw) {
         const int nw = std::min(fw, w1 - w);
         float* out = chunk_out + (long long)(w - w0) * Lc;
-        // Small waves are launch-bound, so a wave that recurs with the same buffers (the streaming client's
-        // one-window requests through the host entry points) is replayed as a CUDA graph: first sight runs
-        // eagerly (lazy set-up: kernel attributes, tensor maps), second sight is captured, later ones replay.
         const bool graphable = E->use_graphs && nw <= E->graph_max_wave && !E->profile && !E->debug && !E->opstats;
+        auto body = [&]() -> int { return run_wave(E, d_codes, n_frames, win_step, w, nw, out, st, nullptr, T); };
         if (!graphable) {
-            if (int r = run_wave(E, d_codes, n_frames, win_step, w, nw, out, st, nullptr, T)) return r;
+            if (int r = body()) return r;
             continue;
         }
-        const auto key = std::make_tuple((const void*)d_codes, (const void*)out, n_frames, win_step, w, nw,
-                                         E->gemm_mode, E->tc_flags * 128 + T);
-        auto git = E->graphs.find(key);
-        if (git != E->graphs.end() && git->second.exec) {
-            git->second.last_use = ++E->graph_clock;
-            CK(cudaGraphLaunch(git->second.exec, st));
-            E->launches += git->second.launches;
-            continue;
-        }
-        if (git == E->graphs.end()) {
-            // first sight runs eagerly (lazy set-up: kernel attributes, tensor maps); the key is remembered so
-            // that the second sight is captured.  The cache is bounded: the least recently used entry goes.
-            if (E->graphs.size() >= (size_t)E->graph_cache_max) {
-                auto lru = E->graphs.begin();
-                for (auto it = E->graphs.begin(); it != E->graphs.end(); ++it)
-                    if (it->second.last_use < lru->second.last_use) lru = it;
-                if (lru->second.exec) cudaGraphExecDestroy(lru->second.exec);
-                E->graphs.erase(lru);
-            }
-            Engine::WaveGraph& N = E->graphs[key];
-            N.seen = 1; N.last_use = ++E->graph_clock;
-            if (int r = run_wave(E, d_codes, n_frames, win_step, w, nw, out, st, nullptr, T)) return r;
-            continue;
-        }
-        Engine::WaveGraph& G = git->second;
-        G.last_use = ++E->graph_clock;
-        if (G.seen < 0) {                                 // known not to be capturable
-            if (int r = run_wave(E, d_codes, n_frames, win_step, w, nw, out, st, nullptr, T)) return r;
-            continue;
-        }
-        const long long l0 = E->launches;
-        CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
-        const int r = run_wave(E, d_codes, n_frames, win_step, w, nw, out, st, nullptr, T);
-        cudaGraph_t graph = nullptr;
-        const cudaError_t ce = cudaStreamEndCapture(st, &graph);
-        if (r) { if (graph) cudaGraphDestroy(graph); return r; }
-        if (ce != cudaSuccess || !graph) {           // not capturable here: stay eager for this key
-            (void)cudaGetLastError();
-            G.seen = -1000000;
-            if (int r2 = run_wave(E, d_codes, n_frames, win_step, w, nw, out, st, nullptr, T)) return r2;
-            continue;
-        }
-        G.launches = E->launches - l0;
-        E->launches = l0;
-        CK(cudaGraphInstantiate(&G.exec, graph, 0));
-        cudaGraphDestroy(graph);
-        CK(cudaGraphLaunch(G.exec, st));
-        E->launches += G.launches;
+        const GraphKey key = std::make_tuple((const void*)d_codes, (const void*)out, n_frames, win_step, w, nw,
+                                             E->gemm_mode, E->tc_flags * 128 + T);
+        if (int r = graph_or_run(E, key, st, body)) return r;
     }
     return VOC_OK;
 }
@@ -1796,9 +1799,20 @@ static int stream_host(void* h, const long long* codes, int n, float* of, short*
         E->d_pcm = nullptr; E->pcm_cap = 0;
         CK(cudaMalloc(&E->d_pcm, (size_t)std::min(n, seg_max) * spf * sizeof(short))); E->pcm_cap = (size_t)std::min(n, seg_max) * spf;
     }
+    if (!E->d_strm_pos) CK(cudaMalloc(&E->d_strm_pos, sizeof(int)));
     for (int f0 = 0; f0 < n; f0 += seg_max) {
         const int m = std::min(seg_max, n - f0);
-        if (int r = guarded(h, [&]() -> int { return stream_segment(E, E->d_codes + (size_t)f0 * 16, m, E->chunks.p, E->stream); })) return r;
+        const int pos_now = (int)E->strm.pos;             // (pageable source: staged by the call, safe to let go)
+        CK(cudaMemcpyAsync(E->d_strm_pos, &pos_now, sizeof(int), cudaMemcpyHostToDevice, E->stream));
+        const long long* seg_codes = E->d_codes + (size_t)f0 * 16;
+        auto body = [&]() -> int { return stream_segment(E, seg_codes, m, E->chunks.p, E->stream); };
+        // live pieces (a few frames per call) are launch-bound: replay them as graphs; long segments are not
+        const bool graphable = E->use_graphs && m <= E->graph_max_wave * c.chunk_frames && !E->strm.halos.empty() &&
+                               !E->profile && !E->debug && !E->opstats;
+        const GraphKey key = std::make_tuple((const void*)seg_codes, (const void*)E->chunks.p, m, -1, 0, 0, E->gemm_mode,
+                                             E->tc_flags * 128);
+        if (int r = guarded(h, [&]() -> int { return graphable ? graph_or_run(E, key, E->stream, body) : body(); })) return r;
+        E->strm.pos += m;
         const size_t cnt = (size_t)m * spf;
         if (of) CK(cudaMemcpyAsync(of + (size_t)f0 * spf, E->chunks.p, cnt * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
         if (oi) {

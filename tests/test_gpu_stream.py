@@ -91,12 +91,14 @@ def test_production_architecture_two_pieces(pkg, backend):
 
 
 def test_production_architecture_live_pieces(pkg, backend):
-    """The live-streaming case (the talker emits 12.5 frames/s): the default architecture decoded in pieces of 1, 4, 3,
-    16, 1 and 7 frames -- block 0 then sees 32-row inputs, the fused residual units a few tiles, every layer its halo from
-    the previous call -- against the oracle run once on all 32 frames."""
+    """The live-streaming case (the talker emits 12.5 frames/s): the default architecture decoded in pieces of 1, 4, 1, 3,
+    1, 16, 1, 4 and 1 frames -- block 0 then sees 32-row inputs, the fused residual units a few tiles, every layer its
+    halo from the previous call -- against the oracle run once on all 32 frames.  A piece length that recurs runs eagerly
+    the first time, is captured as a CUDA graph the second and replayed from the third on (the position reaches the
+    attention kernel through device memory), so the one-frame pieces cover all three."""
     cfg = pkg.VocoderConfig(transconv_trim="right")
     w = pkg.init_weights(cfg, 0)
-    pieces = [1, 4, 3, 16, 1, 7]
+    pieces = [1, 4, 1, 3, 1, 16, 1, 4, 1]
     n = sum(pieces)
     codes = _codes(cfg, n, 13)
     ref, _ = VO.forward(codes[None], VO.Weights(w), cfg)
@@ -110,8 +112,15 @@ def test_production_architecture_live_pieces(pkg, backend):
         at += k
     got = np.concatenate(out)
     assert got.shape == ref.shape == (n * 1920,)
-    _check("production, pieces 1 + 4 + 3 + 16 + 1 + 7", ref, got)
+    _check("production, pieces 1 + 4 + 1 + 3 + 1 + 16 + 1 + 4 + 1", ref, got)
     assert voc.simt_launches == 0
+    # the same stream again: every piece length has been seen, so this pass is graph replays and captures; same bits
+    voc.stream_reset()
+    again, at = [], 0
+    for k in pieces:
+        again.append(voc.stream_decode(codes[at:at + k]))
+        at += k
+    assert np.array_equal(got, np.concatenate(again))
     voc.close()
 
 
