@@ -153,8 +153,10 @@ long long   voc_simt_launches(void* h);
  *            "simt" is the all-float32 CUDA-core path (the on-device cross-check).
  *          "tc_flags" = experiment switches (bit 0 no tap reuse, bit 1 / 2 force 64- / 32-wide K
  *            chunks, bit 3 run-time epilogue only, bit 4 no double-length head segments, bit 7 no
- *            cta_group::2 pairs, bits 8.. = MMAs accumulated in the tensor core per round-to-nearest
- *            flush, default 24)
+ *            cta_group::2 pairs, bit 8 / bit 9 always the widest / the narrowest column tile of a layer's
+ *            family -- default: chosen per launch from the number of tiles, bit-identical results either
+ *            way --, bits 16.. = MMAs accumulated in the tensor core per round-to-nearest flush, default 24)
+ *          "operand_stats" = "0" | "1": see voc_operand_report
  *          "fuse_ru" = "1" | "0": residual units of the blocks with C <= 192 as ONE kernel (conv7 -> Snake ->
  *            conv1 -> + residual, the intermediate operand in shared memory) or as two tap-GEMM launches; the
  *            results are bit-identical
