@@ -2026,8 +2026,28 @@ int voc_test_tapgemm(int device, int mode, int tc_flags, int B, int a_rows, int 
     const size_t na = ((size_t)B * a_rows * K + 63) / 64 * 64, no = ((size_t)B * M * N + 63) / 64 * 64;
     float *dA = nullptr, *dY = nullptr, *dS = nullptr;
     CK(cudaMalloc(&dA, na * 4)); E->owned.push_back(dA); E->cap[dA] = na;
-    CK(cudaMalloc(&dY, no * 4)); E->owned.push_back(dY);
-    CK(cudaMalloc(&dS, no * 4)); E->owned.push_back(dS); E->cap[dS] = no;
+    // Both output buffers are filled with a byte pattern and sit between guard bands of it; after the launches every
+    // byte the layer does not own -- the bands, the padding behind the float32 output and behind each operand plane --
+    // must still hold the pattern (compute-sanitizer is not available on the pool this library is developed on).
+    const size_t G = 16384;                                  // guard floats on each side
+    auto guarded_alloc = [&](float** q, size_t n) -> int {
+        float* raw = nullptr;
+        CK(cudaMalloc(&raw, (n + 2 * G) * 4)); E->owned.push_back(raw);
+        CK(cudaMemsetAsync(raw, 0xA5, (n + 2 * G) * 4, E->stream));
+        *q = raw + G;
+        return VOC_OK;
+    };
+    // [lo, hi) in bytes relative to q must be untouched
+    auto untouched = [&](const float* q, long long lo, long long hi, const char* what) -> int {
+        if (hi <= lo) return VOC_OK;
+        std::vector<unsigned char> g((size_t)(hi - lo));
+        CK(cudaMemcpy(g.data(), reinterpret_cast<const unsigned char*>(q) + lo, g.size(), cudaMemcpyDeviceToHost));
+        for (unsigned char c : g) if (c != 0xA5) return fail(E, VOC_E_CUDA, std::string("guard bytes of ") + what + " overwritten: out-of-bounds store");
+        return VOC_OK;
+    };
+    if (int r = guarded_alloc(&dY, no)) return r;
+    if (int r = guarded_alloc(&dS, no)) return r;
+    E->cap[dS] = no;
     if (mode == 0) {
         CK(cudaMemcpyAsync(dA, A, (size_t)B * a_rows * K * 4, cudaMemcpyHostToDevice, E->stream));
     } else {
@@ -2059,6 +2079,19 @@ int voc_test_tapgemm(int device, int mode, int tc_flags, int B, int a_rows, int 
         float t = 0.f; CK(cudaEventElapsedTime(&t, e0, e1));
         *ms = t / iters;
         cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    {
+        const long long nb = (long long)B * M * N, gb = (long long)G * 4, ob = (long long)no * 4;
+        const bool y_direct = Y && !(d_R && getenv("VOC_TEST_INPLACE"));
+        if (int r = untouched(dY, -gb, y_direct ? 0 : ob, "Y (front)")) return r;
+        if (int r = untouched(dY, y_direct ? nb * 4 : ob, ob + gb, "Y (back)")) return r;
+        if (int r = untouched(dS, -gb, S ? 0 : ob, "S (front)")) return r;
+        if (S && mode != 0) {                                   // two fp16 planes: [0, 2 nb) and [2 no, 2 no + 2 nb)
+            if (int r = untouched(dS, nb * 2, (long long)no * 2, "S (behind the hi plane)")) return r;
+            if (int r = untouched(dS, (long long)no * 2 + nb * 2, ob + gb, "S (behind the lo plane)")) return r;
+        } else {
+            if (int r = untouched(dS, S ? nb * 4 : ob, ob + gb, "S (back)")) return r;
+        }
     }
     if (Y) CK(cudaMemcpy(Y, dY, (size_t)B * M * N * 4, cudaMemcpyDeviceToHost));
     if (S) {

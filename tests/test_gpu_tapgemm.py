@@ -7,6 +7,9 @@ offset 1 under transconv_trim = "both"), Linear / 1x1 conv, with the fused epilo
 Tolerance: the tensor path multiplies split-fp16 operands (~22 mantissa bits) and accumulates in
 FP32, so a dot product of O(1) terms is good to a few 1e-6 relative to the output scale.
 
+Every call goes through voc_test_tapgemm, whose output buffers sit between guard bands of a byte pattern: a store outside
+the rows / columns / planes the layer owns fails the call (the stand-in for compute-sanitizer, which is closed on the pool).
+
 tc_flags: 0 = default (tap reuse through row-shifted descriptors, cta_group::2 pairs where the launcher
 selects them; column tile chosen per launch within the layer's family), 1 = per-tap aligned loads, 8 = run-time epilogue
 only, 128 = single-CTA kernel only, 256 / 512 = always the widest / the narrowest column tile of the family."""
