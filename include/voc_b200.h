@@ -186,6 +186,13 @@ long long   voc_operand_report(void* h, char* buf, long long cap);
  * [windows][time][channels]); returns the element count or a negative error.               */
 long long   voc_debug_stage(void* h, const char* name, float* out, long long cap);
 
+/* How the tcgen05 kernel would tile a dense layer (N output channels, K input channels, ntaps taps, M time steps per
+ * window) for a batch of B windows on `sms` SMs -- host arithmetic only, callable without a GPU.  out5 = {column tile,
+ * K chunk, 1 if cta_group::2 pairs, 1 if the 3-pass form runs on a 96-column tile, 1 if the layer's MMA form is the
+ * 3-pass one (else concatenated)}.  The form and the pairing never depend on B (they fix the rounding); the column
+ * tile may (narrower tiles of one form are bit-identical and fill the machine at small batches).               */
+int voc_tc_plan(int N, int K, int ntaps, int M, int B, int sms, int tc_flags, int* out5);
+
 /* Kernel-level test / micro-benchmark hook: one "tap GEMM" (the contraction every dense layer of
  * the graph maps onto: causal dilated Conv1d, phase-decomposed ConvTranspose1d, Linear) on caller
  * data, through the FP32 CUDA-core kernel (mode 0), the CUDA-core kernel on split-fp16 operands

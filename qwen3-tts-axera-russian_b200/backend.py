@@ -63,6 +63,7 @@ SIGNATURES = {
     "voc_stream": (C.c_void_p, [C.c_void_p]),
     "voc_profile_report": (C.c_longlong, [C.c_void_p, C.c_void_p, C.c_longlong]),
     "voc_operand_report": (C.c_longlong, [C.c_void_p, C.c_void_p, C.c_longlong]),
+    "voc_tc_plan": (C.c_int, [C.c_int] * 7 + [C.c_void_p]),
     "voc_debug_stage": (C.c_longlong, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_longlong]),
     "voc_test_tapgemm": (C.c_int, [C.c_int] * 10 + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 5
                          + [C.c_int, C.c_void_p]),
@@ -121,6 +122,16 @@ def fade_tables(ov: int):
     if rc:
         raise VocoderError(rc, "voc_fade_tables: bad argument")
     return fo, fi
+
+
+def tc_plan(N: int, K: int, ntaps: int, M: int, B: int, sms: int = 148, tc_flags: int = 0) -> dict:
+    """The tcgen05 kernel's tile plan for a dense layer and a batch (host arithmetic; no GPU needed)."""
+    lib = load_library()
+    out = (C.c_int * 5)()
+    rc = lib.voc_tc_plan(N, K, ntaps, M, B, sms, tc_flags, out)
+    if rc:
+        raise ValueError(f"no tensor-core tile for N = {N}")
+    return {"BN": out[0], "BK": out[1], "pair": bool(out[2]), "p3": bool(out[3]), "three_pass": bool(out[4])}
 
 
 def test_tapgemm(mode: int, A: np.ndarray, W: np.ndarray, tap_off, M: int, a_row0: int = 0, bias=None,

@@ -749,37 +749,41 @@ void voc_tc_clear_cache() {
     g_maps.clear();
 }
 
-cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int num_sms, int flags) {
-    if (!voc_tc_eligible(p)) return cudaErrorNotSupported;
-    if (p.M <= 0 || p.B <= 0) return cudaSuccess;
-    const int BN0 = pick_bn(p.N);                 // the family's widest column tile: fixes the MMA form (3-pass / concatenated)
+// The tile plan of one launch: pure host arithmetic (no device needed; tests/test_cabi.py checks the policy through
+// voc_tc_plan).  What may depend on the batch and what may not:
+//   * the MMA form (3-pass / concatenated) and cta_group::2 pairing are properties of the LAYER (N, K, taps, the
+//     per-window length M): the two forms round differently, so a batch must never change them;
+//   * the column tile WITHIN the family may follow the batch.  A narrower tile of the same form computes every output
+//     column with the same passes, k-step order and segment schedule -- the same bits -- so when the widest tile
+//     leaves SMs idle or strands a nearly empty last round (one window: 64 CTAs at C = 768, 160 tiles on 148 SMs at
+//     C = 384, 4 CTAs for the transformer's 512-column projections) a narrower one spreads the same k-steps over
+//     more SMs and each MMA is shorter.  Cost model: the issuing warp's cycles per k-step, one MMA =
+//     max(44 + N/8, N/2) (tools/mma_issue_bench.cu), times k-steps per tile times rounds, plus the exposed final
+//     epilogue of the last tile (~68 cycles per column, profiles/r1_mma_microbench.txt section 5); ties keep the widest.
+TcTilePlan voc_tc_plan_tile(int N, int K, int ntaps, int M, int B, int sms, int flags) {
+    TcTilePlan t{};
+    const int BN0 = pick_bn(N);                   // the family's widest column tile: fixes the MMA form
+    if (!BN0 || K < 1 || ntaps < 1 || M < 1 || B < 1) return t;
+    if (sms <= 1) sms = 148;
     // One SS-mode MMA (M 128, K 16) costs ~64 + N/2 cycles from SWIZZLE_128B operands and ~100 + N/2
     // from SWIZZLE_64B ones (tools/mma_rate.py), so 64-wide K chunks are used whenever K > 32.
-    int BK = p.K > 32 ? 64 : 32;
+    int BK = K > 32 ? 64 : 32;
     if (flags & VOC_TC_BK32) BK = 32;
     if (flags & VOC_TC_BK64) BK = 64;
-    const int sms = num_sms > 0 ? num_sms : 148;
-    // cta_group::2 pairs are a property of the layer shape (see below), never of the batch
-    const bool two = !(flags & VOC_TC_NO_PAIR) && BK == 64 && p.M > BM && (BN0 == 192 || BN0 == 96) &&
-                     ((flags & VOC_TC_FORCE_PAIR) || (BN0 == 192 && (long long)p.ntaps * p.K >= 768) ||
-                      (BN0 == 96 && (long long)p.ntaps * p.K >= 384));
-    // Column tile WITHIN the family.  A narrower tile of the same form computes every output column with the same
-    // passes, k-step order and segment schedule -- the same bits -- so this choice, unlike the form, may follow the
-    // batch: when the widest tile leaves SMs idle or strands a nearly empty last round (one window: 64 CTAs at
-    // C = 768, 160 tiles on 148 SMs at C = 384, 4 CTAs for the transformer's 512-column projections), a narrower one
-    // spreads the same k-steps over more SMs and each MMA is shorter.  Cost model: the issuing warp's cycles per
-    // k-step, one MMA = max(44 + N/8, N/2) (tools/mma_issue_bench.cu), times k-steps per tile times rounds, plus the
-    // exposed final epilogue of the last tile (~68 cycles per column, profiles/r1_mma_microbench.txt section 5).
+    // cta_group::2 pairs: measured per layer kind (see voc_launch_tapgemm_tc); M is the per-window length
+    const bool two = !(flags & VOC_TC_NO_PAIR) && BK == 64 && M > BM && (BN0 == 192 || BN0 == 96) &&
+                     ((flags & VOC_TC_FORCE_PAIR) || (BN0 == 192 && (long long)ntaps * K >= 768) ||
+                      (BN0 == 96 && (long long)ntaps * K >= 384));
     int BN = BN0;
     bool p3 = false;                              // 3-pass form on a 96-column tile
     if (!(flags & VOC_TC_FIXED_TILE) && BK == 64) {
-        const int m_tiles0 = (p.M + BM - 1) / BM;
-        const long long mt = (long long)(two ? (m_tiles0 + 1) / 2 : m_tiles0) * p.B;
+        const int m_tiles0 = (M + BM - 1) / BM;
+        const long long mt = (long long)(two ? (m_tiles0 + 1) / 2 : m_tiles0) * B;
         const long long walkers = two ? sms / 2 : sms;
-        const long long ksteps = (long long)((p.K + 15) / 16) * p.ntaps;
+        const long long ksteps = (long long)((K + 15) / 16) * ntaps;
         auto mma = [](int n) { return std::max(44 + n / 8, n / 2); };
         auto est = [&](int bn, bool cat) {
-            const long long tiles = mt * (p.N / bn), rounds = (tiles + walkers - 1) / walkers;
+            const long long tiles = mt * (N / bn), rounds = (tiles + walkers - 1) / walkers;
             return rounds * ksteps * (cat ? mma(2 * bn) + mma(bn) : 3 * mma(bn)) + 68LL * bn;
         };
         if (BN0 == 192) {
@@ -792,6 +796,19 @@ cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int n
             }
         }
     }
+    t.BN = BN; t.BK = BK; t.pair = two; t.p3 = p3;
+    t.three_pass = BN0 == 192;
+    return t;
+}
+
+cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int num_sms, int flags) {
+    if (!voc_tc_eligible(p)) return cudaErrorNotSupported;
+    if (p.M <= 0 || p.B <= 0) return cudaSuccess;
+    const int sms = num_sms > 0 ? num_sms : 148;
+    const TcTilePlan tp = voc_tc_plan_tile(p.N, p.K, p.ntaps, p.M, p.B, sms, flags);
+    if (!tp.BN) return cudaErrorNotSupported;
+    const int BN = tp.BN, BK = tp.BK;
+    const bool two = tp.pair, p3 = tp.p3;
     const bool cat = BN <= 128 && !p3;            // the kernel's CAT
 
     TcArgs a;

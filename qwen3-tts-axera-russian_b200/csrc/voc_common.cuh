@@ -114,6 +114,10 @@ bool voc_tc_eligible(const TapGemmParams& p);
 bool voc_tc_get_map(const void* base, long long d0, long long d1, long long d2, long long s1, long long s2, long long s3,
                     int bk, int box_rows, int box_planes, CUtensorMap_st* out);
 cudaError_t voc_launch_tapgemm_tc(const TapGemmParams& p, cudaStream_t st, int num_sms, int flags);
+// the tile plan voc_launch_tapgemm_tc would use (pure host arithmetic): column tile, K chunk, cta_group::2 pairing, the
+// 3-pass form on a 96-column tile, and the layer's MMA form (3-pass or concatenated); BN = 0: N is not a multiple of 32
+struct TcTilePlan { int BN, BK; bool pair, p3, three_pass; };
+TcTilePlan voc_tc_plan_tile(int N, int K, int ntaps, int M, int B, int sms, int flags);
 void voc_tc_clear_cache();
 
 // ------------------------------------------------------------------------------------

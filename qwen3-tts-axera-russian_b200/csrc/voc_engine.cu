@@ -1987,6 +1987,15 @@ long long voc_debug_stage(void* h, const char* name, float* out, long long cap) 
 }
 
 
+// The tile plan of a dense layer for a given batch (host arithmetic only: callable without a GPU).
+int voc_tc_plan(int N, int K, int ntaps, int M, int B, int sms, int tc_flags, int* out5) {
+    if (!out5) return VOC_E_INVALID;
+    const TcTilePlan t = voc_tc_plan_tile(N, K, ntaps, M, B, sms, tc_flags);
+    if (!t.BN) return VOC_E_INVALID;
+    out5[0] = t.BN; out5[1] = t.BK; out5[2] = t.pair ? 1 : 0; out5[3] = t.p3 ? 1 : 0; out5[4] = t.three_pass ? 1 : 0;
+    return VOC_OK;
+}
+
 // ---- kernel-level hook: one tap-GEMM on caller data, through either kernel family -------------
 // mode 0 = CUDA cores, float32 operands; 1 = CUDA cores, split-fp16 operands; 2 = tcgen05.
 // A [B][a_rows][K], W [ntaps*K][N] (CUDA-core layout), R / Y / S [B][M][N]; any of bias, scale, R,

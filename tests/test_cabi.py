@@ -104,3 +104,47 @@ def test_native_server_is_built_and_needs_a_gpu(tmp_path, pkg, backend):
         r = subprocess.run([exe, "--model", str(m), "--socket", str(tmp_path / "s.sock")], capture_output=True, text=True,
                            timeout=60)
         assert r.returncode == 1 and "no usable CUDA device" in (r.stderr + r.stdout)
+
+
+# ---- the tcgen05 kernel's tile plan (host arithmetic: runs without a GPU) -------------------------------------
+# layer table of the production decoder: (name, N, K, taps, M per window)
+_LAYERS = [
+    ("xf.qkv", 3072, 512, 1, 64), ("xf.o", 512, 1024, 1, 64), ("xf.gate_up", 2048, 512, 1, 64), ("xf.down", 512, 1024, 1, 64),
+    ("up.pw2", 1024, 4096, 1, 256), ("conv_in", 1536, 1024, 7, 256),
+    ("dec0.convt", 6144, 1536, 2, 256), ("dec0.conv7", 768, 768, 7, 2048), ("dec0.conv1", 768, 768, 1, 2048),
+    ("dec1.convt", 1920, 768, 2, 2048), ("dec1.conv7", 384, 384, 7, 10240), ("dec1.conv1", 384, 384, 1, 10240),
+    ("dec2.convt", 768, 384, 2, 10240), ("dec3.convt", 288, 192, 2, 40960), ("dec3.conv7", 96, 96, 7, 122880),
+]
+
+
+def test_tile_plan_form_and_pairing_never_depend_on_the_batch(backend):
+    """The MMA form (3-pass / concatenated) and cta_group::2 pairing fix the rounding of a layer, so the batch must not
+    change them; only the column tile inside the form's family may follow it (tc_gemm.cu: voc_tc_plan_tile)."""
+    for name, N, K, taps, M in _LAYERS:
+        ref = backend.tc_plan(N, K, taps, M, 1)
+        for B in (1, 2, 3, 4, 6, 8, 16, 20, 32, 157, 256):
+            for flags in (0, 256, 512):
+                t = backend.tc_plan(N, K, taps, M, B, tc_flags=flags)
+                assert (t["three_pass"], t["pair"], t["BK"]) == (ref["three_pass"], ref["pair"], ref["BK"]), (name, B, flags, t, ref)
+                family = (192, 96) if t["three_pass"] else (128, 64, 32) if N % 128 == 0 else (96,) if N % 96 == 0 else (64, 32)
+                assert t["BN"] in family and N % t["BN"] == 0, (name, B, flags, t)
+                assert t["p3"] == (t["three_pass"] and t["BN"] == 96), (name, B, flags, t)
+
+
+def test_tile_plan_widest_tile_for_large_batches_narrower_for_one_window(backend):
+    widest = {name: backend.tc_plan(N, K, taps, M, 1, tc_flags=256)["BN"] for name, N, K, taps, M in _LAYERS}
+    for name, N, K, taps, M in _LAYERS:
+        assert backend.tc_plan(N, K, taps, M, 256)["BN"] == widest[name], name       # the 256-window step is unchanged
+        assert backend.tc_plan(N, K, taps, M, 1, tc_flags=512)["BN"] <= widest[name]
+    one = {name: backend.tc_plan(N, K, taps, M, 1) for name, N, K, taps, M in _LAYERS}
+    # one window: 64 CTAs at C = 768 and 160 tiles on 148 SMs at C = 384 become 96-column 3-pass tiles, the
+    # transformer's 512-column projections (4 CTAs with a 64-k-step chain each) 32-column concatenated tiles
+    assert one["dec0.conv7"] == {"BN": 96, "BK": 64, "pair": True, "p3": True, "three_pass": True}
+    assert one["dec1.conv7"]["BN"] == 96 and one["dec1.conv7"]["pair"]
+    assert one["conv_in"]["BN"] == 96 and one["xf.qkv"]["BN"] == 96 and not one["xf.qkv"]["pair"]
+    assert one["xf.o"]["BN"] == 32 and one["xf.down"]["BN"] == 32 and not one["xf.o"]["three_pass"]
+    # layers whose family has one member keep it
+    assert one["dec3.conv7"] == {"BN": 96, "BK": 64, "pair": True, "p3": False, "three_pass": False}
+    assert one["dec3.convt"]["BN"] == 96 and not one["dec3.convt"]["p3"]
+    with pytest.raises(ValueError):
+        backend.tc_plan(100, 64, 1, 128, 1)                                            # N not a multiple of 32
