@@ -193,6 +193,12 @@ long long   voc_debug_stage(void* h, const char* name, float* out, long long cap
  * tile may (narrower tiles of one form are bit-identical and fill the machine at small batches).               */
 int voc_tc_plan(int N, int K, int ntaps, int M, int B, int sms, int tc_flags, int* out5);
 
+/* The shared-memory plan of the fused residual-unit kernel (C = 96 or 192 channels, kernel size, dilation): out5 = {rows
+ * of the halo tile one TMA box loads, halo stages, weight stages, 1 if the intermediate operand T overlays the halo ring
+ * (the order of work is then conv7, T, 1x1 per tile; else conv7 of the next tile runs under the hand-over), dynamic
+ * shared-memory bytes}.  Host arithmetic only; VOC_E_INVALID for a shape the fused kernel does not take.            */
+int voc_ru_plan(int C, int ksz, int dil, int* out5);
+
 /* Kernel-level test / micro-benchmark hook: one "tap GEMM" (the contraction every dense layer of
  * the graph maps onto: causal dilated Conv1d, phase-decomposed ConvTranspose1d, Linear) on caller
  * data, through the FP32 CUDA-core kernel (mode 0), the CUDA-core kernel on split-fp16 operands

@@ -64,6 +64,7 @@ SIGNATURES = {
     "voc_profile_report": (C.c_longlong, [C.c_void_p, C.c_void_p, C.c_longlong]),
     "voc_operand_report": (C.c_longlong, [C.c_void_p, C.c_void_p, C.c_longlong]),
     "voc_tc_plan": (C.c_int, [C.c_int] * 7 + [C.c_void_p]),
+    "voc_ru_plan": (C.c_int, [C.c_int] * 3 + [C.c_void_p]),
     "voc_debug_stage": (C.c_longlong, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_longlong]),
     "voc_test_tapgemm": (C.c_int, [C.c_int] * 10 + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 5
                          + [C.c_int, C.c_void_p]),
@@ -132,6 +133,15 @@ def tc_plan(N: int, K: int, ntaps: int, M: int, B: int, sms: int = 148, tc_flags
     if rc:
         raise ValueError(f"no tensor-core tile for N = {N}")
     return {"BN": out[0], "BK": out[1], "pair": bool(out[2]), "p3": bool(out[3]), "three_pass": bool(out[4])}
+
+
+def ru_plan(Cc: int, ksz: int, dil: int) -> dict:
+    """Shared-memory plan of the fused residual-unit kernel (host arithmetic; no GPU needed)."""
+    lib = load_library()
+    out = (C.c_int * 5)()
+    if lib.voc_ru_plan(Cc, ksz, dil, out):
+        raise ValueError(f"the fused residual unit does not take C = {Cc}, k = {ksz}, dilation {dil}")
+    return {"box_rows": out[0], "halo_stages": out[1], "weight_stages": out[2], "alias": bool(out[3]), "smem": out[4]}
 
 
 def test_tapgemm(mode: int, A: np.ndarray, W: np.ndarray, tap_off, M: int, a_row0: int = 0, bias=None,

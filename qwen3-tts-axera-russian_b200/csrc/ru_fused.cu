@@ -808,6 +808,16 @@ extern "C" int voc_ru_prof_read(unsigned long long* out, int n, int reset) {
 }
 #endif
 
+// the shared-memory plan of a unit (host arithmetic; exported as voc_ru_plan for the CPU tests)
+bool voc_ru_fused_plan(int C, int ksz, int dil, int* out5) {
+    RuFusedParams p{};
+    p.C = C; p.ksz = ksz; p.dil = dil;
+    FuPlan pl;
+    if ((C != 96 && C != 192) || ksz < 2 || ksz > VOC_MAX_TAPS || dil < 1 || !plan_fused(p, pl)) return false;
+    out5[0] = pl.box_rows; out5[1] = pl.SA; out5[2] = pl.SB; out5[3] = pl.alias ? 1 : 0; out5[4] = (int)pl.smem;
+    return true;
+}
+
 bool voc_ru_fused_eligible(const RuFusedParams& p) {
     if (p.C != 96 && p.C != 192) return false;
     if (p.ksz < 2 || p.ksz > VOC_MAX_TAPS || p.dil < 1) return false;

@@ -140,6 +140,8 @@ struct RuFusedParams {
     const float* head_w;  float* head_part;  int head_taps;
 };
 bool voc_ru_fused_eligible(const RuFusedParams& p);
+// shared-memory plan of the fused unit: {halo box rows, halo stages, weight stages, T overlays the halo ring, bytes}
+bool voc_ru_fused_plan(int C, int ksz, int dil, int* out5);
 cudaError_t voc_launch_ru_fused(const RuFusedParams& p, cudaStream_t st, int num_sms, int flags);
 // flags: bit 0 no tap reuse, bit 1 / bit 2 force 64- / 32-wide K chunks, bit 3 run-time (generic) epilogue only,
 // bit 4 no double-length head segments, bit 6 / bit 7 always / never cta_group::2 pairs, bit 8 / bit 9 always the widest /

@@ -1996,6 +1996,12 @@ int voc_tc_plan(int N, int K, int ntaps, int M, int B, int sms, int tc_flags, in
     return VOC_OK;
 }
 
+// The shared-memory plan of the fused residual unit for a channel count, kernel size and dilation (host arithmetic).
+int voc_ru_plan(int C, int ksz, int dil, int* out5) {
+    if (!out5) return VOC_E_INVALID;
+    return voc_ru_fused_plan(C, ksz, dil, out5) ? VOC_OK : VOC_E_INVALID;
+}
+
 // ---- kernel-level hook: one tap-GEMM on caller data, through either kernel family -------------
 // mode 0 = CUDA cores, float32 operands; 1 = CUDA cores, split-fp16 operands; 2 = tcgen05.
 // A [B][a_rows][K], W [ntaps*K][N] (CUDA-core layout), R / Y / S [B][M][N]; any of bias, scale, R,

@@ -148,3 +148,21 @@ def test_tile_plan_widest_tile_for_large_batches_narrower_for_one_window(backend
     assert one["dec3.convt"]["BN"] == 96 and not one["dec3.convt"]["p3"]
     with pytest.raises(ValueError):
         backend.tc_plan(100, 64, 1, 128, 1)                                            # N not a multiple of 32
+
+
+def test_fused_unit_shared_memory_plan(backend):
+    """ru_fused.cu's plan at the production shapes: everything fits the 227 KB opt-in, the halo tile is one TMA box, C = 96
+    keeps T beside a double-buffered halo ring with >= 4 weight stages (pipelined order of work), C = 192 must overlay T
+    on the ring, and a dilation whose halo tile exceeds one box is refused."""
+    for Cc in (96, 192):
+        for dil in (1, 3, 9):
+            p = backend.ru_plan(Cc, 7, dil)
+            assert p["smem"] <= 232448 - 5120 and p["halo_stages"] == 2 and p["weight_stages"] >= 2, (Cc, dil, p)
+            assert p["box_rows"] >= 128 + 6 * dil and p["box_rows"] % 8 == 0 and p["box_rows"] <= 256
+            assert p["alias"] == (Cc == 192), (Cc, dil, p)
+            if Cc == 96:
+                assert p["weight_stages"] >= 4, (dil, p)
+    with pytest.raises(ValueError):
+        backend.ru_plan(96, 7, 27)                      # 128 + 162 rows: more than one 256-row box
+    with pytest.raises(ValueError):
+        backend.ru_plan(384, 7, 1)                      # a tile's T rows would span two column tiles (blocks 0-1)
