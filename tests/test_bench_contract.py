@@ -22,7 +22,7 @@ def _last_json_line(text):
 
 
 def _recorded_gpu_line():
-    paths = sorted(glob.glob(os.path.join(ROOT, "profiles", "r2_bench_v*_final.json")), key=os.path.getmtime)
+    paths = sorted(glob.glob(os.path.join(ROOT, "profiles", "r2_bench_v*_final.json")))      # by name: v13 after v10
     if not paths:
         pytest.skip("no recorded B200 bench line under profiles/")
     return _last_json_line(open(paths[-1]).read())
