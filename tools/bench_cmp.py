@@ -1,3 +1,5 @@
+"""Per-layer step times of two bench.py JSON lines side by side (A/B runs on one box):
+    python tools/bench_cmp.py a.json b.json"""
 import json,sys
 def load(p):
     return json.loads([l for l in open(p) if l.startswith("{")][-1])
